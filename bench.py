@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- probit-ELBO fwd+bwd throughput (label-samples/s) on B200, BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload eurlex] [--z Z] [--impl reference]
+
+One "step" = one pass of the hot path over one batch: draw the (S,B,Z) noise (Philox, on device), the
+forward of compute_loss (mpvae.py:145-210) and its full backward to logits / R / mu / logvar; at N > 1 every
+rank owns B rows (weak scaling) and the step ends with the NCCL all-reduce of g_R (the path's one exchange).
+`value` times that with the inputs resident in HBM; `e2e` times the same call through the public
+`mpvae_b200.compute_loss` API starting from pinned HOST buffers (H2D of the step's inputs and D2H of the loss
+inside the timed region).  Prints ONE JSON line (rank 0).
+
+`--impl reference` times the reference's algorithm on the host cores instead (the oracle port of
+/root/reference/mpvae.py -- the reference itself is Python and does not travel to the GPU box), on a bounded
+row sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "probit-ELBO fwd+bwd label-samples/s"
+UNIT = "label-samples/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="eurlex", help="one of mpvae_b200.synth.SHAPES")
+    ap.add_argument("--z", type=int, default=None, help="rank of R (default: the workload's, z_dim = label_dim)")
+    ap.add_argument("--batch", type=int, default=None, help="rows per GPU (default: the workload's)")
+    ap.add_argument("--cpu-rows", type=int, default=None, help="rows of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engine", default="auto", choices=["auto", "fma", "tensor"])
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        d["_source"] = "measured"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0,
+            "_source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(a):
+    from mpvae_b200 import synth
+    sh = synth.SHAPES[a.workload]
+    Z = a.z if a.z is not None else sh.z_dim
+    B = a.batch if a.batch is not None else sh.batch
+    return sh, sh.label_dim, Z, B, sh.n_sample
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_step(L, Z, S, rows, seed=0):
+    """One fwd(+bwd) of the reference algorithm (oracle port, O(L^2) pairwise ranking loss, all host threads)
+    on `rows` rows of the workload.  Returns seconds."""
+    import torch
+    from mpvae_b200 import synth
+    from oracle import probit_elbo_oracle as orc
+    inp = synth.loss_inputs(L, Z, rows, S, seed=seed + 1, label_rate=min(0.1, 20.0 / L))
+    t = {k: torch.from_numpy(v) for k, v in inp.items()}
+    noise = t.pop("noise")
+    t0 = time.perf_counter()
+    orc.probit_elbo_with_grads(t, noise, 0.5, 10.0)
+    return time.perf_counter() - t0
+
+
+def cpu_rows_for(L, Z, S, want=None):
+    if want:
+        return want
+    # pairwise ranking loss materialises ~6 (S,rows,L,L) fp32 tensors (fwd+bwd): keep under ~24 GB and ~10-30 s
+    per_row = 6 * S * L * L * 4
+    return max(1, min(128, int(24e9 // per_row)))
+
+
+def run_reference(a):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sh, L, Z, B, S = workload(a)
+    torch.set_num_threads(os.cpu_count())
+    rows = cpu_rows_for(L, Z, S, a.cpu_rows)
+    steps = max(1, a.steps)
+    # bound the whole run to a few minutes: probe one step, then cap the step count
+    t_probe = cpu_reference_step(L, Z, S, rows)
+    budget = 150.0
+    steps = max(1, min(steps, int(budget // max(t_probe, 1e-3))))
+    warm = max(0, min(a.warmup, 1 if t_probe > 5 else 3))
+    for i in range(warm):
+        cpu_reference_step(L, Z, S, rows, seed=i)
+    ts = [cpu_reference_step(L, Z, S, rows, seed=10 + i) for i in range(steps)]
+    t = sum(ts) / len(ts)
+    value = S * rows * L / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{sh.name}-shaped S{S} B{B} L{L} Z{Z} fwd+bwd", "S": S, "B_per_gpu": B, "L": L, "Z": Z,
+                   "note": "CPU arm runs a bounded row sample of this workload"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{rows} of {B} rows per step (the reference's O(L^2) ranking loss needs "
+                                   f"{6 * S * L * L * 4 / 1e9:.1f} GB per row), oracle port of mpvae.py:145-210 on torch CPU"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from mpvae_b200 import _lib, synth
+    from mpvae_b200 import mpvae as M
+    from mpvae_b200.probit import contract_nt, contract_tn
+    from oracle import probit_elbo_oracle as orc   # only for make_args (a SimpleNamespace) and the CPU baseline leg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sh, L, Z, B, S = workload(a)
+    Bg = B * world
+    flags = {"auto": 0, "fma": _lib.FLAG_CONTRACT_FMA, "tensor": _lib.FLAG_CONTRACT_TENSOR}[a.engine]
+    args = orc.make_args(L, Z, n_train_sample=S, mode="train", nll_coeff=0.5, c_coeff=10.0, mpvae_flags=flags,
+                         noise_seed=1234, dp_global_batch=Bg, dp_row0=rank * B)
+
+    inp = synth.loss_inputs(L, Z, B, S, seed=100 + rank, label_rate=sh.label_rate, with_noise=False)
+    row_keys = ["y", "fe_out", "fe_mu", "fe_logvar", "fx_out", "fx_mu", "fx_logvar"]
+    host = {k: torch.from_numpy(inp[k]).pin_memory() for k in row_keys}
+    devt = {k: host[k].to(dev) for k in row_keys}
+    r_sqrt_sigma = torch.from_numpy(synth.loss_inputs(L, Z, 1, 1, seed=100, with_noise=False)["r_sqrt_sigma"]).to(dev)
+    r32 = r_sqrt_sigma.float().requires_grad_(True)      # fp32 working copy of the (replicated) parameter
+    flush = torch.empty(2 * L2_BYTES // 4, dtype=torch.float32, device=dev)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    step_no = [0]
+
+    def one_step(src, from_host):
+        args.noise_offset = step_no[0]
+        step_no[0] += 1
+        if from_host:
+            t = {k: host[k].to(dev, non_blocking=True) for k in row_keys}
+        else:
+            t = src
+        leaves = {k: (t[k] if k == "y" else t[k].requires_grad_(True)) for k in row_keys}
+        r32.grad = None
+        out = M.compute_loss(leaves["y"], leaves["fe_out"], leaves["fe_mu"], leaves["fe_logvar"], leaves["fx_out"],
+                             leaves["fx_mu"], leaves["fx_logvar"], r32, args)
+        out[0].backward()
+        if world > 1:
+            dist.all_reduce(r32.grad)            # the path's one exchange step: NCCL sum over NVLink
+            r32.grad.div_(world)
+        if from_host:
+            loss_host.copy_(out[0].detach(), non_blocking=True)
+        for k in row_keys:
+            if k != "y":
+                t[k].grad = None
+                t[k].requires_grad_(False)
+        return out
+
+    def timed(n_steps, from_host):
+        evs = []
+        for _ in range(n_steps):
+            flush.add_(1.0)                         # evict L2 between timed iterations (2 x 126 MB written)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            one_step(devt, from_host)
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return [e0.elapsed_time(e1) for e0, e1 in evs]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, a.warmup)):
+        one_step(devt, False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ms = timed(a.steps, False)
+    launches = _lib.launch_count() - launches0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(ms)
+    for _ in range(2):
+        one_step(devt, True)
+    barrier()
+    ms_e2e = timed(a.steps, True)
+    barrier()
+    total_e2e = sum(ms_e2e)
+    if world > 1:
+        t = torch.tensor([total_ms, total_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, total_e2e = t.tolist()
+
+    # ---- dominant kernel, timed alone on its stream with CUDA events (roofline.achieved) ----
+    roof = None
+    if rank == 0:
+        peaks = measured_peaks()
+        M_rows = S * B
+        noise = torch.randn(M_rows, Z, device=dev)
+        eng = {"auto": 0, "fma": 1, "tensor": 2}[a.engine]
+        reps = 3
+        contract_nt(noise, r32.detach(), engine=eng)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.add_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); contract_nt(noise, r32.detach(), engine=eng); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t_k = statistics.median(ts) * 1e-3
+        flops = 2.0 * M_rows * L * Z
+        dense = Z >= 128
+        if dense:
+            # parity-preserving 3xTF32 on tcgen05: TF32 dense = 1/2 of bf16, three MMA passes => bf16 / 6
+            peak = peaks["bf16_tflops"] / 6.0
+            roof = {"bound": "tensor", "achieved": flops / t_k / 1e12, "peak": peak, "unit": "TFLOP/s",
+                    "frac": flops / t_k / 1e12 / peak, "traffic": None,
+                    "kernel": "contract_nt (noise.R^T, mpvae.py:168)", "kernel_ms": t_k * 1e3,
+                    "peak_basis": f"{peaks['_source']} bf16 burst {peaks['bf16_tflops']} TFLOP/s / 6 (fp32-equivalent 3xTF32)",
+                    "algorithmic_flops_per_launch": flops}
+        else:
+            bytes_alg = 4.0 * (M_rows * Z + L * Z + M_rows * L)
+            roof = {"bound": "hbm", "achieved": bytes_alg / t_k / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": bytes_alg / t_k / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                    "kernel": "contract_nt (noise.R^T, mpvae.py:168)", "kernel_ms": t_k * 1e3,
+                    "peak_basis": f"{peaks['_source']} HBM copy bandwidth", "algorithmic_bytes_per_launch": bytes_alg}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    units = float(S) * Bg * L * a.steps
+    bi = sum(host[k].numel() * 4 for k in row_keys)
+    line = {
+        "metric": METRIC, "value": units / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": max(3, a.warmup), "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{sh.name}-shaped S{S} B{B} L{L} Z{Z} fwd+bwd", "S": S, "B_per_gpu": B, "B_global": Bg,
+                   "L": L, "Z": Z, "D": 50, "noise": "philox (on device, inside the step)", "engine": a.engine,
+                   "l2": "L2 flushed between timed iterations (252 MB written); per-step CUDA events summed",
+                   "exchange": "NCCL all-reduce of g_R (fp32) per step" if world > 1 else "none (1 GPU)"},
+        "clocks": clocks,
+        "e2e": {"value": units / (total_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": bi, "d2h_bytes_per_step": 4,
+                "ms_per_step": total_e2e / a.steps},
+        "gpu_launches": int(launches),
+        "steps_per_s": a.steps / (total_ms * 1e-3),
+        "roofline": roof,
+    }
+    if not a.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count())
+        rows = cpu_rows_for(L, Z, S, a.cpu_rows)
+        cpu_reference_step(L, Z, S, min(rows, 1))
+        t_cpu = cpu_reference_step(L, Z, S, rows)
+        line["cpu_baseline"] = {"value": S * rows * L / t_cpu, "unit": UNIT, "cores": torch.get_num_threads(),
+                                "kind": "port",
+                                "sample": f"1 step on {rows} of {B} rows ({t_cpu:.1f} s): oracle port of mpvae.py:145-210 "
+                                          "(O(L^2) pairwise ranking loss) on torch CPU, fwd+bwd"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

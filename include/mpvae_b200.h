@@ -1,0 +1,113 @@
+/*
+ * mpvae_b200.h -- C-ABI of the B200-native probit-ELBO hot path.
+ *
+ * Drop-in boundary for lliutianc/MPVAE-1's `compute_loss` (reference mpvae.py:145-210) and its
+ * autograd backward.  The reference has no FFI (pure Python/torch), so the entry points below are what
+ * a binding for this path would call; the Python mirror in mpvae-1_b200/ binds them with ctypes
+ * (INTEGRATION.md shows the stub a reference maintainer would add to mpvae.py).
+ *
+ * Conventions
+ *   - plain C types only: device pointers, sizes, a cudaStream_t passed as void*.
+ *   - every buffer is owned by the caller (PyTorch's caching allocator in practice); the library
+ *     never allocates or frees device memory, never synchronises the device and launches only on the
+ *     given stream.
+ *   - all matrices are dense row-major fp32 unless noted.  S = n_sample, B = batch rows, L = label_dim,
+ *     Z = z_dim, D = latent_dim.
+ *   - return value 0 = success; otherwise an error code, text via mpvae_last_error() (thread-local).
+ *   - there is no CPU implementation behind this header.
+ */
+#ifndef MPVAE_B200_H_
+#define MPVAE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPVAE_ABI_VERSION 3
+
+/* flags */
+#define MPVAE_FLAG_SANITIZE_DEGENERATE 0x1u /* rows with n_pos*n_neg == 0 get zero ranking gradient instead of
+                                               the reference's NaN (mpvae.py:118-121); default off = faithful */
+#define MPVAE_FLAG_CONTRACT_TENSOR     0x2u /* noise.R^T and g_R on tcgen05 (3xTF32); default: chosen by shape */
+#define MPVAE_FLAG_CONTRACT_FMA        0x4u /* force the CUDA-core FMA contraction */
+
+/* order of the six scalar outputs (first six entries of the 8-tuple at mpvae.py:210) */
+enum { MPVAE_TOTAL = 0, MPVAE_NLL = 1, MPVAE_NLL_X = 2, MPVAE_C = 3, MPVAE_C_X = 4, MPVAE_KL = 5 };
+
+typedef struct mpvae_probit_params {
+    uint32_t struct_bytes; /* = sizeof(mpvae_probit_params); ABI guard */
+    uint32_t flags;
+    int32_t S, B, L, Z, D;
+    float nll_coeff; /* args.nll_coeff, mpvae.py:207 */
+    float c_coeff;   /* args.c_coeff,   mpvae.py:208 */
+
+    /* ---- inputs (device) ---- */
+    const float *y;         /* (B,L) labels, input_label                      mpvae.py:145 */
+    const float *fe_out;    /* (B,L) label-branch decoder logits                            */
+    const float *fx_out;    /* (B,L) feature-branch decoder logits                          */
+    const float *fe_mu;     /* (B,D) */
+    const float *fe_logvar; /* (B,D) */
+    const float *fx_mu;     /* (B,D) */
+    const float *fx_logvar; /* (B,D) */
+    const float *r;         /* (L,Z) r_sqrt_sigma cast to fp32                mpvae.py:165 */
+    const float *noise;     /* (S,B,Z) standard normal samples                mpvae.py:162 */
+
+    /* ---- forward outputs (device) ---- */
+    float *scalars[6];       /* six 1-element outputs: total, nll, nll_x, c, c_x, kl   mpvae.py:207-210
+                                (separate buffers so the host can hand them out as independent 0-dim tensors) */
+    float *indiv_prob;       /* (B,L) mean_s E_x                              mpvae.py:203 */
+    float *indiv_prob_label; /* (B,L) mean_s E                                mpvae.py:204 */
+
+    /* ---- backward: upstream cotangents (device; a NULL entry = zero cotangent) ---- */
+    const float *g_scalars[6];       /* d objective / d (total, nll, nll_x, c, c_x, kl), 1 element each */
+    const float *g_indiv_prob;       /* (B,L) or NULL */
+    const float *g_indiv_prob_label; /* (B,L) or NULL */
+
+    /* ---- backward outputs (device; g_r may be NULL when R needs no gradient) ---- */
+    float *g_fe_out, *g_fx_out;                           /* (B,L) */
+    float *g_fe_mu, *g_fe_logvar, *g_fx_mu, *g_fx_logvar; /* (B,D) */
+    float *g_r;                                           /* (L,Z) */
+
+    /* ---- scratch (device), >= mpvae_workspace_bytes(); forward fills it, backward reads it ---- */
+    void *workspace;
+    uint64_t workspace_bytes;
+} mpvae_probit_params;
+
+/* Bytes of scratch for one forward(+backward) call.  want_backward=0 sizes the inference path. */
+uint64_t mpvae_workspace_bytes(int32_t S, int32_t B, int32_t L, int32_t Z, int32_t want_backward, uint32_t flags);
+
+/* Forward: replaces the body of compute_loss (mpvae.py:145-210) given the noise tensor. */
+int mpvae_probit_forward(const mpvae_probit_params *p, void *cuda_stream);
+
+/* Backward: the autograd backward of compute_loss (implicit in the reference, train.py:125),
+ * closed form in SURVEY.md 8(a-12).  Must follow a forward on the same workspace. */
+int mpvae_probit_backward(const mpvae_probit_params *p, void *cuda_stream);
+
+/* Counter-based standard-normal noise, replaces torch.normal(0,1,(S,B,Z)) of mpvae.py:162.
+ * Element (s, b_global, z) depends only on (seed, offset, s, b_global, z): a rank holding rows
+ * [row0, row0+B) of a B_global-row batch draws the same numbers a single GPU would. */
+int mpvae_philox_normal(float *noise, int32_t S, int32_t B, int32_t Z, int32_t B_global, int32_t row0,
+                        uint64_t seed, uint64_t offset, void *cuda_stream);
+
+/* C[M,N] = A[M,K] . B[N,K]^T (fp32).  The contraction of mpvae.py:168 as a stand-alone entry
+ * (A = noise viewed (S*B, Z), B = R).  engine: 0 = auto, 1 = CUDA-core FMA, 2 = tcgen05 3xTF32. */
+int mpvae_contract_nt(const float *A, const float *Bm, float *C, int32_t M, int32_t N, int32_t K, int32_t engine,
+                      void *workspace, uint64_t workspace_bytes, void *cuda_stream);
+
+/* C[N1,N2] = A[M,N1]^T . B[M,N2] (fp32): g_R = gx^T . noise of SURVEY 8(a-12). Same engine codes. */
+int mpvae_contract_tn(const float *A, const float *Bm, float *C, int32_t M, int32_t N1, int32_t N2, int32_t engine,
+                      void *workspace, uint64_t workspace_bytes, void *cuda_stream);
+uint64_t mpvae_contract_workspace_bytes(int32_t M, int32_t N, int32_t K, int32_t engine);
+
+const char *mpvae_last_error(void);
+int mpvae_abi_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches claim) */
+uint64_t mpvae_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPVAE_B200_H_ */

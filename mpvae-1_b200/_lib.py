@@ -1,0 +1,97 @@
+"""ctypes binding of libmpvae_b200.so (C-ABI declared in include/mpvae_b200.h).
+
+No pybind, no torch types across the boundary: raw device pointers, sizes and the CUDA stream handle.
+There is deliberately no fallback: if the shared library is missing (or a symbol is), importing this
+module raises -- the product path must never silently run on anything but the CUDA kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmpvae_b200.so")
+
+ABI_VERSION = 3
+FLAG_SANITIZE_DEGENERATE = 0x1
+FLAG_CONTRACT_TENSOR = 0x2
+FLAG_CONTRACT_FMA = 0x4
+
+# every symbol include/mpvae_b200.h declares
+EXPORTS = (
+    "mpvae_workspace_bytes", "mpvae_probit_forward", "mpvae_probit_backward", "mpvae_philox_normal",
+    "mpvae_contract_nt", "mpvae_contract_tn", "mpvae_contract_workspace_bytes", "mpvae_last_error",
+    "mpvae_abi_version", "mpvae_launch_count",
+)
+
+_f = C.c_void_p  # device pointer
+
+
+class ProbitParams(C.Structure):
+    """Mirror of `mpvae_probit_params` (field order and types must match the header)."""
+    _fields_ = [
+        ("struct_bytes", C.c_uint32), ("flags", C.c_uint32),
+        ("S", C.c_int32), ("B", C.c_int32), ("L", C.c_int32), ("Z", C.c_int32), ("D", C.c_int32),
+        ("nll_coeff", C.c_float), ("c_coeff", C.c_float),
+        ("y", _f), ("fe_out", _f), ("fx_out", _f), ("fe_mu", _f), ("fe_logvar", _f), ("fx_mu", _f),
+        ("fx_logvar", _f), ("r", _f), ("noise", _f),
+        ("scalars", _f * 6), ("indiv_prob", _f), ("indiv_prob_label", _f),
+        ("g_scalars", _f * 6), ("g_indiv_prob", _f), ("g_indiv_prob_label", _f),
+        ("g_fe_out", _f), ("g_fx_out", _f), ("g_fe_mu", _f), ("g_fe_logvar", _f), ("g_fx_mu", _f),
+        ("g_fx_logvar", _f), ("g_r", _f),
+        ("workspace", _f), ("workspace_bytes", C.c_uint64),
+    ]
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). mpvae_b200 has no CPU / eager fallback.")
+    lib = C.CDLL(LIB_PATH)
+    missing = [s for s in EXPORTS if not hasattr(lib, s)]
+    if missing:
+        raise LibraryMissing(f"{LIB_PATH} lacks symbols {missing}")
+    lib.mpvae_abi_version.restype = C.c_int
+    if lib.mpvae_abi_version() != ABI_VERSION:
+        raise LibraryMissing(f"ABI mismatch: library {lib.mpvae_abi_version()} vs binding {ABI_VERSION}; rebuild")
+    lib.mpvae_last_error.restype = C.c_char_p
+    lib.mpvae_launch_count.restype = C.c_uint64
+    lib.mpvae_workspace_bytes.restype = C.c_uint64
+    lib.mpvae_workspace_bytes.argtypes = [C.c_int32] * 5 + [C.c_uint32]
+    lib.mpvae_probit_forward.restype = C.c_int
+    lib.mpvae_probit_forward.argtypes = [C.POINTER(ProbitParams), C.c_void_p]
+    lib.mpvae_probit_backward.restype = C.c_int
+    lib.mpvae_probit_backward.argtypes = [C.POINTER(ProbitParams), C.c_void_p]
+    lib.mpvae_philox_normal.restype = C.c_int
+    lib.mpvae_philox_normal.argtypes = [C.c_void_p] + [C.c_int32] * 5 + [C.c_uint64, C.c_uint64, C.c_void_p]
+    lib.mpvae_contract_workspace_bytes.restype = C.c_uint64
+    lib.mpvae_contract_workspace_bytes.argtypes = [C.c_int32] * 4
+    for fn in (lib.mpvae_contract_nt, lib.mpvae_contract_tn):
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_void_p, C.c_uint64, C.c_void_p]
+    return lib
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = _load()
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().mpvae_last_error()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def launch_count() -> int:
+    return int(lib().mpvae_launch_count())

@@ -1,0 +1,227 @@
+// extern "C" surface of libmpvae_b200 (include/mpvae_b200.h): argument validation, workspace carving and the
+// launch sequence of one forward / backward of the probit ELBO.
+#include <atomic>
+#include <string.h>
+
+#include "../../include/mpvae_b200.h"
+#include "common.cuh"
+#include "rows.h"
+#include "tc.h"
+
+namespace mpv {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+int check_launch(const char* what) {
+    count_launch(1);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+        return 2;
+    }
+    return 0;
+}
+
+namespace {
+
+// Workspace carve-up.  Everything is 256-byte aligned; the same function sizes and places.
+struct Workspace {
+    size_t nr, lp, stat, wts, rowaux, rowout, counter, gxs, contract, total;
+};
+
+bool use_tensor(uint32_t flags, int S, int B, int L, int Z) {
+    if (flags & MPVAE_FLAG_CONTRACT_FMA) return false;
+    if (!tc_available()) return false;
+    if (flags & MPVAE_FLAG_CONTRACT_TENSOR) return true;
+    // dense-GEMM regime (north star: label / rank sets >= 128)
+    return Z >= 128 && L >= 128 && (long long)S * B >= 128;
+}
+
+Workspace carve(int S, int B, int L, int Z, bool want_backward, uint32_t flags) {
+    Workspace w{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t cube = (size_t)S * B * L;
+    w.nr = take(cube * sizeof(float));
+    w.lp = take((size_t)B * S * 2 * sizeof(double));
+    w.stat = take((size_t)B * S * 4 * sizeof(float));
+    w.wts = take((size_t)B * S * 2 * sizeof(float));
+    w.rowaux = take((size_t)B * 2 * sizeof(float));
+    w.rowout = take((size_t)B * 8 * sizeof(double));
+    w.counter = take(256);
+    w.gxs = want_backward ? take(cube * sizeof(float)) : off;
+    size_t c = 0;
+    const bool tensor = use_tensor(flags, S, B, L, Z);
+    if (tensor) {
+        c = tc_workspace_nt(S * B, L, Z);
+        if (want_backward) { size_t c2 = tc_workspace_tn(S * B, L, Z); if (c2 > c) c = c2; }
+    } else if (want_backward) {
+        c = contract_tn_fma_workspace(S * B, L, Z);
+    }
+    w.contract = take(c);
+    w.total = off;
+    return w;
+}
+
+int validate(const mpvae_probit_params* p, bool backward) {
+    if (p == nullptr) { set_error("params is NULL"); return 1; }
+    if (p->struct_bytes != sizeof(mpvae_probit_params)) {
+        set_error("params.struct_bytes=%u, library expects %zu (ABI %d)", p->struct_bytes, sizeof(mpvae_probit_params),
+                  MPVAE_ABI_VERSION);
+        return 1;
+    }
+    if (p->S <= 0 || p->B <= 0 || p->L <= 0 || p->Z <= 0 || p->D < 0) {
+        set_error("bad sizes S=%d B=%d L=%d Z=%d D=%d (empty batches are handled by the host wrapper)", p->S, p->B, p->L,
+                  p->Z, p->D);
+        return 1;
+    }
+    if ((long long)p->S * p->B > 0x7fffffffLL) { set_error("S*B overflows int32"); return 1; }
+    if (!p->y || !p->fe_out || !p->fx_out || !p->r || !p->noise || !p->workspace) {
+        set_error("NULL input pointer (y/fe_out/fx_out/r/noise/workspace)");
+        return 1;
+    }
+    if (p->D > 0 && (!p->fe_mu || !p->fe_logvar || !p->fx_mu || !p->fx_logvar)) { set_error("NULL mu/logvar pointer"); return 1; }
+    if (!backward && (!p->scalars[0] || !p->scalars[1] || !p->scalars[2] || !p->scalars[3] || !p->scalars[4] ||
+                      !p->scalars[5] || !p->indiv_prob || !p->indiv_prob_label)) { set_error("NULL forward output pointer"); return 1; }
+    if (backward) {
+        if (!p->g_fe_out || !p->g_fx_out) { set_error("NULL g_fe_out/g_fx_out"); return 1; }
+        if (p->D > 0 && (!p->g_fe_mu || !p->g_fe_logvar || !p->g_fx_mu || !p->g_fx_logvar)) { set_error("NULL mu/logvar gradient pointer"); return 1; }
+    }
+    const uint64_t need = mpvae_workspace_bytes(p->S, p->B, p->L, p->Z, 1, p->flags);
+    const uint64_t need_fwd = mpvae_workspace_bytes(p->S, p->B, p->L, p->Z, 0, p->flags);
+    if (p->workspace_bytes < (backward ? need : need_fwd)) {
+        set_error("workspace too small: %llu < %llu bytes", (unsigned long long)p->workspace_bytes,
+                  (unsigned long long)(backward ? need : need_fwd));
+        return 1;
+    }
+    if ((reinterpret_cast<uintptr_t>(p->workspace) & 255u) != 0) { set_error("workspace must be 256-byte aligned"); return 1; }
+    return 0;
+}
+
+RowArgs row_args(const mpvae_probit_params* p, const Workspace& w) {
+    char* base = static_cast<char*>(p->workspace);
+    RowArgs a{};
+    a.S = p->S; a.B = p->B; a.L = p->L; a.D = p->D;
+    a.sanitize = (p->flags & MPVAE_FLAG_SANITIZE_DEGENERATE) ? 1 : 0;
+    a.nll_coeff = p->nll_coeff; a.c_coeff = p->c_coeff;
+    a.y = p->y; a.fe_out = p->fe_out; a.fx_out = p->fx_out;
+    a.fe_mu = p->fe_mu; a.fe_logvar = p->fe_logvar; a.fx_mu = p->fx_mu; a.fx_logvar = p->fx_logvar;
+    a.nr = reinterpret_cast<const float*>(base + w.nr);
+    a.lp = reinterpret_cast<double*>(base + w.lp);
+    a.stat = reinterpret_cast<float*>(base + w.stat);
+    a.wts = reinterpret_cast<float*>(base + w.wts);
+    a.rowaux = reinterpret_cast<float*>(base + w.rowaux);
+    a.rowout = reinterpret_cast<double*>(base + w.rowout);
+    a.counter = reinterpret_cast<unsigned int*>(base + w.counter);
+    for (int i = 0; i < 6; ++i) { a.scalars[i] = p->scalars[i]; a.g_scalars[i] = p->g_scalars[i]; }
+    a.indiv_prob = p->indiv_prob; a.indiv_prob_label = p->indiv_prob_label;
+    a.g_indiv_prob = p->g_indiv_prob; a.g_indiv_prob_label = p->g_indiv_prob_label;
+    a.g_fe_out = p->g_fe_out; a.g_fx_out = p->g_fx_out;
+    a.g_fe_mu = p->g_fe_mu; a.g_fe_logvar = p->g_fe_logvar; a.g_fx_mu = p->g_fx_mu; a.g_fx_logvar = p->g_fx_logvar;
+    a.gxs = nullptr;
+    return a;
+}
+
+}  // namespace
+}  // namespace mpv
+
+using namespace mpv;
+
+extern "C" {
+
+int mpvae_abi_version(void) { return MPVAE_ABI_VERSION; }
+const char* mpvae_last_error(void) { return g_err; }
+uint64_t mpvae_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+uint64_t mpvae_workspace_bytes(int32_t S, int32_t B, int32_t L, int32_t Z, int32_t want_backward, uint32_t flags) {
+    if (S <= 0 || B <= 0 || L <= 0 || Z <= 0) return 256;
+    return carve(S, B, L, Z, want_backward != 0, flags).total;
+}
+
+int mpvae_probit_forward(const mpvae_probit_params* p, void* cuda_stream) {
+    if (int rc = validate(p, false)) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    // the scratch may be shorter than the backward layout on the inference path: carve what the caller sized
+    const bool bwd_layout = p->workspace_bytes >= mpvae_workspace_bytes(p->S, p->B, p->L, p->Z, 1, p->flags);
+    const Workspace w = carve(p->S, p->B, p->L, p->Z, bwd_layout, p->flags);
+    char* base = static_cast<char*>(p->workspace);
+    float* nr = reinterpret_cast<float*>(base + w.nr);
+    const int M = p->S * p->B;
+    int rc;
+    if (use_tensor(p->flags, p->S, p->B, p->L, p->Z))
+        rc = tc_contract_nt(p->noise, p->r, nr, M, p->L, p->Z, base + w.contract, w.total - w.contract, stream);
+    else
+        rc = launch_contract_nt_fma(p->noise, p->r, nr, M, p->L, p->Z, stream);
+    if (rc) return rc;
+    cudaError_t e = cudaMemsetAsync(base + w.counter, 0, 256, stream);
+    if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return 2; }
+    return launch_row_forward(row_args(p, w), stream);
+}
+
+int mpvae_probit_backward(const mpvae_probit_params* p, void* cuda_stream) {
+    if (int rc = validate(p, true)) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    const Workspace w = carve(p->S, p->B, p->L, p->Z, true, p->flags);
+    char* base = static_cast<char*>(p->workspace);
+    RowArgs a = row_args(p, w);
+    if (p->g_r) a.gxs = reinterpret_cast<float*>(base + w.gxs);
+    if (int rc = launch_row_backward(a, stream)) return rc;
+    if (!p->g_r) return 0;
+    const int M = p->S * p->B;
+    if (use_tensor(p->flags, p->S, p->B, p->L, p->Z))
+        return tc_contract_tn(a.gxs, p->noise, p->g_r, M, p->L, p->Z, base + w.contract, w.total - w.contract, stream);
+    return launch_contract_tn_fma(a.gxs, p->noise, p->g_r, M, p->L, p->Z, base + w.contract, w.total - w.contract, stream);
+}
+
+int mpvae_philox_normal(float* noise, int32_t S, int32_t B, int32_t Z, int32_t B_global, int32_t row0, uint64_t seed,
+                        uint64_t offset, void* cuda_stream) {
+    if (!noise) { set_error("philox: NULL output"); return 1; }
+    if (S < 0 || B < 0 || Z < 0 || row0 < 0 || B_global < row0 + B) {
+        set_error("philox: bad sizes S=%d B=%d Z=%d B_global=%d row0=%d", S, B, Z, B_global, row0);
+        return 1;
+    }
+    return launch_philox_normal(noise, S, B, Z, B_global, row0, seed, offset, static_cast<cudaStream_t>(cuda_stream));
+}
+
+uint64_t mpvae_contract_workspace_bytes(int32_t M, int32_t N, int32_t K, int32_t engine) {
+    // covers both orientations: nt (M,N,K) and tn (M = reduction, N1 = N, N2 = K)
+    size_t a = contract_tn_fma_workspace(M, N, K);
+    if (engine != 1 && tc_available()) {
+        size_t t1 = tc_workspace_nt(M, N, K), t2 = tc_workspace_tn(M, N, K);
+        if (t1 > a) a = t1;
+        if (t2 > a) a = t2;
+    }
+    return align_up(a, 256) + 256;
+}
+
+int mpvae_contract_nt(const float* A, const float* Bm, float* C, int32_t M, int32_t N, int32_t K, int32_t engine,
+                      void* workspace, uint64_t workspace_bytes, void* cuda_stream) {
+    if (!A || !Bm || !C || M <= 0 || N <= 0 || K <= 0) { set_error("contract_nt: bad arguments"); return 1; }
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    if (engine == 2) {
+        if (!tc_available()) { set_error("contract_nt: tensor engine not built"); return 7; }
+        return tc_contract_nt(A, Bm, C, M, N, K, workspace, workspace_bytes, stream);
+    }
+    return launch_contract_nt_fma(A, Bm, C, M, N, K, stream);
+}
+
+int mpvae_contract_tn(const float* A, const float* Bm, float* C, int32_t M, int32_t N1, int32_t N2, int32_t engine,
+                      void* workspace, uint64_t workspace_bytes, void* cuda_stream) {
+    if (!A || !Bm || !C || M <= 0 || N1 <= 0 || N2 <= 0) { set_error("contract_tn: bad arguments"); return 1; }
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    if (engine == 2) {
+        if (!tc_available()) { set_error("contract_tn: tensor engine not built"); return 7; }
+        return tc_contract_tn(A, Bm, C, M, N1, N2, workspace, workspace_bytes, stream);
+    }
+    return launch_contract_tn_fma(A, Bm, C, M, N1, N2, workspace, workspace_bytes, stream);
+}
+
+}  // extern "C"

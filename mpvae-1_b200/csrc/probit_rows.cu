@@ -1,0 +1,356 @@
+// Row kernels of the probit ELBO: everything in compute_loss (mpvae.py:145-210) after the contraction
+// noise.R^T, and the closed-form backward, one CTA per batch row.
+//
+//   forward  : nr (S,B,L) + y / fe_out / fx_out (B,L) + mu/logvar (B,D)
+//              -> per-(s,b) log-likelihoods, ranking factors, KL row term, predictions (B,L) x2,
+//                 six scalars (last CTA reduces the per-row partials in a fixed order)
+//   backward : same inputs + saved per-(s,b) statistics + upstream cotangents
+//              -> g_fe_out, g_fx_out (B,L), gxs = gx_l + gx_x (S,B,L) for g_R, mu/logvar grads
+//
+// Work decomposition inside a CTA (8 warps): lanes run along the label axis (coalesced 128 B reads of
+// nr / y / logits); the 8 warps are split nws x nwl over samples x 32-label chunks so that short label
+// rows (L = 14..81) still keep every warp busy.  Reductions over labels are warp shuffles (+ one smem
+// hop when nwl > 1); log-likelihood sums are carried in fp64 so the result is independent of the
+// summation order to ~1e-13 (the fp32 reference itself carries ~ulp(lp) of order noise).
+#include "common.cuh"
+#include "probit_math.cuh"
+#include "rows.h"
+
+namespace mpv {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = 8;
+constexpr int kST = 2;   // samples per inner tile (unrolled)
+
+struct BlockCounts { int npos, nneg; };
+
+__device__ __forceinline__ BlockCounts count_labels(const float* __restrict__ yrow, int L, int* s_tmp) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int cp = 0, cn = 0;
+    for (int l = tid; l < L; l += kThreads) {
+        const float v = yrow[l];
+        cp += (v == 1.0f);   // torch.eq(labels, ones)   mpvae.py:107
+        cn += (v == 0.0f);   // torch.eq(labels, zeros)  mpvae.py:108
+    }
+    cp = warp_sum(cp);
+    cn = warp_sum(cn);
+    if (lane == 0) { s_tmp[warp] = cp; s_tmp[kWarps + warp] = cn; }
+    __syncthreads();
+    BlockCounts c{0, 0};
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) { c.npos += s_tmp[w]; c.nneg += s_tmp[kWarps + w]; }
+    return c;
+}
+
+__global__ void __launch_bounds__(kThreads)
+probit_row_fwd_kernel(const RowArgs a) {
+    extern __shared__ float s_pacc[];                 // [nws][2][L] prediction partial sums
+    __shared__ double s_lp[kWarps][kST][2];
+    __shared__ float s_pn[kWarps][kST][4];
+    __shared__ int s_cnt[2 * kWarps];
+    __shared__ double s_kl[kWarps];
+    __shared__ double s_fin[8];
+    __shared__ int s_last;
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int L = a.L, S = a.S, B = a.B;
+    const int nwl = a.nwl, nws = kWarps / nwl;
+    const int wl = warp % nwl, ws = warp / nwl;
+    const int nchunks = (L + 31) >> 5;
+    const float* __restrict__ yrow = a.y + (size_t)b * L;
+    const float* __restrict__ ferow = a.fe_out + (size_t)b * L;
+    const float* __restrict__ fxrow = a.fx_out + (size_t)b * L;
+
+    for (int i = tid; i < nws * 2 * L; i += kThreads) s_pacc[i] = 0.0f;
+    const BlockCounts cnt = count_labels(yrow, L, s_cnt);   // contains a __syncthreads()
+
+    const int steps = (S + kST * nws - 1) / (kST * nws);
+    for (int step = 0; step < steps; ++step) {
+        const int s0 = (step * nws + ws) * kST;
+        double lp[kST][2];
+        float pn[kST][4];
+#pragma unroll
+        for (int i = 0; i < kST; ++i) {
+            lp[i][0] = lp[i][1] = 0.0;
+            pn[i][0] = pn[i][1] = pn[i][2] = pn[i][3] = 0.0f;
+        }
+        if (s0 < S) {
+            float* __restrict__ pacc = s_pacc + (size_t)ws * 2 * L;
+            for (int c = wl; c < nchunks; c += nwl) {
+                const int l = (c << 5) + lane;
+                if (l < L) {
+                    const float yv = yrow[l], fe = ferow[l], fx = fxrow[l];
+                    float pl = 0.0f, px = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < kST; ++i) {
+                        const int s = s0 + i;
+                        if (s < S) {
+                            const float nr = a.nr[((size_t)s * B + b) * L + l];
+                            const CellFwd cl = cell_forward(nr + fe, yv);   // mpvae.py:168,177
+                            const CellFwd cx = cell_forward(nr + fx, yv);   // mpvae.py:170,180
+                            lp[i][0] += (double)cl.ll;
+                            lp[i][1] += (double)cx.ll;
+                            pn[i][0] += cl.epos; pn[i][1] += cl.eneg;
+                            pn[i][2] += cx.epos; pn[i][3] += cx.eneg;
+                            pl += cl.E; px += cx.E;
+                        }
+                    }
+                    pacc[l] += pl;
+                    pacc[L + l] += px;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kST; ++i) {
+            lp[i][0] = warp_sum(lp[i][0]); lp[i][1] = warp_sum(lp[i][1]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pn[i][q] = warp_sum(pn[i][q]);
+            if (lane == 0) {
+                s_lp[warp][i][0] = lp[i][0]; s_lp[warp][i][1] = lp[i][1];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) s_pn[warp][i][q] = pn[i][q];
+            }
+        }
+        __syncthreads();
+        if (tid < nws * kST) {
+            const int g = tid / kST, i = tid % kST;
+            const int s = (step * nws + g) * kST + i;
+            if (s < S) {
+                double l0 = 0.0, l1 = 0.0;
+                float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+                for (int w = g * nwl; w < (g + 1) * nwl; ++w) {   // fixed order
+                    l0 += s_lp[w][i][0]; l1 += s_lp[w][i][1];
+                    q0 += s_pn[w][i][0]; q1 += s_pn[w][i][1]; q2 += s_pn[w][i][2]; q3 += s_pn[w][i][3];
+                }
+                const size_t o = (size_t)b * S + s;
+                a.lp[o * 2 + 0] = l0; a.lp[o * 2 + 1] = l1;
+                reinterpret_cast<float4*>(a.stat)[o] = make_float4(q0, q1, q2, q3);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- predictions: mean over samples (mpvae.py:203-204) ----
+    const float fS = (float)S;
+    for (int l = tid; l < L; l += kThreads) {
+        float sl = 0.0f, sx = 0.0f;
+        for (int g = 0; g < nws; ++g) { sl += s_pacc[(size_t)g * 2 * L + l]; sx += s_pacc[(size_t)g * 2 * L + L + l]; }
+        a.indiv_prob_label[(size_t)b * L + l] = sl / fS;
+        a.indiv_prob[(size_t)b * L + l] = sx / fS;
+    }
+
+    // ---- KL row term (mpvae.py:147-148) ----
+    {
+        double kp = 0.0;
+        const size_t o = (size_t)b * a.D;
+        for (int d = tid; d < a.D; d += kThreads)
+            kp += (double)kl_cell(a.fe_mu[o + d], a.fe_logvar[o + d], a.fx_mu[o + d], a.fx_logvar[o + d]).term;
+        kp = warp_sum(kp);
+        if (lane == 0) s_kl[warp] = kp;
+    }
+    __syncthreads();   // also orders the lp/stat global writes above before warp 0 reads them back
+
+    // ---- per-row log-mean-exp over samples, softmax weights, ranking sums (mpvae.py:188-190,115-122) ----
+    if (warp == 0) {
+        const float norm5 = 5.0f * ((float)cnt.npos * (float)cnt.nneg);
+        double outv[5];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            float m = -INFINITY;
+            for (int s = lane; s < S; s += 32) m = fmaxf(m, (float)a.lp[((size_t)b * S + s) * 2 + q]);
+            m = warp_max(m);
+            double se = 0.0;
+            for (int s = lane; s < S; s += 32) se += (double)expf((float)a.lp[((size_t)b * S + s) * 2 + q] - m);
+            se = warp_sum(se);
+            const float fse = (float)se;
+            outv[q] = (double)(-logf(fse / fS) - m);
+            double cs = 0.0;
+            for (int s = lane; s < S; s += 32) {
+                const size_t o = (size_t)b * S + s;
+                a.wts[o * 2 + q] = expf((float)a.lp[o * 2 + q] - m) / fse;
+                const float pos = a.stat[o * 4 + 2 * q], neg = a.stat[o * 4 + 2 * q + 1];
+                float v = (pos * neg) / norm5;
+                if (isnan(v) || isinf(v)) v = 0.0f;   // torch.where(isinf | isnan, 0, loss), mpvae.py:120
+                cs += (double)v;
+            }
+            outv[2 + q] = warp_sum(cs);
+        }
+        double kl = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) kl += s_kl[w];
+        outv[4] = 0.5 * kl;
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) a.rowout[(size_t)b * 8 + q] = outv[q];
+            a.rowaux[(size_t)b * 2 + 0] = (float)cnt.npos;
+            a.rowaux[(size_t)b * 2 + 1] = (float)cnt.nneg;
+        }
+    }
+
+    // ---- last CTA: batch means and the total (mpvae.py:190,122,147,207-208), fixed summation order ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (warp < 5) {
+        double acc = 0.0;
+        for (int r = lane; r < B; r += 32) acc += __ldcg(&a.rowout[(size_t)r * 8 + warp]);
+        acc = warp_sum(acc);
+        if (lane == 0) s_fin[warp] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const double dB = (double)B, dSB = (double)S * (double)B;
+        const float nll = (float)(s_fin[0] / dB), nllx = (float)(s_fin[1] / dB);
+        const float c = (float)(s_fin[2] / dSB), cx = (float)(s_fin[3] / dSB);
+        const float kl = (float)(s_fin[4] / dB);
+        const float total = MPV_ADD(MPV_ADD(MPV_MUL(MPV_ADD(nll, nllx), a.nll_coeff), MPV_MUL(MPV_ADD(c, cx), a.c_coeff)),
+                                    MPV_MUL(kl, 1.1f));
+        *a.scalars[0] = total; *a.scalars[1] = nll; *a.scalars[2] = nllx;
+        *a.scalars[3] = c; *a.scalars[4] = cx; *a.scalars[5] = kl;
+        *a.counter = 0u;   // ready for the next launch on this workspace
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+probit_row_bwd_kernel(const RowArgs a) {
+    extern __shared__ float s_gacc[];   // [nws][2][L] logit-gradient partial sums
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int L = a.L, S = a.S, B = a.B;
+    const int nwl = a.nwl, nws = kWarps / nwl;
+    const int wl = warp % nwl, ws = warp / nwl;
+    const int nchunks = (L + 31) >> 5;
+    const float* __restrict__ yrow = a.y + (size_t)b * L;
+    const float* __restrict__ ferow = a.fe_out + (size_t)b * L;
+    const float* __restrict__ fxrow = a.fx_out + (size_t)b * L;
+
+    for (int i = tid; i < nws * 2 * L; i += kThreads) s_gacc[i] = 0.0f;
+
+    // effective weights of the five loss terms: d objective / d term (mpvae.py:207-208 + upstream)
+    const float gt = a.g_scalars[0] ? *a.g_scalars[0] : 0.0f, g1 = a.g_scalars[1] ? *a.g_scalars[1] : 0.0f,
+                g2 = a.g_scalars[2] ? *a.g_scalars[2] : 0.0f, g3 = a.g_scalars[3] ? *a.g_scalars[3] : 0.0f,
+                g4 = a.g_scalars[4] ? *a.g_scalars[4] : 0.0f, g5 = a.g_scalars[5] ? *a.g_scalars[5] : 0.0f;
+    const float a_nll[2] = {gt * a.nll_coeff + g1, gt * a.nll_coeff + g2};
+    const float a_c[2] = {gt * a.c_coeff + g3, gt * a.c_coeff + g4};
+    const float a_kl = gt * 1.1f + g5;
+
+    const float npos = a.rowaux[(size_t)b * 2], nneg = a.rowaux[(size_t)b * 2 + 1];
+    const float norm5 = 5.0f * (npos * nneg);
+    const float fS = (float)S, fB = (float)B;
+    float kb[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        if (norm5 == 0.0f) {
+            // the reference back-propagates 0/0 through torch.div here (mpvae.py:118): NaN for the whole row
+            kb[q] = a.sanitize ? 0.0f : __fdiv_rn(0.0f, norm5);
+        } else {
+            kb[q] = (a_c[q] / (fS * fB)) / norm5;
+        }
+    }
+    const float cnb[2] = {-(a_nll[0] / fB), -(a_nll[1] / fB)};
+    const bool has_gp = a.g_indiv_prob != nullptr, has_gpl = a.g_indiv_prob_label != nullptr;
+    __syncthreads();
+
+    const int steps = (S + kST * nws - 1) / (kST * nws);
+    for (int step = 0; step < steps; ++step) {
+        const int s0 = (step * nws + ws) * kST;
+        if (s0 >= S) continue;
+        float cn[kST][2], cp[kST][2], cq[kST][2];
+#pragma unroll
+        for (int i = 0; i < kST; ++i) {
+            const int s = min(s0 + i, S - 1);
+            const size_t o = (size_t)b * S + s;
+            const float4 st = reinterpret_cast<const float4*>(a.stat)[o];
+            const float2 w = reinterpret_cast<const float2*>(a.wts)[o];
+            cn[i][0] = cnb[0] * w.x;           cn[i][1] = cnb[1] * w.y;
+            cp[i][0] = -5.0f * kb[0] * st.y;   cp[i][1] = -5.0f * kb[1] * st.w;   // x neg sums
+            cq[i][0] = 5.0f * kb[0] * st.x;    cq[i][1] = 5.0f * kb[1] * st.z;    // x pos sums
+        }
+        float* __restrict__ gacc = s_gacc + (size_t)ws * 2 * L;
+        for (int c = wl; c < nchunks; c += nwl) {
+            const int l = (c << 5) + lane;
+            if (l >= L) continue;
+            const float yv = yrow[l], fe = ferow[l], fx = fxrow[l];
+            const float gpl = has_gpl ? a.g_indiv_prob_label[(size_t)b * L + l] / fS : 0.0f;
+            const float gpx = has_gp ? a.g_indiv_prob[(size_t)b * L + l] / fS : 0.0f;
+            float gl = 0.0f, gx = 0.0f;
+#pragma unroll
+            for (int i = 0; i < kST; ++i) {
+                const int s = s0 + i;
+                if (s < S) {
+                    const size_t idx = ((size_t)s * B + b) * L + l;
+                    const float nr = a.nr[idx];
+                    const float dl = cell_backward(nr + fe, yv, cn[i][0], cp[i][0], cq[i][0], gpl);
+                    const float dx = cell_backward(nr + fx, yv, cn[i][1], cp[i][1], cq[i][1], gpx);
+                    gl += dl; gx += dx;
+                    if (a.gxs) a.gxs[idx] = dl + dx;
+                }
+            }
+            gacc[l] += gl;
+            gacc[L + l] += gx;
+        }
+    }
+    __syncthreads();
+    for (int l = tid; l < L; l += kThreads) {
+        float sl = 0.0f, sx = 0.0f;
+        for (int g = 0; g < nws; ++g) { sl += s_gacc[(size_t)g * 2 * L + l]; sx += s_gacc[(size_t)g * 2 * L + L + l]; }
+        a.g_fe_out[(size_t)b * L + l] = sl;
+        a.g_fx_out[(size_t)b * L + l] = sx;
+    }
+    // KL gradients: c = a_kl * 0.5 / B
+    const float kc = a_kl * 0.5f / fB;
+    const size_t o = (size_t)b * a.D;
+    for (int d = tid; d < a.D; d += kThreads) {
+        const KlCell k = kl_cell(a.fe_mu[o + d], a.fe_logvar[o + d], a.fx_mu[o + d], a.fx_logvar[o + d]);
+        a.g_fe_mu[o + d] = kc * k.d_fe_mu;
+        a.g_fe_logvar[o + d] = kc * k.d_fe_lv;
+        a.g_fx_mu[o + d] = kc * k.d_fx_mu;
+        a.g_fx_logvar[o + d] = kc * k.d_fx_lv;
+    }
+}
+
+int pick_nwl(int L) {
+    const int nchunks = (L + 31) / 32;
+    int nwl = 1;
+    while (nwl < nchunks && nwl < kWarps) nwl <<= 1;
+    return nwl;
+}
+
+}  // namespace
+
+size_t row_smem_bytes(int L) {
+    const int nwl = pick_nwl(L);
+    return (size_t)(kWarps / nwl) * 2 * (size_t)L * sizeof(float);
+}
+
+int launch_row_forward(RowArgs a, cudaStream_t stream) {
+    a.nwl = pick_nwl(a.L);
+    const size_t smem = row_smem_bytes(a.L);
+    if (smem > 200 * 1024) { set_error("label_dim %d needs %zu B of shared memory per row (limit 200 KiB)", a.L, smem); return 3; }
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(probit_row_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(fwd): %s", cudaGetErrorString(e)); return 4; }
+    }
+    probit_row_fwd_kernel<<<a.B, kThreads, smem, stream>>>(a);
+    return check_launch("probit_row_fwd_kernel");
+}
+
+int launch_row_backward(RowArgs a, cudaStream_t stream) {
+    a.nwl = pick_nwl(a.L);
+    const size_t smem = row_smem_bytes(a.L);
+    if (smem > 200 * 1024) { set_error("label_dim %d needs %zu B of shared memory per row (limit 200 KiB)", a.L, smem); return 3; }
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(probit_row_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(bwd): %s", cudaGetErrorString(e)); return 4; }
+    }
+    probit_row_bwd_kernel<<<a.B, kThreads, smem, stream>>>(a);
+    return check_launch("probit_row_bwd_kernel");
+}
+
+}  // namespace mpv

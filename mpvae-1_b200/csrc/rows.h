@@ -1,0 +1,50 @@
+// Internal launch interfaces shared by the .cu translation units of libmpvae_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace mpv {
+
+// Arguments of the per-row kernels (probit_rows.cu).  Pointers are device pointers.
+struct RowArgs {
+    int S, B, L, D;
+    int nwl;        // warps along the label axis (filled by the launcher)
+    int sanitize;   // MPVAE_FLAG_SANITIZE_DEGENERATE
+    float nll_coeff, c_coeff;
+    const float *y, *fe_out, *fx_out, *fe_mu, *fe_logvar, *fx_mu, *fx_logvar;
+    const float* nr;   // (S,B,L) noise.R^T
+    // saved statistics (workspace)
+    double* lp;        // (B,S,2)  Bernoulli log-likelihood per sample: label branch, feature branch
+    float* stat;       // (B,S,4)  pos_l, neg_l, pos_x, neg_x ranking factors
+    float* wts;        // (B,S,2)  softmax_s(lp)
+    float* rowaux;     // (B,2)    n_pos, n_neg
+    double* rowout;    // (B,8)    per-row nll_l, nll_x, c_l, c_x, kl
+    unsigned int* counter;
+    // forward outputs
+    float* scalars[6];
+    float *indiv_prob, *indiv_prob_label;
+    // backward
+    const float* g_scalars[6];
+    const float *g_indiv_prob, *g_indiv_prob_label;
+    float *g_fe_out, *g_fx_out, *g_fe_mu, *g_fe_logvar, *g_fx_mu, *g_fx_logvar;
+    float* gxs;        // (S,B,L) gx_l + gx_x, or nullptr when R needs no gradient
+};
+
+size_t row_smem_bytes(int L);
+int launch_row_forward(RowArgs a, cudaStream_t stream);
+int launch_row_backward(RowArgs a, cudaStream_t stream);
+
+// CUDA-core contraction (contract_fma.cu)
+//   nt: C[M,N] = A[M,K] . B[N,K]^T
+//   tn: C[N1,N2] = A[M,N1]^T . B[M,N2]   (split over M, partials reduced in a fixed order)
+int launch_contract_nt_fma(const float* A, const float* Bm, float* C, int M, int N, int K, cudaStream_t stream);
+size_t contract_tn_fma_workspace(int M, int N1, int N2);
+int launch_contract_tn_fma(const float* A, const float* Bm, float* C, int M, int N1, int N2, void* ws, size_t ws_bytes,
+                           cudaStream_t stream);
+
+// Philox noise (philox.cu)
+int launch_philox_normal(float* noise, int S, int B, int Z, int B_global, int row0, uint64_t seed, uint64_t offset,
+                         cudaStream_t stream);
+
+}  // namespace mpv

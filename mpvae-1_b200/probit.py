@@ -1,0 +1,182 @@
+"""Host side of the probit-ELBO boundary: one `torch.autograd.Function` over the C-ABI.
+
+Mirrors the autograd contract of the reference's `compute_loss` (mpvae.py:145-210):
+differentiable w.r.t. fe_out, fx_out, the four encoder outputs and R; cotangents may arrive on any of
+the 8 outputs (total_loss from train.py:125, indiv_prob / indiv_prob_label from the fairness
+regulariser, fairsoft_train.py:76-140).  PyTorch is used for device memory and the stream only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+_NAMES = ("input_label", "fe_out", "fe_mu", "fe_logvar", "fx_out", "fx_mu", "fx_logvar", "r_sqrt_sigma", "noise")
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _check_inputs(y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise):
+    tensors = (y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise)
+    dev = y.device
+    for name, t in zip(_NAMES, tensors):
+        if not t.is_cuda:
+            raise RuntimeError(f"mpvae_b200: {name} is on {t.device}; the probit ELBO runs on CUDA only "
+                               "(there is no CPU fallback)")
+        if t.device != dev:
+            raise RuntimeError(f"mpvae_b200: {name} is on {t.device}, expected {dev}")
+        if t.dtype != torch.float32:
+            raise TypeError(f"mpvae_b200: {name} must be float32, got {t.dtype}")
+    B, L = fe_out.shape
+    D = fe_mu.shape[1]
+    S, Bn, Z = noise.shape
+    if y.shape != (B, L) or fx_out.shape != (B, L):
+        raise ValueError(f"label / logit shapes disagree: {tuple(y.shape)}, {tuple(fe_out.shape)}, {tuple(fx_out.shape)}")
+    for name, t in (("fe_mu", fe_mu), ("fe_logvar", fe_logvar), ("fx_mu", fx_mu), ("fx_logvar", fx_logvar)):
+        if t.shape != (B, D):
+            raise ValueError(f"{name} has shape {tuple(t.shape)}, expected {(B, D)}")
+    if r32.shape != (L, Z):
+        raise ValueError(f"r_sqrt_sigma has shape {tuple(r32.shape)}, expected {(L, Z)} (label_dim, z_dim)")
+    if Bn != B:
+        raise ValueError(f"noise has {Bn} rows, batch has {B}")
+    return S, B, L, Z, D
+
+
+class ProbitELBO(torch.autograd.Function):
+    """(y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, R32, noise) -> the 8-tuple of mpvae.py:210."""
+
+    @staticmethod
+    def forward(ctx, y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise, nll_coeff, c_coeff, flags):
+        lib = _lib.lib()
+        y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise = (
+            t.contiguous() for t in (y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise))
+        S, B, L, Z, D = _check_inputs(y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise)
+        dev = y.device
+        want_bwd = any(ctx.needs_input_grad)
+        with torch.cuda.device(dev):
+            ws_bytes = int(lib.mpvae_workspace_bytes(S, B, L, Z, 1 if want_bwd else 0, flags))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            scalars = [torch.empty((), dtype=torch.float32, device=dev) for _ in range(6)]
+            prob = torch.empty((B, L), dtype=torch.float32, device=dev)
+            prob_label = torch.empty((B, L), dtype=torch.float32, device=dev)
+            p = _lib.ProbitParams()
+            p.struct_bytes = C.sizeof(_lib.ProbitParams)
+            p.flags = flags
+            p.S, p.B, p.L, p.Z, p.D = S, B, L, Z, D
+            p.nll_coeff, p.c_coeff = float(nll_coeff), float(c_coeff)
+            p.y, p.fe_out, p.fx_out = _ptr(y), _ptr(fe_out), _ptr(fx_out)
+            p.fe_mu, p.fe_logvar, p.fx_mu, p.fx_logvar = _ptr(fe_mu), _ptr(fe_logvar), _ptr(fx_mu), _ptr(fx_logvar)
+            p.r, p.noise = _ptr(r32), _ptr(noise)
+            for i in range(6):
+                p.scalars[i] = scalars[i].data_ptr()
+            p.indiv_prob, p.indiv_prob_label = _ptr(prob), _ptr(prob_label)
+            p.workspace, p.workspace_bytes = _ptr(ws), ws_bytes
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(lib.mpvae_probit_forward(C.byref(p), stream), "mpvae_probit_forward")
+        if want_bwd:
+            ctx.save_for_backward(y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise, ws)
+            ctx.dims = (S, B, L, Z, D)
+            ctx.coeffs = (float(nll_coeff), float(c_coeff), int(flags))
+            ctx.set_materialize_grads(False)
+        return (*scalars, prob, prob_label)
+
+    @staticmethod
+    def backward(ctx, g_total, g_nll, g_nll_x, g_c, g_c_x, g_kl, g_prob, g_prob_label):
+        lib = _lib.lib()
+        y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise, ws = ctx.saved_tensors
+        S, B, L, Z, D = ctx.dims
+        nll_coeff, c_coeff, flags = ctx.coeffs
+        dev = y.device
+        need_r = ctx.needs_input_grad[7]
+
+        def as_f32(g, shape=None):
+            if g is None:
+                return None
+            g = g.to(device=dev, dtype=torch.float32)
+            if shape is not None:
+                g = g.expand(shape)
+            return g.contiguous()
+
+        g_scal = [as_f32(g) for g in (g_total, g_nll, g_nll_x, g_c, g_c_x, g_kl)]
+        g_prob = as_f32(g_prob, (B, L))
+        g_prob_label = as_f32(g_prob_label, (B, L))
+        with torch.cuda.device(dev):
+            g_fe_out = torch.empty_like(fe_out)
+            g_fx_out = torch.empty_like(fx_out)
+            g_mulv = [torch.empty_like(fe_mu) for _ in range(4)]
+            g_r = torch.empty_like(r32) if need_r else None
+            p = _lib.ProbitParams()
+            p.struct_bytes = C.sizeof(_lib.ProbitParams)
+            p.flags = flags
+            p.S, p.B, p.L, p.Z, p.D = S, B, L, Z, D
+            p.nll_coeff, p.c_coeff = nll_coeff, c_coeff
+            p.y, p.fe_out, p.fx_out = _ptr(y), _ptr(fe_out), _ptr(fx_out)
+            p.fe_mu, p.fe_logvar, p.fx_mu, p.fx_logvar = _ptr(fe_mu), _ptr(fe_logvar), _ptr(fx_mu), _ptr(fx_logvar)
+            p.r, p.noise = _ptr(r32), _ptr(noise)
+            for i in range(6):
+                p.g_scalars[i] = g_scal[i].data_ptr() if g_scal[i] is not None else None
+            p.g_indiv_prob, p.g_indiv_prob_label = _ptr(g_prob), _ptr(g_prob_label)
+            p.g_fe_out, p.g_fx_out = _ptr(g_fe_out), _ptr(g_fx_out)
+            p.g_fe_mu, p.g_fe_logvar, p.g_fx_mu, p.g_fx_logvar = (_ptr(t) for t in g_mulv)
+            p.g_r = _ptr(g_r)
+            p.workspace, p.workspace_bytes = _ptr(ws), ws.numel()
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(lib.mpvae_probit_backward(C.byref(p), stream), "mpvae_probit_backward")
+        #       y     fe_out    fe_mu      fe_logvar  fx_out    fx_mu      fx_logvar  r32  noise nll_c c_c flags
+        return (None, g_fe_out, g_mulv[0], g_mulv[1], g_fx_out, g_mulv[2], g_mulv[3], g_r, None, None, None, None)
+
+
+def philox_normal(S, B, Z, *, seed, offset=0, device="cuda", global_batch=None, row0=0):
+    """Standard-normal (S, B, Z) noise from the library's counter-based generator (mpvae.py:162 stand-in).
+    Rows [row0, row0+B) of a `global_batch`-row draw: independent of how the batch is sharded."""
+    lib = _lib.lib()
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("mpvae_b200.philox_normal runs on CUDA only")
+    out = torch.empty((S, B, Z), dtype=torch.float32, device=dev)
+    if out.numel() == 0:
+        return out
+    with torch.cuda.device(dev):
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(lib.mpvae_philox_normal(_ptr(out), S, B, Z, int(global_batch if global_batch is not None else B),
+                                           int(row0), C.c_uint64(seed & (2 ** 64 - 1)), C.c_uint64(offset), stream),
+                   "mpvae_philox_normal")
+    return out
+
+
+def contract_nt(a, b, engine=0):
+    """C[M,N] = A[M,K] . B[N,K]^T through the library (the product of mpvae.py:168)."""
+    lib = _lib.lib()
+    a, b = a.contiguous(), b.contiguous()
+    M, K = a.shape
+    N = b.shape[0]
+    assert b.shape[1] == K and a.is_cuda and b.is_cuda and a.dtype == b.dtype == torch.float32
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        nbytes = int(lib.mpvae_contract_workspace_bytes(M, N, K, engine))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
+        stream = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
+        _lib.check(lib.mpvae_contract_nt(_ptr(a), _ptr(b), _ptr(out), M, N, K, engine, _ptr(ws), nbytes, stream),
+                   "mpvae_contract_nt")
+    return out
+
+
+def contract_tn(a, b, engine=0):
+    """C[N1,N2] = A[M,N1]^T . B[M,N2] through the library (g_R = gx^T . noise)."""
+    lib = _lib.lib()
+    a, b = a.contiguous(), b.contiguous()
+    M, N1 = a.shape
+    N2 = b.shape[1]
+    assert b.shape[0] == M and a.is_cuda and b.is_cuda and a.dtype == b.dtype == torch.float32
+    out = torch.empty((N1, N2), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        nbytes = int(lib.mpvae_contract_workspace_bytes(M, N1, N2, engine))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
+        stream = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
+        _lib.check(lib.mpvae_contract_tn(_ptr(a), _ptr(b), _ptr(out), M, N1, N2, engine, _ptr(ws), nbytes, stream),
+                   "mpvae_contract_tn")
+    return out

@@ -1,0 +1,168 @@
+"""GPU tests of the individual kernels behind the C-ABI: Philox noise, the contraction engines, and
+size-independent properties of the full path at BASELINE.json's large shapes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import probit_elbo_oracle as orc
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+# ----------------------------------------------------------------------------- Philox noise
+def philox4x32_10_numpy(counter, offset, seed):
+    """Reference Philox4x32-10 (Salmon et al. 2011) in numpy uint64 arithmetic, vectorised over counters."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    mask = np.uint64(0xFFFFFFFF)
+    c = [(counter & mask), (counter >> np.uint64(32)) & mask,
+         np.full_like(counter, offset & 0xFFFFFFFF), np.full_like(counter, (offset >> 32) & 0xFFFFFFFF)]
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(M0) * c[0]
+        p1 = np.uint64(M1) * c[2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & mask
+        hi1, lo1 = p1 >> np.uint64(32), p1 & mask
+        c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+        k0 = (k0 + np.uint64(W0)) & mask
+        k1 = (k1 + np.uint64(W1)) & mask
+    return c
+
+
+def philox_normals_numpy(n, seed, offset):
+    ctr = np.arange((n + 3) // 4, dtype=np.uint64)
+    r = philox4x32_10_numpy(ctr, offset, seed)
+    def bm(a, b):
+        u1 = ((a >> np.uint64(9)).astype(np.float64) + 0.5) / 8388608.0
+        u2 = ((b >> np.uint64(9)).astype(np.float64) + 0.5) / 8388608.0
+        rad = np.sqrt(-2.0 * np.log(u1))
+        return rad * np.cos(2 * np.pi * u2), rad * np.sin(2 * np.pi * u2)
+    n0, n1 = bm(r[0], r[1])
+    n2, n3 = bm(r[2], r[3])
+    return np.stack([n0, n1, n2, n3], axis=1).reshape(-1)[:n]
+
+
+def test_philox_matches_numpy_reference():
+    from mpvae_b200.probit import philox_normal
+    S, B, Z = 3, 7, 13
+    got = philox_normal(S, B, Z, seed=1234567890123, offset=5, device=DEV).cpu().numpy()
+    want = philox_normals_numpy(S * B * Z, 1234567890123, 5).reshape(S, B, Z)
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-6)
+
+
+def test_philox_is_shard_invariant_and_deterministic():
+    """Rows [row0, row0+B) of a global draw equal the same rows drawn on one device."""
+    from mpvae_b200.probit import philox_normal
+    S, Bg, Z = 10, 64, 38
+    full = philox_normal(S, Bg, Z, seed=99, offset=3, device=DEV)
+    again = philox_normal(S, Bg, Z, seed=99, offset=3, device=DEV)
+    assert torch.equal(full, again)
+    for row0, B in ((0, 16), (16, 16), (40, 24), (63, 1)):
+        part = philox_normal(S, B, Z, seed=99, offset=3, device=DEV, global_batch=Bg, row0=row0)
+        assert torch.equal(part, full[:, row0:row0 + B, :]), (row0, B)
+    other = philox_normal(S, Bg, Z, seed=99, offset=4, device=DEV)
+    assert not torch.equal(full, other)
+
+
+def test_philox_moments():
+    from mpvae_b200.probit import philox_normal
+    x = philox_normal(10, 1024, 1001, seed=7, device=DEV).double()
+    n = x.numel()
+    assert abs(x.mean().item()) < 5 / np.sqrt(n)
+    assert abs(x.var().item() - 1.0) < 5 * np.sqrt(2.0 / n)
+    assert abs((x ** 3).mean().item()) < 5 * np.sqrt(15.0 / n)
+    assert abs((x ** 4).mean().item() - 3.0) < 5 * np.sqrt(96.0 / n)
+    assert x.abs().max().item() < 6.0
+    # consecutive elements are uncorrelated
+    flat = x.flatten()
+    assert abs((flat[:-1] * flat[1:]).mean().item()) < 5 / np.sqrt(n)
+
+
+def test_philox_noise_fed_to_oracle():
+    """Philox mode is validated by dumping its noise and giving the same tensor to the oracle."""
+    from mpvae_b200 import synth
+    from mpvae_b200.mpvae import compute_loss
+    from mpvae_b200.probit import philox_normal
+    L, Z, B, S = 38, 38, 64, 10
+    inp = synth.loss_inputs(L, Z, B, S, seed=21, with_noise=False)
+    args = orc.make_args(L, Z, n_train_sample=S, noise_seed=4242, noise_offset=17)
+    t = {k: torch.from_numpy(v).to(DEV).requires_grad_(k != "y") for k, v in inp.items()}
+    out = compute_loss(t["y"], t["fe_out"], t["fe_mu"], t["fe_logvar"], t["fx_out"], t["fx_mu"], t["fx_logvar"],
+                       t["r_sqrt_sigma"], args)
+    out[0].backward()
+    noise = philox_normal(S, B, Z, seed=4242, offset=17, device=DEV).cpu()
+    ref, ref_g = orc.probit_elbo_with_grads({k: torch.from_numpy(v) for k, v in inp.items()}, noise, 0.5, 10.0)
+    for i, k in enumerate(H.SCALAR_KEYS):
+        assert H.rel_err(out[i].item(), getattr(ref, k).item()) <= 1e-5, k
+    for k in H.GRAD_KEYS:
+        assert H.rel_err(t[k].grad.cpu().numpy(), ref_g[k].numpy()) <= 1e-5, k
+
+
+# ----------------------------------------------------------------------------- contraction engines
+@pytest.mark.parametrize("M,N,K", [(1280, 38, 38), (1280, 14, 14), (12800, 81, 81), (333, 130, 5), (1280, 983, 10),
+                                   (1280, 983, 983), (257, 129, 127), (64, 3993, 10)])
+def test_contract_nt_fma(M, N, K):
+    from mpvae_b200.probit import contract_nt
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
+    a = torch.randn(M, K, generator=g)
+    b = torch.randn(N, K, generator=g) * 0.1
+    got = contract_nt(a.to(DEV), b.to(DEV), engine=1).cpu()
+    want = (a.double() @ b.double().T)
+    assert H.rel_err(got.numpy(), want.numpy()) <= 2e-6
+
+
+@pytest.mark.parametrize("M,N1,N2", [(1280, 38, 38), (1280, 14, 14), (333, 130, 5), (10240, 983, 10),
+                                     (1280, 983, 983), (257, 129, 127), (10240, 3993, 10)])
+def test_contract_tn_fma(M, N1, N2):
+    from mpvae_b200.probit import contract_tn
+    g = torch.Generator(device="cpu").manual_seed(M * 3 + N1)
+    a = torch.randn(M, N1, generator=g) * 0.01
+    b = torch.randn(M, N2, generator=g)
+    got = contract_tn(a.to(DEV), b.to(DEV), engine=1)
+    again = contract_tn(a.to(DEV), b.to(DEV), engine=1)
+    assert torch.equal(got, again)          # split-K partials are reduced in a fixed order
+    want = (a.double().T @ b.double())
+    assert H.rel_err(got.cpu().numpy(), want.numpy()) <= 5e-6
+
+
+# ----------------------------------------------------------------------------- full-size properties
+def _run(inp, noise, args, scale=None, rows=None):
+    from mpvae_b200.mpvae import compute_loss
+    sel = (lambda v: v) if rows is None else (lambda v: v[rows])
+    t = {k: (torch.from_numpy(sel(v)) if k != "r_sqrt_sigma" else torch.from_numpy(v)).to(DEV).requires_grad_(k != "y")
+         for k, v in inp.items()}
+    nz = torch.from_numpy(noise if rows is None else noise[:, rows]).to(DEV)
+    out = compute_loss(t["y"], t["fe_out"], t["fe_mu"], t["fe_logvar"], t["fx_out"], t["fx_mu"], t["fx_logvar"],
+                       t["r_sqrt_sigma"], args, noise=nz)
+    (out[0] * (1.0 if scale is None else scale)).backward()
+    return out, {k: t[k].grad for k in H.GRAD_KEYS}
+
+
+@pytest.mark.parametrize("name,L,Z,B", [("eurlex_z10", 3993, 10, 1024), ("delicious", 983, 983, 128)])
+def test_full_size_properties(name, L, Z, B):
+    """BASELINE.json full sizes, through properties that need no O(L^2) oracle:
+      * every loss term is a mean over rows => halves recombine: term = (term_A + term_B) / 2, grads likewise
+      * the backward is linear in the upstream cotangent
+      * predictions are probabilities inside the clamp [eps/2, 1 - eps/2]"""
+    from mpvae_b200 import synth
+    S = 10
+    inp = synth.loss_inputs(L, Z, B, S, seed=3, label_rate=20.0 / L)
+    noise = inp.pop("noise")
+    args = orc.make_args(L, Z, n_train_sample=S)
+    full, g_full = _run(inp, noise, args)
+    half = B // 2
+    a, g_a = _run(inp, noise, args, rows=slice(0, half))
+    b, g_b = _run(inp, noise, args, rows=slice(half, B))
+    for i in range(6):
+        assert H.rel_err(full[i].item(), 0.5 * (a[i].item() + b[i].item())) <= 2e-6, i
+    assert torch.equal(full[6][:half], a[6]) and torch.equal(full[6][half:], b[6])
+    recombined = 0.5 * (g_a["r_sqrt_sigma"] + g_b["r_sqrt_sigma"])
+    assert H.rel_err(g_full["r_sqrt_sigma"].cpu().numpy(), recombined.cpu().numpy()) <= 1e-5
+    assert H.rel_err(g_full["fe_out"][:half].cpu().numpy(), 0.5 * g_a["fe_out"].cpu().numpy()) <= 1e-6
+    _, g_scaled = _run(inp, noise, args, scale=-2.5)
+    for k in H.GRAD_KEYS:
+        assert H.rel_err(g_scaled[k].cpu().numpy(), -2.5 * g_full[k].cpu().numpy()) <= 2e-6, k
+    p = full[6]
+    assert float(p.min()) >= 5e-7 * 0.99 and float(p.max()) <= 1.0 - 4.7e-7
+    assert all(torch.isfinite(g).all() for g in g_full.values())
