@@ -91,12 +91,13 @@ def test_philox_noise_fed_to_oracle():
     out = compute_loss(t["y"], t["fe_out"], t["fe_mu"], t["fe_logvar"], t["fx_out"], t["fx_mu"], t["fx_logvar"],
                        t["r_sqrt_sigma"], args)
     out[0].backward()
-    noise = philox_normal(S, B, Z, seed=4242, offset=17, device=DEV).cpu()
-    ref, ref_g = orc.probit_elbo_with_grads({k: torch.from_numpy(v) for k, v in inp.items()}, noise, 0.5, 10.0)
+    noise = philox_normal(S, B, Z, seed=4242, offset=17, device=DEV)
+    # same-device oracle (the reference's torch ops on cuda): strict bar, see test_parity_gpu.py
+    ref, ref_g = orc.probit_elbo_with_grads({k: torch.from_numpy(v).to(DEV) for k, v in inp.items()}, noise, 0.5, 10.0)
     for i, k in enumerate(H.SCALAR_KEYS):
         assert H.rel_err(out[i].item(), getattr(ref, k).item()) <= 1e-5, k
     for k in H.GRAD_KEYS:
-        assert H.rel_err(t[k].grad.cpu().numpy(), ref_g[k].numpy()) <= 1e-5, k
+        assert H.rel_err(t[k].grad.cpu().numpy(), ref_g[k].cpu().numpy()) <= 1e-5, k
 
 
 # ----------------------------------------------------------------------------- contraction engines
