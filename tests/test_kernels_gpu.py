@@ -167,3 +167,46 @@ def test_full_size_properties(name, L, Z, B):
     p = full[6]
     assert float(p.min()) >= 5e-7 * 0.99 and float(p.max()) <= 1.0 - 4.7e-7
     assert all(torch.isfinite(g).all() for g in g_full.values())
+
+
+# ----------------------------------------------------------------------------- tcgen05 3xTF32 engine
+def _tc_report(**kw):
+    import json, os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "tc_report.jsonl")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "a") as f:
+            f.write(json.dumps(kw) + "\n")
+    except OSError:
+        pass
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (128, 256, 64), (256, 512, 256), (300, 500, 200), (1280, 983, 983),
+                                   (10240, 983, 983), (640, 3993, 3993)])
+def test_contract_nt_tensor(M, N, K):
+    """3xTF32 on tcgen05 must agree with the exact product to fp32-SGEMM accuracy (parity needs ~1e-6)."""
+    from mpvae_b200.probit import contract_nt
+    g = torch.Generator(device="cpu").manual_seed(M + 3 * N + 7 * K)
+    a = torch.randn(M, K, generator=g)
+    b = (torch.rand(N, K, generator=g) - 0.5) * 0.06
+    got = contract_nt(a.to(DEV), b.to(DEV), engine=2)
+    want = a.to(DEV).double() @ b.to(DEV).double().T
+    fma = contract_nt(a.to(DEV), b.to(DEV), engine=1)
+    err = ((got.double() - want).abs().max() / want.abs().max()).item()
+    err_fma = ((fma.double() - want).abs().max() / want.abs().max()).item()
+    _tc_report(test="nt", M=M, N=N, K=K, err=err, err_fma=err_fma)
+    assert err <= 3e-6, (err, err_fma)
+
+
+@pytest.mark.parametrize("M,N1,N2", [(32, 128, 256), (64, 128, 256), (256, 256, 512), (200, 300, 500), (1280, 983, 983),
+                                     (10240, 983, 983), (1280, 3993, 3993)])
+def test_contract_tn_tensor(M, N1, N2):
+    from mpvae_b200.probit import contract_tn
+    g = torch.Generator(device="cpu").manual_seed(M + 3 * N1 + 7 * N2)
+    a = torch.randn(M, N1, generator=g) * 0.01
+    b = torch.randn(M, N2, generator=g)
+    got = contract_tn(a.to(DEV), b.to(DEV), engine=2)
+    want = a.to(DEV).double().T @ b.to(DEV).double()
+    err = ((got.double() - want).abs().max() / want.abs().max()).item()
+    _tc_report(test="tn", M=M, N1=N1, N2=N2, err=err)
+    assert err <= 3e-6, err
