@@ -29,6 +29,9 @@ follows the same ATen kernels the reference would hit:
                                   but every reduction accumulated in fp64: the
                                   "exact-sum" truth used to bound summation-order
                                   noise at large L
+  * `probit_elbo(..., contract=torch.float64)`
+                                  the product noise.R^T accumulated in fp64 and rounded once (the exact
+                                  contraction; bounds the fp32 SGEMM's own rounding at Z >= 983)
   * `probit_elbo(..., dtype=torch.float64)`
                                   everything in fp64 (error budgeting)
 
@@ -144,7 +147,8 @@ def bernoulli_log_mean_exp(E, y, accum=None):
 def probit_elbo(input_label, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r_sqrt_sigma,
                 noise, nll_coeff, c_coeff, *, ranking: str = "pairwise",
                 dtype: torch.dtype = torch.float32,
-                accum: Optional[torch.dtype] = None) -> ElboTerms:
+                accum: Optional[torch.dtype] = None,
+                contract: Optional[torch.dtype] = None) -> ElboTerms:
     """Restatement of compute_loss (mpvae.py:145-210) with the noise of :162 as an argument.
 
     The dead code at mpvae.py:150-153 (sigma / covariance, never used) is not reproduced.
@@ -158,8 +162,13 @@ def probit_elbo(input_label, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar,
     noise = noise.to(dev).to(dtype)
     basis = r_sqrt_sigma.T.float().to(dev).to(dtype) if dtype == torch.float32 \
         else r_sqrt_sigma.T.to(dev).to(dtype)                        # :165
-    sample_r = torch.tensordot(noise, basis, dims=1) + fe_out        # :168
-    sample_r_x = torch.tensordot(noise, basis, dims=1) + fx_out      # :170
+    if contract is not None:
+        # exact-contraction truth: noise.R^T accumulated in `contract` (fp64), rounded once to the working dtype
+        nr = torch.tensordot(noise.to(contract), basis.to(contract), dims=1).to(dtype)
+        sample_r, sample_r_x = nr + fe_out, nr + fx_out
+    else:
+        sample_r = torch.tensordot(noise, basis, dims=1) + fe_out        # :168
+        sample_r_x = torch.tensordot(noise, basis, dims=1) + fx_out      # :170
     E = clamped_probit(sample_r, eps1)                               # :177
     E_x = clamped_probit(sample_r_x, eps1)                           # :180
 

@@ -54,11 +54,15 @@ def rel_err(a, b):
     return 0.0 if num == 0 else num / max(den, 1e-300)
 
 
-def threshold_mismatches(p, q, thresholds=THRESHOLDS):
-    """evals.py:201-202 semantics: pred = (p >= t).  Returns number of differing thresholded cells."""
+def threshold_mismatches(p, q, thresholds=THRESHOLDS, tie=0.0):
+    """evals.py:201-202 semantics: pred = (p >= t).  Number of differing thresholded cells whose reference
+    score is further than `tie` from the threshold (tie = 0: every differing cell counts)."""
     bad = 0
     for t in thresholds:
-        bad += int(np.sum((p >= t) != (q >= t)))
+        diff = (p >= t) != (q >= t)
+        if tie > 0:
+            diff &= np.abs(q.astype(np.float64) - t) > tie
+        bad += int(np.sum(diff))
     return bad
 
 
@@ -77,3 +81,12 @@ def topk_mismatches(p, q, ks=(1, 3, 5), tie=2.5e-7):
         real = np.abs(q[rows, a].astype(np.float64) - q[rows, b].astype(np.float64)) > tie
         bad += int(np.sum(differ & real))
     return bad
+
+
+def rel_err_l2(a, b):
+    """||a-b||_2 / ||b||_2 (Frobenius): averages over rows instead of reporting the single worst cell."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    den = float(np.sqrt(np.sum(b * b)))
+    num = float(np.sqrt(np.sum((a - b) ** 2)))
+    return 0.0 if num == 0 else num / max(den, 1e-300)

@@ -203,13 +203,54 @@ def test_large_label_sets_against_exact_sum_oracle(name, L, Z, B):
     S = 10
     inp = synth.loss_inputs(L, Z, B, S, seed=31, sigma=1.0, label_rate=20.0 / L)
     noise = inp.pop("noise")
-    got_o, got_g = run_cuda(inp, noise, 0.5, 10.0)
+    from mpvae_b200 import _lib
+    # CUDA-core contraction: same fp32 FMA chain as the reference's SGEMM, so the exact-sum oracle is the 1e-5 bar
+    got_o, got_g = run_cuda(inp, noise, 0.5, 10.0, flags=_lib.FLAG_CONTRACT_FMA)
     ex_o, ex_g = run_oracle(inp, noise, 0.5, 10.0, device="cuda:0", ranking="factorised", accum=torch.float64)
     errs = compare("exact_sum/" + name, got_o, got_g, ex_o, ex_g, tol_grad=1e-5, tol_grad_r=2e-5)
     f32_o, f32_g = run_oracle(inp, noise, 0.5, 10.0, device="cuda:0", ranking="factorised")
     noise_floor = {k: H.rel_err(f32_g[k], ex_g[k]) for k in ex_g}
     report(tag="fp32_oracle_vs_exact_sum/" + name, **{k: float(v) for k, v in noise_floor.items()})
     assert errs["g_fe_out"] <= max(1e-5, noise_floor["fe_out"])
+
+
+@pytest.mark.parametrize("name,L,Z,B", [("delicious", 983, 983, 16), ("delicious_b128", 983, 983, 128),
+                                        ("eurlex_b16", 3993, 3993, 16)])
+def test_tensor_engine_is_as_accurate_as_the_reference(name, L, Z, B):
+    """Dense regime (Z >= 128): noise.R^T runs as 3xTF32 on tcgen05, whose rounding differs from an fp32 SGEMM's
+    (it is ~2x closer to the exact product).  At these sizes a 1e-6 perturbation of x moves softmax_s(lp) -- and
+    with it every gradient -- by ~sqrt(L) * 1e-6 * |dll/dx| ~ 1e-4, for ANY implementation including the
+    reference's own cuBLAS path.  So the bar is: forward terms within 1e-5 of the reference path, decisions equal
+    away from ties, and gradients at least as close to the exact-contraction truth (fp64 product, exact sums, fp32
+    cell arithmetic) as the reference's own fp32 path is."""
+    from mpvae_b200 import _lib, synth
+    S = 10
+    inp = synth.loss_inputs(L, Z, B, S, seed=32, sigma=1.0, label_rate=20.0 / L)
+    noise = inp.pop("noise")
+    got_o, got_g = run_cuda(inp, noise, 0.5, 10.0, flags=_lib.FLAG_CONTRACT_TENSOR)
+    ref_o, ref_g = run_oracle(inp, noise, 0.5, 10.0, device="cuda:0", ranking="factorised")
+    tru_o, tru_g = run_oracle(inp, noise, 0.5, 10.0, device="cuda:0", ranking="factorised", accum=torch.float64,
+                              contract=torch.float64)
+    rec = {}
+    for k in H.SCALAR_KEYS:
+        rec[k] = H.rel_err(got_o[k], ref_o[k])
+        assert rec[k] <= 1e-5, (k, rec[k])
+    dp = float(np.max(np.abs(got_o["indiv_prob"].astype(np.float64) - ref_o["indiv_prob"])))
+    rec["indiv_prob_abs"] = dp
+    assert dp <= 5e-6
+    # decisions may only differ where the reference score sits within the two paths' distance of a threshold
+    assert H.threshold_mismatches(got_o["indiv_prob"], ref_o["indiv_prob"], tie=2 * dp + 1e-7) == 0
+    rec["threshold_ties"] = H.threshold_mismatches(got_o["indiv_prob"], ref_o["indiv_prob"])
+    # Frobenius-relative distance to the truth (the max-norm is decided by one saturated cell of one row and
+    # fluctuates by 10x between two equally accurate implementations; it is recorded, and capped at 2e-3)
+    for k in H.GRAD_KEYS:
+        mine, theirs = H.rel_err_l2(got_g[k], tru_g[k]), H.rel_err_l2(ref_g[k], tru_g[k])
+        rec["g_" + k], rec["ref_" + k] = mine, theirs
+        rec["gmax_" + k], rec["refmax_" + k] = H.rel_err(got_g[k], tru_g[k]), H.rel_err(ref_g[k], tru_g[k])
+    report(tag="tensor_vs_truth/" + name, **{k: float(v) for k, v in rec.items()})
+    for k in H.GRAD_KEYS:
+        assert rec["g_" + k] <= max(1e-5, 2.0 * rec["ref_" + k]), (k, rec["g_" + k], rec["ref_" + k])
+        assert rec["gmax_" + k] <= 2e-3, (k, rec["gmax_" + k])
 
 
 def test_upstream_on_every_output():
