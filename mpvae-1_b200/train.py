@@ -1,0 +1,188 @@
+"""Data-parallel training step: the loop body of the reference's train.py:103-129 (and its fairness twin,
+fairsoft_train.py:47-146) as one object, one process per GPU.
+
+    zero_grad -> batch shard -> VAE.forward -> compute_loss -> [extra regulariser] -> backward
+              -> all-reduce(flat fp32 bucket: g_R || every MLP gradient) -> clip_grad_norm_ -> Adam -> StepLR
+
+Batch rows are the unit that shards (every loss term is a mean over rows, mpvae.py:147,122,190): rank r owns
+rows [r*B/G, (r+1)*B/G) of the global batch, gradients are averaged, and every rank then applies the identical
+clip + Adam update, so parameters stay replicated without a broadcast.  The one exchange per step is an NCCL
+all-reduce over NVLink; the g_R segment is launched from an autograd hook as soon as the probit backward has
+produced it, so it overlaps the MLP backward.  Noise is Philox keyed by the GLOBAL row index, which makes the
+result independent of the world size (an external (S, B_global, Z) noise tensor is sliced instead).
+
+The reference has no distributed code at all; with world_size == 1 this object is exactly
+its single-GPU step.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Callable, NamedTuple, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+
+class StepOutput(NamedTuple):
+    total_loss: torch.Tensor
+    nll_loss: torch.Tensor
+    nll_loss_x: torch.Tensor
+    c_loss: torch.Tensor
+    c_loss_x: torch.Tensor
+    kl_loss: torch.Tensor
+    indiv_prob: torch.Tensor          # this rank's rows
+    indiv_prob_label: torch.Tensor
+    grad_norm: torch.Tensor
+    stepped: bool
+
+
+def shard_rows(n_rows: int, rank: int, world: int):
+    """Contiguous, near-equal row shards: rank r gets [lo, hi).  (Equal shards when world | n_rows.)"""
+    base, rem = divmod(n_rows, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class GradBucket:
+    """One flat fp32 buffer holding [g_R || all fp32 parameter gradients]; .grad of every fp32 parameter is a view
+    into it (autograd accumulates in place), so the all-reduce needs no gather / scatter copies."""
+
+    def __init__(self, r_shadow: Optional[torch.Tensor], params):
+        self.params = [p for p in params if p.requires_grad and p.dtype == torch.float32]
+        sizes = ([r_shadow.numel()] if r_shadow is not None else []) + [p.numel() for p in self.params]
+        dev = (r_shadow if r_shadow is not None else self.params[0]).device
+        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        off = 0
+        self.r_view = None
+        if r_shadow is not None:
+            self.r_view = self.flat[off:off + r_shadow.numel()].view_as(r_shadow)
+            off += r_shadow.numel()
+        self.r_numel = off
+        self.views = []
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    def attach(self, r_shadow):
+        self.flat.zero_()
+        if r_shadow is not None:
+            r_shadow.grad = self.r_view
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+
+class DataParallelStep:
+    """`step(input_label, input_feat)` = one training step on the GLOBAL batch, this rank computing its shard."""
+
+    def __init__(self, model: nn.Module, optimizer, scheduler, args, *, clip_norm: float = 100.0,
+                 skip_nonfinite: bool = False, group=None, loss_fn: Optional[Callable] = None,
+                 regulariser: Optional[Callable] = None):
+        self.model, self.optimizer, self.scheduler = model, optimizer, scheduler
+        self.args = copy.copy(args)
+        self.clip_norm = clip_norm                 # 100 in train.py:126, 10 in fairsoft_train.py:141
+        self.skip_nonfinite = skip_nonfinite       # has_finite_grad guard of fairsoft_train.py:142
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        if loss_fn is None:
+            from .mpvae import compute_loss as loss_fn
+        self.loss_fn = loss_fn
+        self.regulariser = regulariser             # callable(StepOutput-like 8-tuple, row slice) -> scalar tensor
+        self.step_no = 0
+        r = getattr(model, "r_sqrt_sigma", None)
+        self.r_param = r if (r is not None and r.requires_grad) else None
+        self.r_shadow = None
+        if self.r_param is not None:
+            # fp32 working copy of the fp64 Parameter (the reference casts per call, mpvae.py:165); its gradient
+            # lives in the bucket, and is cast back to fp64 for the optimizer after the all-reduce
+            self.r_shadow = self.r_param.detach().float().requires_grad_(True)
+        others = [p for n, p in model.named_parameters() if p is not self.r_param]
+        self.bucket = GradBucket(self.r_shadow, others)
+        self._pending = []
+        if self.world > 1 and self.r_shadow is not None:
+            self.r_shadow.register_post_accumulate_grad_hook(self._reduce_r_early)
+
+    # -- collectives --------------------------------------------------------------------------------------
+    def _reduce_r_early(self, _):
+        """Fires as soon as the probit backward has written g_R: overlap its all-reduce with the MLP backward."""
+        seg = self.bucket.flat[:self.bucket.r_numel]
+        self._pending.append(dist.all_reduce(seg, group=self.group, async_op=True))
+
+    def _finish_reduce(self):
+        if self.world == 1:
+            return
+        start = self.bucket.r_numel if self._pending else 0
+        seg = self.bucket.flat[start:]
+        if seg.numel():
+            self._pending.append(dist.all_reduce(seg, group=self.group, async_op=True))
+        for w in self._pending:
+            w.wait()
+        self._pending = []
+        self.bucket.flat.div_(self.world)
+
+    # -- the step -------------------------------------------------------------------------------------------
+    def step(self, input_label: torch.Tensor, input_feat: torch.Tensor, noise: Optional[torch.Tensor] = None,
+             r_override: Optional[torch.Tensor] = None) -> StepOutput:
+        """`input_label` (B, L) and `input_feat` (B, F) are the GLOBAL batch (train.py:106-111); every rank slices
+        its rows.  `noise`, if given, is the global (S, B, Z) tensor (validation mode).  `r_override` is the
+        fresh non-trainable R of residue_sigma == 'random' (train.py:120-122)."""
+        args = self.args
+        n_rows = input_label.shape[0]
+        lo, hi = shard_rows(n_rows, self.rank, self.world)
+        y, x = input_label[lo:hi], input_feat[lo:hi]
+        args.dp_global_batch, args.dp_row0 = n_rows, lo
+        if getattr(args, "noise_offset_auto", True):
+            args.noise_offset = self.step_no         # same Philox offset on every rank
+        if self.r_shadow is not None:
+            with torch.no_grad():
+                self.r_shadow.copy_(self.r_param)
+        self.bucket.attach(self.r_shadow)             # optimizer.zero_grad() of train.py:103 (in place, one memset)
+
+        label_out, label_mu, label_logvar, feat_out, feat_mu, feat_logvar = self.model(y, x)
+        r = r_override if r_override is not None else (self.r_shadow if self.r_shadow is not None
+                                                        else self.model.r_sqrt_sigma)
+        kw = {} if noise is None else {"noise": noise[:, lo:hi]}
+        out = self.loss_fn(y, label_out, label_mu, label_logvar, feat_out, feat_mu, feat_logvar, r, args, **kw)
+        total = out[0]
+        if self.regulariser is not None:
+            extra = self.regulariser(out, slice(lo, hi))
+            if extra is not None:
+                total = total + extra
+        # every term is a mean over this rank's rows; weight by the shard size so unequal shards still average right
+        weight = (hi - lo) * self.world / max(n_rows, 1)
+        (total * weight if weight != 1.0 else total).backward()
+        self._finish_reduce()
+        if self.r_param is not None:
+            self.r_param.grad = self.bucket.r_view.double()
+        params = [p for p in self.model.parameters() if p.grad is not None]
+        grad_norm = nn.utils.clip_grad_norm_(params, self.clip_norm)
+        stepped = True
+        if self.skip_nonfinite and not bool(torch.isfinite(grad_norm)):
+            stepped = False
+        if stepped:
+            self.optimizer.step()
+            if self.scheduler is not None:
+                self.scheduler.step()
+        self.step_no += 1
+        scal = [t.detach() for t in out[:6]]
+        if self.world > 1:
+            packed = torch.stack(scal) * ((hi - lo) / max(n_rows, 1))
+            dist.all_reduce(packed, group=self.group)
+            scal = list(packed.unbind(0))
+        return StepOutput(*scal, out[6].detach(), out[7].detach(), grad_norm, stepped)
+
+
+def train_one_epoch(step: DataParallelStep, feats, labels, batch_size: int, order=None):
+    """Epoch driver with the reference's batching (train.py:98-111): int(N/bs)+1 steps, ragged (possibly empty)
+    last batch.  `feats` / `labels` are device tensors (kept resident: SURVEY 8f-N4); returns per-step outputs."""
+    n = feats.shape[0]
+    if order is None:
+        order = torch.arange(n, device=feats.device)
+    outs = []
+    for i in range(int(n / float(batch_size)) + 1):
+        idx = order[i * batch_size:min(batch_size * (i + 1), n)]
+        if idx.numel() == 0:
+            continue          # the reference computes NaN losses on the empty batch and steps on them; we skip it
+        outs.append(step.step(labels[idx], feats[idx]))
+    return outs
