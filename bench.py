@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=None, help="rows per GPU (default: the workload's)")
     ap.add_argument("--cpu-rows", type=int, default=None, help="rows of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the full-training-step (steps/s) leg")
     ap.add_argument("--engine", default="auto", choices=["auto", "fma", "tensor"])
     return ap.parse_args()
 
@@ -305,6 +306,46 @@ def run_b200(a):
                     "kernel": "contract_nt (noise.R^T, mpvae.py:168)", "kernel_ms": t_k * 1e3,
                     "peak_basis": f"{peaks['_source']} HBM copy bandwidth", "algorithmic_bytes_per_launch": bytes_alg}
 
+    # ---- full training step (train.py:103-129: VAE fwd -> loss -> bwd -> all-reduce -> clip -> Adam -> StepLR) ----
+    train = None
+    if not a.no_train_step:
+        import numpy as np
+        from types import SimpleNamespace
+        from mpvae_b200.train import DataParallelStep
+        margs = SimpleNamespace(feature_dim=sh.feature_dim, label_dim=L, latent_dim=50, z_dim=Z, keep_prob=0.5,
+                                scale_coeff=1.0, residue_sigma="", n_train_sample=S, n_test_sample=S, mode="train",
+                                nll_coeff=0.5, c_coeff=10.0, mpvae_flags=flags, noise_seed=99)
+        np.random.seed(4)
+        torch.manual_seed(0)
+        vae = M.VAE(margs).to(dev)
+        opt = torch.optim.Adam(vae.parameters(), lr=1e-3, weight_decay=1e-5)
+        sched = torch.optim.lr_scheduler.StepLR(opt, 1000, 0.5)
+        stepper = DataParallelStep(vae, opt, sched, margs, clip_norm=100.0)
+        rng = np.random.RandomState(5)
+        xg = torch.from_numpy(synth.features(Bg, sh.feature_dim, rng)).to(dev)
+        yg = torch.from_numpy(synth.labels(Bg, L, sh.label_rate, rng)).to(dev)
+        for _ in range(3):
+            stepper.step(yg, xg)
+        barrier()
+        k_train = max(3, min(a.steps, 20))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall = time.perf_counter()
+        e0.record()
+        for _ in range(k_train):
+            out_t = stepper.step(yg, xg)
+        e1.record()
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall
+        t_dev = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        train = {"steps_per_s": k_train / (t_dev.item() * 1e-3), "ms_per_step": t_dev.item() / k_train,
+                 "wall_ms_per_step": t_wall * 1e3 / k_train, "steps": k_train, "global_batch": Bg,
+                 "params": int(sum(p.numel() for p in vae.parameters())), "loss": float(out_t.total_loss),
+                 "what": "zero_grad, VAE fwd (torch/cuBLAS), probit ELBO fwd+bwd (this library), MLP bwd, "
+                         "grad all-reduce, clip_grad_norm_(100), Adam(wd=1e-5), StepLR; per-step host metrics excluded"}
+        del vae, opt, stepper
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -323,7 +364,8 @@ def run_b200(a):
         "e2e": {"value": units / (total_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": bi, "d2h_bytes_per_step": 4,
                 "ms_per_step": total_e2e / a.steps},
         "gpu_launches": int(launches),
-        "steps_per_s": a.steps / (total_ms * 1e-3),
+        "loss_steps_per_s": a.steps / (total_ms * 1e-3),
+        "train_step": train,
         "roofline": roof,
     }
     if not a.no_cpu_baseline:

@@ -22,6 +22,7 @@
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA), tmem full/empty mbarriers (MMA <-> promotion).
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc.h"
@@ -35,7 +36,12 @@ constexpr int A_BYTES = BM * BK * 4;                     // 16 KiB per (hi | lo)
 constexpr int B_BYTES = BN * BK * 4;                     // 32 KiB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 96 KiB
 constexpr int EPI_BYTES = 0;
-constexpr int KC = 4;                                    // k-blocks accumulated in tensor memory per chunk
+constexpr int kDefaultKC = 2;                             // k-blocks accumulated in tensor memory per chunk
+// The tensor core truncates (toward zero) when it adds into the fp32 accumulator, which shrinks a chunk sum by
+// a measured 1.85e-7 of its value per k-block (12 MMAs of K=8; profiles/r1_tc_chunk_experiment.txt).  The
+// promotion multiplies the chunk by (1 + this * k-blocks) to take the systematic part out again; what is left
+// is random and ~2x below an fp32 SGEMM's own rounding.
+constexpr float kTruncBiasPerKBlock = 1.85e-7f;
 constexpr int kEpiWarps = 16;                            // 4 TMEM lane quadrants x 4 column quarters
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
@@ -122,7 +128,7 @@ __device__ __forceinline__ constexpr uint32_t umma_idesc() {
 template <bool MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   float* __restrict__ C, int Mc, int Nc, int K, int ldc, int tiles_m, int tiles_n) {
+                   float* __restrict__ C, int Mc, int Nc, int K, int ldc, int tiles_m, int tiles_n, int kc) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;             // 128B-swizzled tiles need 1024 B alignment
@@ -200,11 +206,11 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             int stage = 0, buf = 0;
             uint32_t phase = 0, bphase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                for (int kb0 = 0; kb0 < num_kb; kb0 += KC) {
+                for (int kb0 = 0; kb0 < num_kb; kb0 += kc) {
                     mbar_wait(tempty_bar(buf), bphase ^ 1u);     // promotion warps have drained this TMEM buffer
                     tc_fence_after();
                     const uint32_t d = tmem_base + (uint32_t)(buf * BN);
-                    const int kb1 = min(kb0 + KC, num_kb);
+                    const int kb1 = min(kb0 + kc, num_kb);
                     for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
@@ -235,16 +241,18 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         int buf = 0;
         uint32_t bphase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            for (int kb0 = 0; kb0 < num_kb; kb0 += KC) {
+            for (int kb0 = 0; kb0 < num_kb; kb0 += kc) {
                 mbar_wait(tfull_bar(buf), bphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + h * 64);
+                const float unbias = 1.0f + kTruncBiasPerKBlock * (float)(min(kb0 + kc, num_kb) - kb0);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     uint32_t v[16];
                     tmem_ld_32x16(taddr + i * 16, v);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[i * 16 + j] += __uint_as_float(v[j]);   // round-to-nearest promotion
+                    for (int j = 0; j < 16; ++j)   // round-to-nearest promotion
+                        acc[i * 16 + j] = fmaf(__uint_as_float(v[j]), unbias, acc[i * 16 + j]);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -330,6 +338,17 @@ int make_map(CUtensorMap* map, const float* ptr, int cols, int rows, int pitch, 
 
 int pitch_of(int cols) { return ceil_div(cols, 32) * 32; }
 
+// k-blocks per tensor-memory chunk (MPVAE_TC_KC overrides it for accuracy / speed experiments)
+int chunk_kblocks() {
+    static int kc = 0;
+    if (kc == 0) {
+        const char* e = getenv("MPVAE_TC_KC");
+        kc = e ? atoi(e) : kDefaultKC;
+        if (kc < 1) kc = kDefaultKC;
+    }
+    return kc;
+}
+
 int split(const float* src, float* dst, int rows, int cols, int pitch, cudaStream_t stream) {
     const size_t n = (size_t)rows * pitch;
     const int blocks = (int)((n + 255) / 256 < (size_t)(8 * kNumSMs) ? (n + 255) / 256 : 8 * kNumSMs);
@@ -348,7 +367,7 @@ int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc, in
     const int tiles_m = ceil_div(Mc, BM), tiles_n = ceil_div(Nc, BN);
     const int tiles = tiles_m * tiles_n;
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    gemm_3xtf32_kernel<MN><<<grid, kThreads, SMEM_BYTES, stream>>>(a, b, C, Mc, Nc, K, ldc, tiles_m, tiles_n);
+    gemm_3xtf32_kernel<MN><<<grid, kThreads, SMEM_BYTES, stream>>>(a, b, C, Mc, Nc, K, ldc, tiles_m, tiles_n, chunk_kblocks());
     return check_launch("gemm_3xtf32_kernel");
 }
 

@@ -1,0 +1,124 @@
+"""GPU: the callers either side of the hot path -- the training step wrapper (train.py:103-129) and the
+test-time inference loop (test.py:45-77) -- running on the real CUDA loss."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import probit_elbo_oracle as orc
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def yeast_args(**kw):
+    a = SimpleNamespace(feature_dim=103, label_dim=14, latent_dim=50, z_dim=14, keep_prob=0.5, scale_coeff=1.0,
+                        residue_sigma="", n_train_sample=10, n_test_sample=100, mode="train", nll_coeff=0.5,
+                        c_coeff=10.0, batch_size=128, noise_seed=2024)
+    a.__dict__.update(kw)
+    return a
+
+
+def yeast_data(n=1500, seed=0):
+    from mpvae_b200 import synth
+    rng = np.random.RandomState(seed)
+    x = synth.features(n, 103, rng)
+    w = rng.standard_normal((103, 14)).astype(np.float32) * 0.3
+    y = ((x @ w + rng.standard_normal((n, 14)).astype(np.float32)) > 1.0).astype(np.float32)   # learnable labels
+    y[:, 0], y[:, 1] = 1.0, 0.0
+    return torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV)
+
+
+def test_first_step_gradients_match_reference_loop():
+    """One step of DataParallelStep (world 1) == the literal loop body with the oracle loss on the same device."""
+    from mpvae_b200.mpvae import VAE
+    from mpvae_b200.train import DataParallelStep
+    args = yeast_args(keep_prob=0.0)
+    x, y = yeast_data(256)
+    np.random.seed(4); torch.manual_seed(0)
+    ours = VAE(args).to(DEV)
+    twin = VAE(args).to(DEV)
+    twin.load_state_dict(ours.state_dict())
+    opt = torch.optim.SGD(ours.parameters(), lr=0.0)
+    step = DataParallelStep(ours, opt, None, args, clip_norm=1e9)
+    noise = torch.randn(10, 128, 14, device=DEV)
+    torch.manual_seed(7)
+    out = step.step(y[:128], x[:128], noise=noise)
+    torch.manual_seed(7)
+    o = twin(y[:128], x[:128])
+    terms = orc.compute_loss(y[:128], *o, twin.r_sqrt_sigma, args, noise=noise)
+    terms[0].backward()
+    assert H.rel_err(out.total_loss.item(), terms[0].item()) <= 1e-5
+    for (n, p), (_, q) in zip(ours.named_parameters(), twin.named_parameters()):
+        assert p.grad.dtype == q.grad.dtype, n
+        assert H.rel_err(p.grad.cpu().numpy(), q.grad.cpu().numpy()) <= 2e-5, (n, H.rel_err(p.grad.cpu().numpy(), q.grad.cpu().numpy()))
+
+
+def test_training_reduces_the_loss_and_learns():
+    """BASELINE.json configs[1]: yeast-shaped full train loop on 1 GPU (70/20/10 split, a few epochs)."""
+    from mpvae_b200.infer import predict_proba
+    from mpvae_b200.mpvae import VAE
+    from mpvae_b200.train import DataParallelStep, train_one_epoch
+    args = yeast_args()
+    x, y = yeast_data(1500)
+    n_train, n_valid = int(1500 * 0.7), int(1500 * 0.2)
+    np.random.seed(4); torch.manual_seed(0)
+    vae = VAE(args).to(DEV)
+    opt = torch.optim.Adam(vae.parameters(), lr=1e-3, weight_decay=1e-5)
+    sched = torch.optim.lr_scheduler.StepLR(opt, 9 * 5, 0.5)
+    step = DataParallelStep(vae, opt, sched, args, clip_norm=100.0)
+    first = last = None
+    for epoch in range(12):
+        order = torch.randperm(n_train, device=DEV)
+        outs = train_one_epoch(step, x[:n_train], y[:n_train], 128, order)
+        assert len(outs) == 9                       # int(1050/128)+1 steps, ragged last batch of 26 rows
+        mean_total = float(torch.stack([o.total_loss for o in outs]).mean())
+        first = mean_total if first is None else first
+        last = mean_total
+        assert all(torch.isfinite(o.grad_norm) for o in outs)
+    assert last < 0.8 * first, (first, last)
+    args_t = yeast_args(n_test_sample=100)
+    probs, sums = predict_proba(vae, x[n_train:n_train + n_valid], y[n_train:n_train + n_valid], args_t, batch_size=128)
+    assert probs.shape == (n_valid, 14)
+    pred = (probs >= 0.5).float()
+    yy = y[n_train:n_train + n_valid]
+    tp = (pred * yy)[:, 2:].sum()
+    f1 = 2 * tp / (pred[:, 2:].sum() + yy[:, 2:].sum() + 1e-6)
+    assert f1 > 0.3, float(f1)                      # far above chance: the model has learned the synthetic rule
+
+
+def test_inference_path_matches_oracle():
+    """test.py:64-65: no_grad, eval, mode='test' => S = n_test_sample; predictions vs the oracle on the same noise."""
+    from mpvae_b200.infer import predict_proba
+    from mpvae_b200.mpvae import VAE
+    from mpvae_b200.probit import philox_normal
+    args = yeast_args(n_test_sample=100, noise_seed=31, feature_dim=128, label_dim=81, z_dim=81)
+    rng = np.random.RandomState(2)
+    from mpvae_b200 import synth
+    x = torch.from_numpy(synth.features(200, 128, rng)).to(DEV)
+    y = torch.from_numpy(synth.labels(200, 81, 0.1, rng)).to(DEV)
+    np.random.seed(4); torch.manual_seed(0)
+    vae = VAE(args).to(DEV)
+    probs, _ = predict_proba(vae, x, y, args, batch_size=128)
+    # replay: same model outputs (eval mode is deterministic up to randn_like -> reseed), same Philox noise
+    vae.eval()
+    got = []
+    with torch.no_grad():
+        for i, (a, b) in enumerate(((0, 128), (128, 200))):
+            noise = philox_normal(100, b - a, 81, seed=31, offset=i, device=DEV, global_batch=200, row0=a)
+            torch.manual_seed(100 + i)
+            o = vae(y[a:b], x[a:b])
+            t_args = yeast_args(n_test_sample=100, mode="test", label_dim=81, z_dim=81)
+            ref = orc.compute_loss(y[a:b], *o, vae.r_sqrt_sigma, t_args, noise=noise)
+            torch.manual_seed(100 + i)
+            args_i = yeast_args(n_test_sample=100, mode="test", noise_seed=31, noise_offset=i, dp_global_batch=200,
+                                dp_row0=a, label_dim=81, z_dim=81)
+            from mpvae_b200.mpvae import compute_loss
+            mine = compute_loss(y[a:b], *vae(y[a:b], x[a:b]), vae.r_sqrt_sigma, args_i)
+            assert H.threshold_mismatches(mine[6].cpu().numpy(), ref.indiv_prob.cpu().numpy()) == 0
+            assert H.rel_err(mine[0].item(), ref.total_loss.item()) <= 1e-5
+            got.append(mine[6])
+    assert probs.shape == (200, 81)
+    assert float(probs.min()) > 0 and float(probs.max()) < 1
