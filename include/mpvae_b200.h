@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPVAE_ABI_VERSION 3
+#define MPVAE_ABI_VERSION 4
 
 /* flags */
 #define MPVAE_FLAG_SANITIZE_DEGENERATE 0x1u /* rows with n_pos*n_neg == 0 get zero ranking gradient instead of
@@ -53,7 +53,8 @@ typedef struct mpvae_probit_params {
     const float *fx_mu;     /* (B,D) */
     const float *fx_logvar; /* (B,D) */
     const float *r;         /* (L,Z) r_sqrt_sigma cast to fp32                mpvae.py:165 */
-    const float *noise;     /* (S,B,Z) standard normal samples                mpvae.py:162 */
+    const float *noise;     /* (S,B,Z) standard normal samples                mpvae.py:162
+                               NULL = draw them inside the library (Philox, fields at the end of this struct) */
 
     /* ---- forward outputs (device) ---- */
     float *scalars[6];       /* six 1-element outputs: total, nll, nll_x, c, c_x, kl   mpvae.py:207-210
@@ -74,6 +75,12 @@ typedef struct mpvae_probit_params {
     /* ---- scratch (device), >= mpvae_workspace_bytes(); forward fills it, backward reads it ---- */
     void *workspace;
     uint64_t workspace_bytes;
+
+    /* ---- library-side noise (noise == NULL): the numbers of mpvae_philox_normal(seed, offset, B_global, row0),
+       generated straight into the layout the contraction engine wants (never materialised as fp32 in the dense
+       regime).  The backward must be given the same values. ---- */
+    uint64_t noise_seed, noise_offset;
+    int32_t noise_b_global, noise_row0;
 } mpvae_probit_params;
 
 /* Bytes of scratch for one forward(+backward) call.  want_backward=0 sizes the inference path. */

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmpvae_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 FLAG_SANITIZE_DEGENERATE = 0x1
 FLAG_CONTRACT_TENSOR = 0x2
 FLAG_CONTRACT_FMA = 0x4
@@ -40,6 +40,8 @@ class ProbitParams(C.Structure):
         ("g_fe_out", _f), ("g_fx_out", _f), ("g_fe_mu", _f), ("g_fe_logvar", _f), ("g_fx_mu", _f),
         ("g_fx_logvar", _f), ("g_r", _f),
         ("workspace", _f), ("workspace_bytes", C.c_uint64),
+        ("noise_seed", C.c_uint64), ("noise_offset", C.c_uint64),
+        ("noise_b_global", C.c_int32), ("noise_row0", C.c_int32),
     ]
 
 

@@ -34,8 +34,14 @@ namespace {
 
 // Workspace carve-up.  Everything is 256-byte aligned; the same function sizes and places.
 struct Workspace {
-    size_t nr, lp, stat, wts, rowaux, rowout, counter, gxs, contract, total;
+    size_t nr, lp, stat, wts, rowaux, rowout, slots, gxs;
+    size_t noise_f32;                             // FMA engine, library-side noise
+    size_t noise_planes, r_planes, gxs_planes;    // tensor engine operand planes (noise planes persist fwd -> bwd)
+    size_t fma_partials;                          // FMA engine split-K partials of g_R
+    size_t total;
 };
+// 32-bit slots of the 256-byte `slots` block
+enum { SLOT_COUNTER = 0, SLOT_ABSMAX_R = 1, SLOT_ABSMAX_GXS = 2 };
 
 bool use_tensor(uint32_t flags, int S, int B, int L, int Z) {
     if (flags & MPVAE_FLAG_CONTRACT_FMA) return false;
@@ -56,17 +62,22 @@ Workspace carve(int S, int B, int L, int Z, bool want_backward, uint32_t flags) 
     w.wts = take((size_t)B * S * 2 * sizeof(float));
     w.rowaux = take((size_t)B * 2 * sizeof(float));
     w.rowout = take((size_t)B * 8 * sizeof(double));
-    w.counter = take(256);
-    w.gxs = want_backward ? take(cube * sizeof(float)) : off;
-    size_t c = 0;
+    w.slots = take(256);
+    // everything the forward writes and the backward reads sits before the backward-only buffers, so a forward
+    // sized for inference and a forward sized for training place the shared buffers identically
     const bool tensor = use_tensor(flags, S, B, L, Z);
+    const int M = S * B;
     if (tensor) {
-        c = tc_workspace_nt(S * B, L, Z);
-        if (want_backward) { size_t c2 = tc_workspace_tn(S * B, L, Z); if (c2 > c) c = c2; }
-    } else if (want_backward) {
-        c = contract_tn_fma_workspace(S * B, L, Z);
+        w.noise_planes = take(tc_planes_bytes(M, Z));
+        w.r_planes = take(tc_planes_bytes(L, Z));
+    } else {
+        w.noise_f32 = take((size_t)M * Z * sizeof(float));
     }
-    w.contract = take(c);
+    if (want_backward) {
+        w.gxs = take(cube * sizeof(float));
+        if (tensor) w.gxs_planes = take(tc_planes_bytes(M, L));
+        else w.fma_partials = take(contract_tn_fma_workspace(M, L, Z));
+    }
     w.total = off;
     return w;
 }
@@ -84,8 +95,13 @@ int validate(const mpvae_probit_params* p, bool backward) {
         return 1;
     }
     if ((long long)p->S * p->B > 0x7fffffffLL) { set_error("S*B overflows int32"); return 1; }
-    if (!p->y || !p->fe_out || !p->fx_out || !p->r || !p->noise || !p->workspace) {
-        set_error("NULL input pointer (y/fe_out/fx_out/r/noise/workspace)");
+    if (!p->y || !p->fe_out || !p->fx_out || !p->r || !p->workspace) {
+        set_error("NULL input pointer (y/fe_out/fx_out/r/workspace)");
+        return 1;
+    }
+    if (!p->noise && (p->noise_row0 < 0 || p->noise_b_global < p->noise_row0 + p->B)) {
+        set_error("library-side noise: rows [%d, %d) do not fit a global batch of %d", p->noise_row0, p->noise_row0 + p->B,
+                  p->noise_b_global);
         return 1;
     }
     if (p->D > 0 && (!p->fe_mu || !p->fe_logvar || !p->fx_mu || !p->fx_logvar)) { set_error("NULL mu/logvar pointer"); return 1; }
@@ -120,13 +136,14 @@ RowArgs row_args(const mpvae_probit_params* p, const Workspace& w) {
     a.wts = reinterpret_cast<float*>(base + w.wts);
     a.rowaux = reinterpret_cast<float*>(base + w.rowaux);
     a.rowout = reinterpret_cast<double*>(base + w.rowout);
-    a.counter = reinterpret_cast<unsigned int*>(base + w.counter);
+    a.counter = reinterpret_cast<unsigned int*>(base + w.slots) + SLOT_COUNTER;
     for (int i = 0; i < 6; ++i) { a.scalars[i] = p->scalars[i]; a.g_scalars[i] = p->g_scalars[i]; }
     a.indiv_prob = p->indiv_prob; a.indiv_prob_label = p->indiv_prob_label;
     a.g_indiv_prob = p->g_indiv_prob; a.g_indiv_prob_label = p->g_indiv_prob_label;
     a.g_fe_out = p->g_fe_out; a.g_fx_out = p->g_fx_out;
     a.g_fe_mu = p->g_fe_mu; a.g_fe_logvar = p->g_fe_logvar; a.g_fx_mu = p->g_fx_mu; a.g_fx_logvar = p->g_fx_logvar;
     a.gxs = nullptr;
+    a.gxs_absmax = nullptr;
     return a;
 }
 
@@ -149,20 +166,35 @@ uint64_t mpvae_workspace_bytes(int32_t S, int32_t B, int32_t L, int32_t Z, int32
 int mpvae_probit_forward(const mpvae_probit_params* p, void* cuda_stream) {
     if (int rc = validate(p, false)) return rc;
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
-    // the scratch may be shorter than the backward layout on the inference path: carve what the caller sized
-    const bool bwd_layout = p->workspace_bytes >= mpvae_workspace_bytes(p->S, p->B, p->L, p->Z, 1, p->flags);
-    const Workspace w = carve(p->S, p->B, p->L, p->Z, bwd_layout, p->flags);
+    // the scratch may be shorter than the backward layout on the inference path; the buffers the forward touches
+    // are placed identically in both layouts
+    const Workspace w = carve(p->S, p->B, p->L, p->Z, false, p->flags);
     char* base = static_cast<char*>(p->workspace);
     float* nr = reinterpret_cast<float*>(base + w.nr);
+    uint32_t* slots = reinterpret_cast<uint32_t*>(base + w.slots);
     const int M = p->S * p->B;
-    int rc;
-    if (use_tensor(p->flags, p->S, p->B, p->L, p->Z))
-        rc = tc_contract_nt(p->noise, p->r, nr, M, p->L, p->Z, base + w.contract, w.total - w.contract, stream);
-    else
-        rc = launch_contract_nt_fma(p->noise, p->r, nr, M, p->L, p->Z, stream);
-    if (rc) return rc;
-    cudaError_t e = cudaMemsetAsync(base + w.counter, 0, 256, stream);
+    cudaError_t e = cudaMemsetAsync(slots, 0, 256, stream);   // last-CTA counter + absmax slots
     if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return 2; }
+    int rc;
+    if (use_tensor(p->flags, p->S, p->B, p->L, p->Z)) {
+        void* npl = base + w.noise_planes;
+        void* rpl = base + w.r_planes;
+        if (p->noise) rc = tc_split(p->noise, M, p->Z, npl, nullptr, 0, stream);   // |N(0,1)| fits fp16 at scale 1
+        else rc = tc_philox_planes(npl, p->S, p->B, p->Z, p->noise_b_global, p->noise_row0, p->noise_seed, p->noise_offset, stream);
+        if (rc) return rc;
+        if ((rc = tc_split(p->r, p->L, p->Z, rpl, slots + SLOT_ABSMAX_R, 1, stream))) return rc;
+        rc = tc_gemm_nt(npl, rpl, nr, M, p->L, p->Z, nullptr, slots + SLOT_ABSMAX_R, stream);
+    } else {
+        const float* nz = p->noise;
+        if (!nz) {
+            float* gen = reinterpret_cast<float*>(base + w.noise_f32);
+            if ((rc = launch_philox_normal(gen, p->S, p->B, p->Z, p->noise_b_global, p->noise_row0, p->noise_seed,
+                                           p->noise_offset, stream))) return rc;
+            nz = gen;
+        }
+        rc = launch_contract_nt_fma(nz, p->r, nr, M, p->L, p->Z, stream);
+    }
+    if (rc) return rc;
     return launch_row_forward(row_args(p, w), stream);
 }
 
@@ -171,14 +203,27 @@ int mpvae_probit_backward(const mpvae_probit_params* p, void* cuda_stream) {
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     const Workspace w = carve(p->S, p->B, p->L, p->Z, true, p->flags);
     char* base = static_cast<char*>(p->workspace);
+    uint32_t* slots = reinterpret_cast<uint32_t*>(base + w.slots);
+    const bool tensor = use_tensor(p->flags, p->S, p->B, p->L, p->Z);
     RowArgs a = row_args(p, w);
-    if (p->g_r) a.gxs = reinterpret_cast<float*>(base + w.gxs);
+    if (p->g_r) {
+        a.gxs = reinterpret_cast<float*>(base + w.gxs);
+        if (tensor) {
+            a.gxs_absmax = slots + SLOT_ABSMAX_GXS;
+            if (cudaMemsetAsync(a.gxs_absmax, 0, sizeof(uint32_t), stream) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return 2; }
+        }
+    }
     if (int rc = launch_row_backward(a, stream)) return rc;
     if (!p->g_r) return 0;
     const int M = p->S * p->B;
-    if (use_tensor(p->flags, p->S, p->B, p->L, p->Z))
-        return tc_contract_tn(a.gxs, p->noise, p->g_r, M, p->L, p->Z, base + w.contract, w.total - w.contract, stream);
-    return launch_contract_tn_fma(a.gxs, p->noise, p->g_r, M, p->L, p->Z, base + w.contract, w.total - w.contract, stream);
+    if (tensor) {
+        void* gpl = base + w.gxs_planes;
+        if (int rc = tc_split(a.gxs, M, p->L, gpl, slots + SLOT_ABSMAX_GXS, 0, stream)) return rc;   // absmax came from the row kernel
+        // the noise planes the forward left in the workspace are the MN-major B operand as they are
+        return tc_gemm_tn(gpl, base + w.noise_planes, p->g_r, M, p->L, p->Z, slots + SLOT_ABSMAX_GXS, nullptr, stream);
+    }
+    const float* nz = p->noise ? p->noise : reinterpret_cast<const float*>(base + w.noise_f32);
+    return launch_contract_tn_fma(a.gxs, nz, p->g_r, M, p->L, p->Z, base + w.fma_partials, w.total - w.fma_partials, stream);
 }
 
 int mpvae_philox_normal(float* noise, int32_t S, int32_t B, int32_t Z, int32_t B_global, int32_t row0, uint64_t seed,

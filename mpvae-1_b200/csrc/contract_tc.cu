@@ -1,52 +1,79 @@
-// tcgen05 contraction engine (sm_100a): split-precision 3xTF32 GEMMs for the dense regime of the probit ELBO
+// tcgen05 contraction engine (sm_100a): split-precision tensor-core GEMMs for the dense regime of the probit ELBO
 // (label / rank sets >= 128, e.g. the delicious and eurlex shapes).
 //
 //   nt: nr[m, l]  = sum_z noise[m, z] * R[l, z]        both operands K-major     (mpvae.py:168)
 //   tn: g_R[l, z] = sum_m gxs[m, l]  * noise[m, z]     both operands MN-major    
 //
-// Plain TF32 (10-bit mantissa) cannot hold the 1e-5 parity bar, so every fp32 operand x is split on the fly
-// into hi = tf32(x), lo = tf32(x - hi) (one streaming pre-pass) and the product is accumulated in fp32 in
-// tensor memory as  A_lo.B_hi + A_hi.B_lo + A_hi.B_hi  (error ~2^-21 relative, below fp32 SGEMM order noise).
+// A 10/11-bit mantissa on the operands cannot hold the 1e-5 parity bar, so every fp32 operand x is split by a
+// streaming pre-pass into hi + lo (two 11-bit pieces, ~22 bits together) and the product is accumulated in fp32
+// in tensor memory as  A_lo.B_hi + A_hi.B_lo + A_hi.B_hi  (the dropped lo.lo term is ~2^-22 relative):
+//   kind::tf32  hi = tf32(x),     lo = tf32(x - hi)                       fp32 containers, K = 8 per MMA
+//   kind::f16   hi = fp16(x * s), lo = fp16(x * s - hi), s = 2^k chosen per tensor so that max|x * s| is in
+//               [1, 2); half the bytes and twice the MMA rate of tf32, result rescaled by 1 / (s_a * s_b)
 //
-// The tensor core adds into its fp32 accumulator with truncation, so a K = 3993 chain drifts by ~K * 2^-24
-// (measured 3.4e-5 relative).  The accumulation is therefore chunked: tensor memory only ever holds the sum of
-// KC k-blocks (128 values of K); the epilogue warps promote each chunk into fp32 REGISTER accumulators with
-// round-to-nearest adds while the tensor core fills the other TMEM buffer.
+// The tensor core adds into its fp32 accumulator with truncation toward zero, so a long K chain drifts
+// (K = 3993: -2.4e-5 relative, measured).  The accumulation is therefore chunked: tensor memory only ever holds
+// `kc` k-blocks; sixteen promotion warps add each chunk into fp32 REGISTER accumulators (round-to-nearest) while
+// the tensor core fills the other TMEM buffer, and scale the chunk by (1 + bias * k-blocks) to take the systematic
+// part of the truncation out again (profiles/r1_tc_chunk_experiment.txt).
 //
 // Kernel anatomy (one CTA per SM, persistent over 128 x 256 output tiles, 640 threads):
-//   warp 0    : TMA producer  -- cp.async.bulk.tensor (128B-swizzled boxes) into a 2-stage smem ring
-//   warp 1    : MMA issuer    -- one lane issues tcgen05.mma.kind::tf32 (M128 N256 K8), 12 per k-block
+//   warp 0    : TMA producer  -- cp.async.bulk.tensor (128B-swizzled boxes) into a 2-stage, 96 KiB-per-stage smem ring
+//   warp 1    : MMA issuer    -- one lane issues tcgen05.mma (M128 N256), 12 per k-block
 //   warp 2    : TMEM allocator (512 columns = two 128x256 fp32 chunk accumulators, ping-pong)
 //   warps 4-19: promotion + epilogue -- tcgen05.ld a chunk (32 rows x 64 columns per warp), add into registers,
 //               store the finished tile
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA), tmem full/empty mbarriers (MMA <-> promotion).
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
+#include "philox.cuh"
 #include "tc.h"
 
 namespace mpv {
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 32;              // fp32 elements; BK * 4 B = one 128-byte swizzle row
+constexpr int BM = 128, BN = 256;
 constexpr int STAGES = 2;
-constexpr int A_BYTES = BM * BK * 4;                     // 16 KiB per (hi | lo) tile
-constexpr int B_BYTES = BN * BK * 4;                     // 32 KiB
+constexpr int A_BYTES = BM * 128;                        // 16 KiB per (hi | lo) tile: BM rows x one 128-byte swizzle row
+constexpr int B_BYTES = BN * 128;                        // 32 KiB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 96 KiB
-constexpr int EPI_BYTES = 0;
-constexpr int kDefaultKC = 2;                             // k-blocks accumulated in tensor memory per chunk
-// The tensor core truncates (toward zero) when it adds into the fp32 accumulator, which shrinks a chunk sum by
-// a measured 1.85e-7 of its value per k-block (12 MMAs of K=8; profiles/r1_tc_chunk_experiment.txt).  The
-// promotion multiplies the chunk by (1 + this * k-blocks) to take the systematic part out again; what is left
-// is random and ~2x below an fp32 SGEMM's own rounding.
-constexpr float kTruncBiasPerKBlock = 1.85e-7f;
-constexpr int kEpiWarps = 16;                            // 4 TMEM lane quadrants x 4 column quarters
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES;
 constexpr int TMEM_COLS = 512;
+constexpr int kEpiWarps = 16;                            // 4 TMEM lane quadrants x 4 column quarters
 constexpr int kThreads = 128 + 32 * kEpiWarps;
+
+// Per-kind geometry.  One k-block is one 128-byte swizzle row of K (K-major) or one TMA box of k-rows (MN-major).
+template <bool MN, bool F16>
+struct Geo {
+    static constexpr int ELT = F16 ? 2 : 4;
+    static constexpr int BK = 128 / ELT;                 // K elements per k-block: 32 (tf32) / 64 (f16)
+    static constexpr int UK = F16 ? 16 : 8;              // K per tcgen05.mma
+    static constexpr int BOX_MN = 128 / ELT;             // MN elements per 128-byte row of an MN-major box
+    // K-major: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (= 1); a k-step is +32 B in the row.
+    // MN-major: each k-row holds 128 B of MN; the next MN chunk is one TMA box (BK * 128 B) away (LBO);
+    //   16-bit: k-rows in groups of 8, 1024 B apart (SWIZZLE_128B);
+    //   32-bit: k-rows in groups of 4,  512 B apart (SWIZZLE_128B_BASE32B -- the only layout the hardware takes
+    //           for MN-major 32-bit operands; TMA side: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    //   a k-step of UK rows is + UK * 128 B.
+    static constexpr uint32_t kstep = MN ? UK * 128u : 32u;
+    static constexpr uint32_t lbo = MN ? (BK * 128u) / 16u : 1u;
+    static constexpr uint32_t sbo = (MN && !F16) ? 512u / 16u : 1024u / 16u;
+    static constexpr uint32_t layout = (MN && !F16) ? 1u : 2u;
+    // Instruction descriptor (cute::UMMA::InstrDescriptor): [4,6) D = F32 | [7,10) A fmt | [10,13) B fmt
+    // (0 = F16, 2 = TF32) | 15 A major | 16 B major (1 = MN) | [17,23) N >> 3 | [24,29) M >> 4
+    static constexpr uint32_t idesc = (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) |
+                                      (MN ? ((1u << 15) | (1u << 16)) : 0u) | ((uint32_t)(BN >> 3) << 17) |
+                                      ((uint32_t)(BM >> 4) << 24);
+    // measured shrink of a TMEM chunk sum per k-block (12 MMAs), see header
+    static constexpr float trunc_bias = F16 ? 1.85e-7f : 1.85e-7f;
+    static constexpr int default_kc = 2;
+};
 
 // ------------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -85,13 +112,23 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
+template <bool F16>
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    if (F16) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+            : "memory");
+    }
 }
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -104,42 +141,54 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// UMMA shared-memory matrix descriptor, 128B swizzle (cute::UMMA::SmemDescriptor bit layout):
+// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
 //   [46,48) version = 1 (sm_100) | [61,64) layout type: 2 = SWIZZLE_128B (16 B atoms), 1 = SWIZZLE_128B_BASE32B
-//   (32 B atoms -- the only layout the hardware accepts for MN-major 32-bit operands)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16, uint32_t layout) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(lbo16 & 0x3FFFu) << 16) | ((uint64_t)(sbo16 & 0x3FFFu) << 32) |
            (1ull << 46) | ((uint64_t)layout << 61);
 }
 
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, majors, N >> 3, M >> 4.
-template <bool MN>
-__device__ __forceinline__ constexpr uint32_t umma_idesc() {
-    return (1u << 4) | (2u << 7) | (2u << 10) | (MN ? ((1u << 15) | (1u << 16)) : 0u) | ((uint32_t)(BN >> 3) << 17) |
-           ((uint32_t)(BM >> 4) << 24);
+// Per-tensor power-of-two scale for the fp16 split: s = 2^-e with e = exponent of max|x|, so max|x| * s is in
+// [1, 2).  max == 0, Inf or NaN (e.g. the NaN gradients of degenerate rows) -> s = 1 and the values pass through.
+__host__ __device__ __forceinline__ float scale_from_absmax_bits(uint32_t bits) {
+    bits &= 0x7FFFFFFFu;
+    if (bits == 0u || bits >= 0x7F800000u) return 1.0f;
+    int e = (int)(bits >> 23) - 127;
+    if (e < -100) e = -100;
+    if (e > 100) e = 100;
+    const uint32_t sb = (uint32_t)(127 - e) << 23;
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(sb);
+#else
+    float f;
+    memcpy(&f, &sb, 4);
+    return f;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM
-// C[Mc, Nc] (row-major, pitch ldc) = sum_k A(m, k) * B(n, k); operands come pre-split as [2][.][.] fp32
-// (plane 0 = hi, plane 1 = lo) through 3-D TMA maps.
-//   MN == false: A is [Mc][K], B is [Nc][K] (K contiguous);  box {BK, rows, 1}
-//   MN == true : A is [K][Mc], B is [K][Nc] (Mc / Nc contiguous); boxes {32, BK, 1}, 4 per A tile, 8 per B tile
-template <bool MN>
+// C[Mc, Nc] (row-major, pitch ldc) = inv_scale * sum_k A(m, k) * B(n, k); operands come pre-split as [2][.][.]
+// planes (0 = hi, 1 = lo) through 3-D TMA maps.
+//   MN == false: A is [Mc][K], B is [Nc][K] (K contiguous);   one box {BK, rows, 1} per tile and plane
+//   MN == true : A is [K][Mc], B is [K][Nc] (Mc / Nc contiguous); boxes {BOX_MN, BK, 1}
+template <bool MN, bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   float* __restrict__ C, int Mc, int Nc, int K, int ldc, int tiles_m, int tiles_n, int kc) {
+gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  float* __restrict__ C, int Mc, int Nc, int K, int ldc, int tiles_m, int tiles_n, int kc,
+                  const uint32_t* __restrict__ absmax_a, const uint32_t* __restrict__ absmax_b) {
+    using G = Geo<MN, F16>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;             // 128B-swizzled tiles need 1024 B alignment
     uint8_t* gen = smem_raw + (base - raw);
-    const uint32_t bars = base + STAGES * STAGE_BYTES + EPI_BYTES;
+    const uint32_t bars = base + STAGES * STAGE_BYTES;
     // barrier slots (8 B each): full[STAGES], empty[STAGES], tfull[2], tempty[2]; then the TMEM base address
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
     auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + STAGES * STAGE_BYTES + EPI_BYTES + 128);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + STAGES * STAGE_BYTES + 128);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -159,7 +208,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
 
     const int num_tiles = tiles_m * tiles_n;
-    const int num_kb = (K + BK - 1) / BK;
+    const int num_kb = (K + G::BK - 1) / G::BK;
 
     if (warp == 0) {
         if (lane == 0) {   // ------------------------------------------------ TMA producer
@@ -173,20 +222,21 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     mbar_arrive_expect_tx(fb, STAGE_BYTES);
                     const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + 2 * A_BYTES;
                     if (!MN) {
-                        tma_load_3d(sa, &tmA, fb, kb * BK, m0, 0);
-                        tma_load_3d(sa + A_BYTES, &tmA, fb, kb * BK, m0, 1);
-                        tma_load_3d(sb, &tmB, fb, kb * BK, n0, 0);
-                        tma_load_3d(sb + B_BYTES, &tmB, fb, kb * BK, n0, 1);
+                        tma_load_3d(sa, &tmA, fb, kb * G::BK, m0, 0);
+                        tma_load_3d(sa + A_BYTES, &tmA, fb, kb * G::BK, m0, 1);
+                        tma_load_3d(sb, &tmB, fb, kb * G::BK, n0, 0);
+                        tma_load_3d(sb + B_BYTES, &tmB, fb, kb * G::BK, n0, 1);
                     } else {
+                        constexpr int box = G::BK * 128;
 #pragma unroll
-                        for (int j = 0; j < BM / 32; ++j) {
-                            tma_load_3d(sa + j * (BK * 128), &tmA, fb, m0 + j * 32, kb * BK, 0);
-                            tma_load_3d(sa + A_BYTES + j * (BK * 128), &tmA, fb, m0 + j * 32, kb * BK, 1);
+                        for (int j = 0; j < BM / G::BOX_MN; ++j) {
+                            tma_load_3d(sa + j * box, &tmA, fb, m0 + j * G::BOX_MN, kb * G::BK, 0);
+                            tma_load_3d(sa + A_BYTES + j * box, &tmA, fb, m0 + j * G::BOX_MN, kb * G::BK, 1);
                         }
 #pragma unroll
-                        for (int j = 0; j < BN / 32; ++j) {
-                            tma_load_3d(sb + j * (BK * 128), &tmB, fb, n0 + j * 32, kb * BK, 0);
-                            tma_load_3d(sb + B_BYTES + j * (BK * 128), &tmB, fb, n0 + j * 32, kb * BK, 1);
+                        for (int j = 0; j < BN / G::BOX_MN; ++j) {
+                            tma_load_3d(sb + j * box, &tmB, fb, n0 + j * G::BOX_MN, kb * G::BK, 0);
+                            tma_load_3d(sb + B_BYTES + j * box, &tmB, fb, n0 + j * G::BOX_MN, kb * G::BK, 1);
                         }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -195,14 +245,6 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
     } else if (warp == 1) {
         if (lane == 0) {   // ------------------------------------------------ MMA issuer
-            constexpr uint32_t idesc = umma_idesc<MN>();
-            // K-major (SWIZZLE_128B): rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1); a k-step of
-            //   8 elements is +32 B inside the swizzle row.
-            // MN-major (SWIZZLE_128B_BASE32B): each k-row holds 128 B of MN, the next 32-wide MN chunk is one TMA
-            //   box (BK*128 B) away (LBO), k-rows come in groups of 4 that are 512 B apart (SBO); a k-step of 8 is
-            //   +1024 B.
-            constexpr uint32_t lbo = MN ? (BK * 128) / 16 : 1, sbo = MN ? 512 / 16 : 1024 / 16;
-            constexpr uint32_t kstep = MN ? 1024u : 32u, layout = MN ? 1u : 2u;
             int stage = 0, buf = 0;
             uint32_t phase = 0, bphase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -216,14 +258,14 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         tc_fence_after();
                         const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + 2 * A_BYTES;
 #pragma unroll
-                        for (int kk = 0; kk < BK / 8; ++kk) {
-                            const uint64_t a_hi = umma_desc(sa + kk * kstep, lbo, sbo, layout);
-                            const uint64_t a_lo = umma_desc(sa + A_BYTES + kk * kstep, lbo, sbo, layout);
-                            const uint64_t b_hi = umma_desc(sb + kk * kstep, lbo, sbo, layout);
-                            const uint64_t b_lo = umma_desc(sb + B_BYTES + kk * kstep, lbo, sbo, layout);
-                            tc_mma_tf32(d, a_lo, b_hi, idesc, (kb != kb0 || kk != 0) ? 1u : 0u);   // small terms first
-                            tc_mma_tf32(d, a_hi, b_lo, idesc, 1u);
-                            tc_mma_tf32(d, a_hi, b_hi, idesc, 1u);
+                        for (int kk = 0; kk < G::BK / G::UK; ++kk) {
+                            const uint64_t a_hi = umma_desc(sa + kk * G::kstep, G::lbo, G::sbo, G::layout);
+                            const uint64_t a_lo = umma_desc(sa + A_BYTES + kk * G::kstep, G::lbo, G::sbo, G::layout);
+                            const uint64_t b_hi = umma_desc(sb + kk * G::kstep, G::lbo, G::sbo, G::layout);
+                            const uint64_t b_lo = umma_desc(sb + B_BYTES + kk * G::kstep, G::lbo, G::sbo, G::layout);
+                            tc_mma<F16>(d, a_lo, b_hi, G::idesc, (kb != kb0 || kk != 0) ? 1u : 0u);   // small terms first
+                            tc_mma<F16>(d, a_hi, b_lo, G::idesc, 1u);
+                            tc_mma<F16>(d, a_hi, b_hi, G::idesc, 1u);
                         }
                         tc_commit(empty_bar(stage));            // smem stage reusable once these MMAs retire
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -235,6 +277,12 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
     } else if (warp >= 4) {   // ------------------------------- promotion + epilogue: TMEM lanes 32q.., columns 64h..
         const int q = warp & 3, h = (warp - 4) >> 2;
+        float inv_scale = 1.0f;
+        if (F16) {
+            const float sa = absmax_a ? scale_from_absmax_bits(*absmax_a) : 1.0f;
+            const float sb = absmax_b ? scale_from_absmax_bits(*absmax_b) : 1.0f;
+            inv_scale = 1.0f / (sa * sb);                        // powers of two: exact
+        }
         float acc[64];
 #pragma unroll
         for (int j = 0; j < 64; ++j) acc[j] = 0.0f;
@@ -245,7 +293,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 mbar_wait(tfull_bar(buf), bphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + h * 64);
-                const float unbias = 1.0f + kTruncBiasPerKBlock * (float)(min(kb0 + kc, num_kb) - kb0);
+                const float unbias = 1.0f + G::trunc_bias * (float)(min(kb0 + kc, num_kb) - kb0);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     uint32_t v[16];
@@ -265,7 +313,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 float* __restrict__ crow = C + (size_t)row * ldc;
 #pragma unroll
                 for (int j = 0; j < 64; ++j)
-                    if (col0 + j < Nc) crow[col0 + j] = acc[j];
+                    if (col0 + j < Nc) crow[col0 + j] = acc[j] * inv_scale;
             }
 #pragma unroll
             for (int j = 0; j < 64; ++j) acc[j] = 0.0f;
@@ -279,16 +327,16 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
 }
 
+// ------------------------------------------------------------------------------------------------ pre-passes
 // hi = tf32(x) (round to nearest, ties away), lo = tf32(x - hi); dst planes are [rows][dpitch], pad columns zero.
 __global__ void __launch_bounds__(256)
-split_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, int spitch, int dpitch,
-                  size_t plane) {
+split_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, int dpitch, size_t plane) {
     const size_t n = (size_t)rows * dpitch;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / dpitch), c = (int)(i % dpitch);
         float hi = 0.0f, lo = 0.0f;
         if (c < cols) {
-            const float x = src[(size_t)r * spitch + c];
+            const float x = src[(size_t)r * cols + c];
             uint32_t h, l;
             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
             hi = __uint_as_float(h);
@@ -297,6 +345,41 @@ split_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, int ro
         }
         dst[i] = hi;
         dst[plane + i] = lo;
+    }
+}
+
+// max |x| as raw fp32 bits (ordering of non-negative floats == ordering of their bit patterns; NaN sorts highest)
+__global__ void __launch_bounds__(256)
+absmax_kernel(const float* __restrict__ src, size_t n, uint32_t* __restrict__ out) {
+    uint32_t m = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t b = __float_as_uint(src[i]) & 0x7FFFFFFFu;
+        m = b > m ? b : m;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t t = __shfl_xor_sync(0xffffffffu, m, o);
+        m = t > m ? t : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m != 0) atomicMax(out, m);
+}
+
+// hi = fp16(x * s), lo = fp16(x * s - hi) with s from the tensor's absmax; two elements per thread.
+__global__ void __launch_bounds__(256)
+split_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int rows, int cols, int dpitch, size_t plane,
+                 const uint32_t* __restrict__ absmax) {
+    const float s = absmax ? scale_from_absmax_bits(*absmax) : 1.0f;
+    const size_t n2 = (size_t)rows * dpitch / 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = 2 * i;
+        const int r = (int)(e / dpitch), c = (int)(e % dpitch);
+        float x0 = 0.0f, x1 = 0.0f;
+        if (c < cols) x0 = src[(size_t)r * cols + c] * s;
+        if (c + 1 < cols) x1 = src[(size_t)r * cols + c + 1] * s;
+        const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+        const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+        reinterpret_cast<__half2*>(dst)[i] = __halves2half2(h0, h1);
+        reinterpret_cast<__half2*>(dst + plane)[i] = __halves2half2(l0, l1);
     }
 }
 
@@ -319,56 +402,84 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 3-D map over a split operand [2][rows][pitch] (fp32): dims {cols, rows, 2}, 128B swizzle (16 B atoms for
-// K-major tiles, 32 B atoms for MN-major tiles), zero OOB fill.
-int make_map(CUtensorMap* map, const float* ptr, int cols, int rows, int pitch, int box_cols, int box_rows,
+// 3-D map over a split operand [2][rows][pitch]: dims {cols, rows, 2}, 128B swizzle, zero OOB fill.
+int make_map(CUtensorMap* map, const void* ptr, bool f16, int cols, int rows, int pitch, int box_cols, int box_rows,
              CUtensorMapSwizzle swizzle) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled unavailable from the driver"); return 8; }
+    const cuuint64_t esz = f16 ? 2 : 4;
     cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
-    cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)rows * pitch * 4};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch * esz, (cuuint64_t)rows * pitch * esz};
     cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                          const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) cols=%d rows=%d pitch=%d", (int)r, cols, rows, pitch); return 8; }
     return 0;
 }
 
-int pitch_of(int cols) { return ceil_div(cols, 32) * 32; }
+int pitch_of(int cols) { return ceil_div(cols, 64) * 64; }
 
-// k-blocks per tensor-memory chunk (MPVAE_TC_KC overrides it for accuracy / speed experiments)
-int chunk_kblocks() {
-    static int kc = 0;
-    if (kc == 0) {
-        const char* e = getenv("MPVAE_TC_KC");
-        kc = e ? atoi(e) : kDefaultKC;
-        if (kc < 1) kc = kDefaultKC;
+// MPVAE_TC_KIND = tf32 | f16 selects the operand kind (default below); MPVAE_TC_KC the TMEM chunk length.
+bool use_f16() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MPVAE_TC_KIND");
+        v = (e && strcmp(e, "tf32") == 0) ? 0 : 1;   // default: fp16 split (same accuracy, half the bytes, 2x MMA rate)
     }
-    return kc;
+    return v == 1;
+}
+int chunk_kblocks(int dflt) {
+    static int kc = -1;
+    if (kc < 0) {
+        const char* e = getenv("MPVAE_TC_KC");
+        kc = e ? atoi(e) : 0;
+    }
+    return kc > 0 ? kc : dflt;
 }
 
-int split(const float* src, float* dst, int rows, int cols, int pitch, cudaStream_t stream) {
+int grid_for(size_t n) { return (int)((n + 255) / 256 < (size_t)(8 * kNumSMs) ? (n + 255) / 256 : 8 * kNumSMs); }
+
+// scratch layout: [absmax_a, absmax_b (256 B)] [A planes] [B planes]
+struct Scratch { uint32_t* absmax; char* a; char* b; };
+
+size_t planes_bytes(size_t rows, size_t pitch) { return align_up(2 * rows * pitch * 4, 1024); }   // sized for fp32 planes
+
+Scratch carve_scratch(void* ws, size_t rows_a, size_t pitch_a) {
+    char* p = static_cast<char*>(ws);
+    return {reinterpret_cast<uint32_t*>(p), p + 256, p + 256 + planes_bytes(rows_a, pitch_a)};
+}
+
+int split_operand(const float* src, void* dst, int rows, int cols, int pitch, bool f16, uint32_t* absmax, cudaStream_t stream) {
     const size_t n = (size_t)rows * pitch;
-    const int blocks = (int)((n + 255) / 256 < (size_t)(8 * kNumSMs) ? (n + 255) / 256 : 8 * kNumSMs);
-    split_tf32_kernel<<<blocks, 256, 0, stream>>>(src, dst, rows, cols, cols, pitch, n);
-    return check_launch("split_tf32_kernel");
+    if (!f16) {
+        split_tf32_kernel<<<grid_for(n), 256, 0, stream>>>(src, static_cast<float*>(dst), rows, cols, pitch, n);
+        return check_launch("split_tf32_kernel");
+    }
+    if (absmax) {
+        absmax_kernel<<<grid_for((size_t)rows * cols), 256, 0, stream>>>(src, (size_t)rows * cols, absmax);
+        if (int rc = check_launch("absmax_kernel")) return rc;
+    }
+    split_f16_kernel<<<grid_for(n / 2), 256, 0, stream>>>(src, static_cast<__half*>(dst), rows, cols, pitch, n, absmax);
+    return check_launch("split_f16_kernel");
 }
 
-template <bool MN>
-int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc, int Nc, int K, int ldc, cudaStream_t stream) {
+template <bool MN, bool F16>
+int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc, int Nc, int K, int ldc, const uint32_t* ma,
+                const uint32_t* mb, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        const cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_kernel<MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(gemm_3xtf32): %s", cudaGetErrorString(e)); return 4; }
+        const cudaError_t e = cudaFuncSetAttribute(gemm_split_kernel<MN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(gemm_split): %s", cudaGetErrorString(e)); return 4; }
         configured = true;
     }
     const int tiles_m = ceil_div(Mc, BM), tiles_n = ceil_div(Nc, BN);
     const int tiles = tiles_m * tiles_n;
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    gemm_3xtf32_kernel<MN><<<grid, kThreads, SMEM_BYTES, stream>>>(a, b, C, Mc, Nc, K, ldc, tiles_m, tiles_n, chunk_kblocks());
-    return check_launch("gemm_3xtf32_kernel");
+    gemm_split_kernel<MN, F16><<<grid, kThreads, SMEM_BYTES, stream>>>(a, b, C, Mc, Nc, K, ldc, tiles_m, tiles_n,
+                                                                        chunk_kblocks(Geo<MN, F16>::default_kc), ma, mb);
+    return check_launch("gemm_split_kernel");
 }
 
 }  // namespace
@@ -377,39 +488,138 @@ bool tc_available() { return true; }
 
 size_t tc_workspace_nt(int M, int N, int K) {
     const size_t kp = pitch_of(K);
-    return align_up(2 * (size_t)M * kp * 4, 1024) + align_up(2 * (size_t)N * kp * 4, 1024);
+    return 256 + planes_bytes(M, kp) + planes_bytes(N, kp);
 }
 
 size_t tc_workspace_tn(int M, int N1, int N2) {
-    return align_up(2 * (size_t)M * pitch_of(N1) * 4, 1024) + align_up(2 * (size_t)M * pitch_of(N2) * 4, 1024);
+    return 256 + planes_bytes(M, pitch_of(N1)) + planes_bytes(M, pitch_of(N2));
 }
 
 int tc_contract_nt(const float* A, const float* Bm, float* C, int M, int N, int K, void* ws, size_t ws_bytes,
                    cudaStream_t stream) {
     if (!ws || ws_bytes < tc_workspace_nt(M, N, K)) { set_error("tc_contract_nt: workspace too small"); return 5; }
+    const bool f16 = use_f16();
     const int kp = pitch_of(K);
-    float* a2 = static_cast<float*>(ws);
-    float* b2 = reinterpret_cast<float*>(static_cast<char*>(ws) + align_up(2 * (size_t)M * kp * 4, 1024));
-    if (int rc = split(A, a2, M, K, kp, stream)) return rc;
-    if (int rc = split(Bm, b2, N, K, kp, stream)) return rc;
+    const Scratch s = carve_scratch(ws, M, kp);
+    if (f16 && cudaMemsetAsync(s.absmax, 0, 256, stream) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return 2; }
+    if (int rc = split_operand(A, s.a, M, K, kp, f16, s.absmax, stream)) return rc;
+    if (int rc = split_operand(Bm, s.b, N, K, kp, f16, s.absmax + 1, stream)) return rc;
     CUtensorMap ma, mb;
-    if (int rc = make_map(&ma, a2, K, M, kp, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    if (int rc = make_map(&mb, b2, K, N, kp, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    return launch_gemm<false>(ma, mb, C, M, N, K, N, stream);
+    const int bk = f16 ? 64 : 32;
+    if (int rc = make_map(&ma, s.a, f16, K, M, kp, bk, BM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_map(&mb, s.b, f16, K, N, kp, bk, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (f16) return launch_gemm<false, true>(ma, mb, C, M, N, K, N, s.absmax, s.absmax + 1, stream);
+    return launch_gemm<false, false>(ma, mb, C, M, N, K, N, nullptr, nullptr, stream);
 }
 
 int tc_contract_tn(const float* A, const float* Bm, float* C, int M, int N1, int N2, void* ws, size_t ws_bytes,
                    cudaStream_t stream) {
     if (!ws || ws_bytes < tc_workspace_tn(M, N1, N2)) { set_error("tc_contract_tn: workspace too small"); return 5; }
+    const bool f16 = use_f16();
     const int p1 = pitch_of(N1), p2 = pitch_of(N2);
-    float* a2 = static_cast<float*>(ws);
-    float* b2 = reinterpret_cast<float*>(static_cast<char*>(ws) + align_up(2 * (size_t)M * p1 * 4, 1024));
-    if (int rc = split(A, a2, M, N1, p1, stream)) return rc;
-    if (int rc = split(Bm, b2, M, N2, p2, stream)) return rc;
+    const Scratch s = carve_scratch(ws, M, p1);
+    if (f16 && cudaMemsetAsync(s.absmax, 0, 256, stream) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return 2; }
+    if (int rc = split_operand(A, s.a, M, N1, p1, f16, s.absmax, stream)) return rc;
+    if (int rc = split_operand(Bm, s.b, M, N2, p2, f16, s.absmax + 1, stream)) return rc;
     CUtensorMap ma, mb;
-    if (int rc = make_map(&ma, a2, N1, M, p1, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
-    if (int rc = make_map(&mb, b2, N2, M, p2, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
-    return launch_gemm<true>(ma, mb, C, N1, N2, M, N2, stream);
+    const int bk = f16 ? 64 : 32, box_mn = f16 ? 64 : 32;
+    const CUtensorMapSwizzle sw = f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    if (int rc = make_map(&ma, s.a, f16, N1, M, p1, box_mn, bk, sw)) return rc;
+    if (int rc = make_map(&mb, s.b, f16, N2, M, p2, box_mn, bk, sw)) return rc;
+    if (f16) return launch_gemm<true, true>(ma, mb, C, N1, N2, M, N2, s.absmax, s.absmax + 1, stream);
+    return launch_gemm<true, false>(ma, mb, C, N1, N2, M, N2, nullptr, nullptr, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ staged interface
+size_t tc_planes_bytes(int rows, int cols) { return planes_bytes((size_t)rows, (size_t)pitch_of(cols)); }
+
+int tc_split(const float* src, int rows, int cols, void* planes, uint32_t* absmax, int compute_absmax, cudaStream_t stream) {
+    const bool f16 = use_f16();
+    const int pitch = pitch_of(cols);
+    const size_t n = (size_t)rows * pitch;
+    if (!f16) {
+        split_tf32_kernel<<<grid_for(n), 256, 0, stream>>>(src, static_cast<float*>(planes), rows, cols, pitch, n);
+        return check_launch("split_tf32_kernel");
+    }
+    if (absmax && compute_absmax) {
+        absmax_kernel<<<grid_for((size_t)rows * cols), 256, 0, stream>>>(src, (size_t)rows * cols, absmax);
+        if (int rc = check_launch("absmax_kernel")) return rc;
+    }
+    split_f16_kernel<<<grid_for(n / 2), 256, 0, stream>>>(src, static_cast<__half*>(planes), rows, cols, pitch, n, absmax);
+    return check_launch("split_f16_kernel");
+}
+
+namespace {
+
+// Philox normals written straight into operand planes (scale 1: |n| < 6 fits fp16).  One thread per counter, same
+// counter -> element mapping as philox_normal_kernel, so the numbers are identical to the fp32 tensor it would write.
+template <bool F16>
+__global__ void __launch_bounds__(256)
+philox_planes_kernel(void* __restrict__ planes, int S, int B, int Z, int pitch, int Bg, int row0, uint2 key, uint2 off) {
+    const int s = blockIdx.y;
+    const unsigned long long span_beg = ((unsigned long long)s * Bg + row0) * Z;
+    const unsigned long long span_end = span_beg + (unsigned long long)B * Z;
+    const unsigned long long c = (span_beg >> 2) + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if ((c << 2) >= span_end) return;
+    float n[4];
+    philox_normal4(c, key, off, n);
+    const size_t plane = (size_t)S * B * pitch;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const unsigned long long g = (c << 2) + j;
+        if (g < span_beg || g >= span_end) continue;
+        const unsigned long long e = g - span_beg;                       // index inside this sample's (B, Z) block
+        const size_t o = ((size_t)s * B + (size_t)(e / Z)) * pitch + (size_t)(e % Z);
+        if (F16) {
+            const __half h = __float2half_rn(n[j]);
+            static_cast<__half*>(planes)[o] = h;
+            static_cast<__half*>(planes)[plane + o] = __float2half_rn(n[j] - __half2float(h));
+        } else {
+            uint32_t h, l;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(n[j]));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(n[j] - __uint_as_float(h)));
+            static_cast<uint32_t*>(planes)[o] = h;
+            static_cast<uint32_t*>(planes)[plane + o] = l;
+        }
+    }
+}
+
+}  // namespace
+
+int tc_philox_planes(void* planes, int S, int B, int Z, int Bg, int row0, uint64_t seed, uint64_t offset,
+                     cudaStream_t stream) {
+    if (S > 65535) { set_error("philox: S=%d exceeds grid.y limit", S); return 6; }
+    const unsigned long long counters = ((unsigned long long)B * Z + 3) / 4 + 1;
+    dim3 grid((unsigned)((counters + 255) / 256), S);
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint2 off = make_uint2((uint32_t)offset, (uint32_t)(offset >> 32));
+    if (use_f16()) philox_planes_kernel<true><<<grid, 256, 0, stream>>>(planes, S, B, Z, pitch_of(Z), Bg, row0, key, off);
+    else philox_planes_kernel<false><<<grid, 256, 0, stream>>>(planes, S, B, Z, pitch_of(Z), Bg, row0, key, off);
+    return check_launch("philox_planes_kernel");
+}
+
+int tc_gemm_nt(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, const uint32_t* absmax_a,
+               const uint32_t* absmax_b, cudaStream_t stream) {
+    const bool f16 = use_f16();
+    const int kp = pitch_of(K), bk = f16 ? 64 : 32;
+    CUtensorMap ma, mb;
+    if (int rc = make_map(&ma, a_planes, f16, K, M, kp, bk, BM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_map(&mb, b_planes, f16, K, N, kp, bk, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (f16) return launch_gemm<false, true>(ma, mb, C, M, N, K, N, absmax_a, absmax_b, stream);
+    return launch_gemm<false, false>(ma, mb, C, M, N, K, N, nullptr, nullptr, stream);
+}
+
+int tc_gemm_tn(const void* a_planes, const void* b_planes, float* C, int M, int N1, int N2, const uint32_t* absmax_a,
+               const uint32_t* absmax_b, cudaStream_t stream) {
+    const bool f16 = use_f16();
+    const int p1 = pitch_of(N1), p2 = pitch_of(N2);
+    const int bk = f16 ? 64 : 32, box_mn = f16 ? 64 : 32;
+    const CUtensorMapSwizzle sw = f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    CUtensorMap ma, mb;
+    if (int rc = make_map(&ma, a_planes, f16, N1, M, p1, box_mn, bk, sw)) return rc;
+    if (int rc = make_map(&mb, b_planes, f16, N2, M, p2, box_mn, bk, sw)) return rc;
+    if (f16) return launch_gemm<true, true>(ma, mb, C, N1, N2, M, N2, absmax_a, absmax_b, stream);
+    return launch_gemm<true, false>(ma, mb, C, N1, N2, M, N2, nullptr, nullptr, stream);
 }
 
 }  // namespace mpv

@@ -257,6 +257,7 @@ probit_row_bwd_kernel(const RowArgs a) {
     const bool has_gp = a.g_indiv_prob != nullptr, has_gpl = a.g_indiv_prob_label != nullptr;
     __syncthreads();
 
+    unsigned int gmax = 0u;
     const int steps = (S + kST * nws - 1) / (kST * nws);
     for (int step = 0; step < steps; ++step) {
         const int s0 = (step * nws + ws) * kST;
@@ -289,12 +290,25 @@ probit_row_bwd_kernel(const RowArgs a) {
                     const float dl = cell_backward(nr + fe, yv, cn[i][0], cp[i][0], cq[i][0], gpl);
                     const float dx = cell_backward(nr + fx, yv, cn[i][1], cp[i][1], cq[i][1], gpx);
                     gl += dl; gx += dx;
-                    if (a.gxs) a.gxs[idx] = dl + dx;
+                    if (a.gxs) {
+                        const float g = dl + dx;
+                        a.gxs[idx] = g;
+                        const unsigned int gb = __float_as_uint(g) & 0x7FFFFFFFu;   // |g| as ordered bits, NaN highest
+                        gmax = gb > gmax ? gb : gmax;
+                    }
                 }
             }
             gacc[l] += gl;
             gacc[L + l] += gx;
         }
+    }
+    if (a.gxs_absmax) {   // one atomic per warp: scale of the fp16 operand split of gxs (contract_tc.cu)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned int t = __shfl_xor_sync(0xffffffffu, gmax, o);
+            gmax = t > gmax ? t : gmax;
+        }
+        if (lane == 0 && gmax != 0u) atomicMax(a.gxs_absmax, gmax);
     }
     __syncthreads();
     for (int l = tid; l < L; l += kThreads) {

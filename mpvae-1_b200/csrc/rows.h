@@ -29,6 +29,7 @@ struct RowArgs {
     const float *g_indiv_prob, *g_indiv_prob_label;
     float *g_fe_out, *g_fx_out, *g_fe_mu, *g_fe_logvar, *g_fx_mu, *g_fx_logvar;
     float* gxs;        // (S,B,L) gx_l + gx_x, or nullptr when R needs no gradient
+    unsigned int* gxs_absmax;   // max |gxs| as fp32 bits (atomicMax), or nullptr; feeds the fp16 operand scale
 };
 
 size_t row_smem_bytes(int L);

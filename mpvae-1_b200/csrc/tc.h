@@ -1,13 +1,15 @@
-// tcgen05 (5th-gen tensor core) contraction engine: 3xTF32 split-precision GEMMs for the dense regime
-// (label / rank sets >= 128).  See contract_tc.cu.
+// tcgen05 (5th-gen tensor core) contraction engine: split-precision GEMMs for the dense regime (label / rank sets
+// >= 128).  See contract_tc.cu.
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
+#include <stdint.h>
 
 namespace mpv {
 
 bool tc_available();
-// scratch for operand staging (hi/lo tf32 splits, K padded to the TMA box)
+
+// ---- all-in-one entry points (split pre-pass + GEMM), used by mpvae_contract_nt / _tn ----
 size_t tc_workspace_nt(int M, int N, int K);
 size_t tc_workspace_tn(int M, int N1, int N2);
 // C[M,N] = A[M,K] . B[N,K]^T
@@ -16,5 +18,21 @@ int tc_contract_nt(const float* A, const float* Bm, float* C, int M, int N, int 
 // C[N1,N2] = A[M,N1]^T . B[M,N2]
 int tc_contract_tn(const float* A, const float* Bm, float* C, int M, int N1, int N2, void* ws, size_t ws_bytes,
                    cudaStream_t stream);
+
+// ---- staged interface used by the probit forward / backward (operand planes persist between the two) ----
+// An operand is stored as two planes [2][rows][pitch] (hi | lo) of fp16 (default) or tf32-in-fp32.  A row-major
+// [rows][cols] operand serves both as a K-major operand of the nt product (cols = K) and as an MN-major operand of
+// the tn product (rows = K): the noise planes written by the forward are reused by the backward as they are.
+size_t tc_planes_bytes(int rows, int cols);
+// absmax: device slot holding max|x| as fp32 bits (the fp16 kind scales by 2^-exponent of it); nullptr = scale 1.
+// compute_absmax != 0 runs the reduction first (slot must be zeroed by the caller).
+int tc_split(const float* src, int rows, int cols, void* planes, uint32_t* absmax, int compute_absmax, cudaStream_t stream);
+// standard normals (Philox4x32-10, same stream of numbers as philox_normal_kernel) written directly as planes
+int tc_philox_planes(void* planes, int S, int B, int Z, int B_global, int row0, uint64_t seed, uint64_t offset,
+                     cudaStream_t stream);
+int tc_gemm_nt(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, const uint32_t* absmax_a,
+               const uint32_t* absmax_b, cudaStream_t stream);
+int tc_gemm_tn(const void* a_planes, const void* b_planes, float* C, int M, int N1, int N2, const uint32_t* absmax_a,
+               const uint32_t* absmax_b, cudaStream_t stream);
 
 }  // namespace mpv

@@ -114,13 +114,14 @@ class VAE(nn.Module):
         return label_out, label_mu, label_logvar, feat_out, feat_mu, feat_logvar
 
 
-def draw_noise(args, n_sample, n_batch, device, noise=None):
-    """The (S, B, Z) standard-normal tensor of mpvae.py:162 in one of the three modes above."""
+def noise_plan(args, n_sample, n_batch, device, noise=None):
+    """How the (S, B, Z) standard-normal tensor of mpvae.py:162 is obtained: returns (tensor | None, spec | None).
+    A spec (S, seed, offset, B_global, row0) means the library draws the Philox normals itself."""
     if noise is not None:
-        return noise.to(device=device, dtype=torch.float32)
+        return noise.to(device=device, dtype=torch.float32), None
     mode = getattr(args, "noise_mode", "philox")
     if mode == "reference":
-        return torch.normal(0, 1, size=(n_sample, n_batch, args.z_dim)).to(device)
+        return torch.normal(0, 1, size=(n_sample, n_batch, args.z_dim)).to(device), None
     if mode != "philox":
         raise ValueError(f"args.noise_mode={mode!r}: expected 'philox' or 'reference'")
     seed = getattr(args, "noise_seed", None)
@@ -130,8 +131,17 @@ def draw_noise(args, n_sample, n_batch, device, noise=None):
     if offset is None:
         offset = _state["offset"]
         _state["offset"] += 1
+    return None, (n_sample, seed, offset, getattr(args, "dp_global_batch", None), getattr(args, "dp_row0", 0))
+
+
+def draw_noise(args, n_sample, n_batch, device, noise=None):
+    """The noise tensor itself (materialised; the loss path normally never needs it in Philox mode)."""
+    tensor, spec = noise_plan(args, n_sample, n_batch, device, noise)
+    if tensor is not None:
+        return tensor
+    _, seed, offset, b_global, row0 = spec
     return philox_normal(n_sample, n_batch, args.z_dim, seed=seed, offset=offset, device=device,
-                         global_batch=getattr(args, "dp_global_batch", None), row0=getattr(args, "dp_row0", 0))
+                         global_batch=b_global, row0=row0)
 
 
 def compute_loss(input_label, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r_sqrt_sigma, args, noise=None):
@@ -149,10 +159,10 @@ def compute_loss(input_label, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar
         empty = fx_out.new_empty((0, fx_out.shape[1]))
         return (nan, nan.clone(), nan.clone(), nan.clone(), nan.clone(), nan.clone(), empty, empty.clone())
     r32 = r_sqrt_sigma.to(device).float()                # mpvae.py:165 -- outside the Function: grad returns as fp64
-    noise = draw_noise(args, n_sample, n_batch, device, noise)
+    noise, spec = noise_plan(args, n_sample, n_batch, device, noise)
     flags = int(getattr(args, "mpvae_flags", 0))
     return ProbitELBO.apply(input_label.float(), fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise,
-                            float(args.nll_coeff), float(args.c_coeff), flags)
+                            float(args.nll_coeff), float(args.c_coeff), flags, spec)
 
 
 probit_elbo = compute_loss

@@ -20,10 +20,12 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
-def _check_inputs(y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise):
+def _check_inputs(y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise, noise_spec):
     tensors = (y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise)
     dev = y.device
     for name, t in zip(_NAMES, tensors):
+        if t is None:
+            continue
         if not t.is_cuda:
             raise RuntimeError(f"mpvae_b200: {name} is on {t.device}; the probit ELBO runs on CUDA only "
                                "(there is no CPU fallback)")
@@ -33,7 +35,10 @@ def _check_inputs(y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, no
             raise TypeError(f"mpvae_b200: {name} must be float32, got {t.dtype}")
     B, L = fe_out.shape
     D = fe_mu.shape[1]
-    S, Bn, Z = noise.shape
+    if noise is not None:
+        S, Bn, Z = noise.shape
+    else:
+        S, Bn, Z = int(noise_spec[0]), B, r32.shape[1]
     if y.shape != (B, L) or fx_out.shape != (B, L):
         raise ValueError(f"label / logit shapes disagree: {tuple(y.shape)}, {tuple(fe_out.shape)}, {tuple(fx_out.shape)}")
     for name, t in (("fe_mu", fe_mu), ("fe_logvar", fe_logvar), ("fx_mu", fx_mu), ("fx_logvar", fx_logvar)):
@@ -46,15 +51,35 @@ def _check_inputs(y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, no
     return S, B, L, Z, D
 
 
+def _set_noise_spec(p, spec, B):
+    if spec is None:
+        p.noise_seed = p.noise_offset = 0
+        p.noise_b_global, p.noise_row0 = B, 0
+        return
+    _, seed, offset, b_global, row0 = spec
+    p.noise_seed = int(seed) & (2 ** 64 - 1)
+    p.noise_offset = int(offset) & (2 ** 64 - 1)
+    p.noise_b_global = int(b_global if b_global is not None else B)
+    p.noise_row0 = int(row0)
+
+
 class ProbitELBO(torch.autograd.Function):
-    """(y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, R32, noise) -> the 8-tuple of mpvae.py:210."""
+    """(y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, R32, noise) -> the 8-tuple of mpvae.py:210.
+
+    `noise` is either the (S, B, Z) tensor or None, in which case `noise_spec` = (S, seed, offset, B_global, row0)
+    and the library draws the Philox normals itself, straight into the contraction engine's operand layout."""
 
     @staticmethod
-    def forward(ctx, y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise, nll_coeff, c_coeff, flags):
+    def forward(ctx, y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise, nll_coeff, c_coeff, flags,
+                noise_spec=None):
         lib = _lib.lib()
-        y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise = (
-            t.contiguous() for t in (y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise))
-        S, B, L, Z, D = _check_inputs(y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise)
+        y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32 = (
+            t.contiguous() for t in (y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32))
+        if noise is not None:
+            noise = noise.contiguous()
+        elif noise_spec is None:
+            raise ValueError("ProbitELBO needs either a noise tensor or a noise_spec")
+        S, B, L, Z, D = _check_inputs(y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise, noise_spec)
         dev = y.device
         want_bwd = any(ctx.needs_input_grad)
         with torch.cuda.device(dev):
@@ -71,6 +96,7 @@ class ProbitELBO(torch.autograd.Function):
             p.y, p.fe_out, p.fx_out = _ptr(y), _ptr(fe_out), _ptr(fx_out)
             p.fe_mu, p.fe_logvar, p.fx_mu, p.fx_logvar = _ptr(fe_mu), _ptr(fe_logvar), _ptr(fx_mu), _ptr(fx_logvar)
             p.r, p.noise = _ptr(r32), _ptr(noise)
+            _set_noise_spec(p, noise_spec, B)
             for i in range(6):
                 p.scalars[i] = scalars[i].data_ptr()
             p.indiv_prob, p.indiv_prob_label = _ptr(prob), _ptr(prob_label)
@@ -78,7 +104,10 @@ class ProbitELBO(torch.autograd.Function):
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             _lib.check(lib.mpvae_probit_forward(C.byref(p), stream), "mpvae_probit_forward")
         if want_bwd:
-            ctx.save_for_backward(y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise, ws)
+            ctx.has_noise = noise is not None
+            ctx.noise_spec = noise_spec
+            ctx.save_for_backward(y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, ws,
+                                  *([noise] if noise is not None else []))
             ctx.dims = (S, B, L, Z, D)
             ctx.coeffs = (float(nll_coeff), float(c_coeff), int(flags))
             ctx.set_materialize_grads(False)
@@ -87,7 +116,8 @@ class ProbitELBO(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_total, g_nll, g_nll_x, g_c, g_c_x, g_kl, g_prob, g_prob_label):
         lib = _lib.lib()
-        y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise, ws = ctx.saved_tensors
+        y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, ws = ctx.saved_tensors[:9]
+        noise = ctx.saved_tensors[9] if ctx.has_noise else None
         S, B, L, Z, D = ctx.dims
         nll_coeff, c_coeff, flags = ctx.coeffs
         dev = y.device
@@ -117,6 +147,7 @@ class ProbitELBO(torch.autograd.Function):
             p.y, p.fe_out, p.fx_out = _ptr(y), _ptr(fe_out), _ptr(fx_out)
             p.fe_mu, p.fe_logvar, p.fx_mu, p.fx_logvar = _ptr(fe_mu), _ptr(fe_logvar), _ptr(fx_mu), _ptr(fx_logvar)
             p.r, p.noise = _ptr(r32), _ptr(noise)
+            _set_noise_spec(p, ctx.noise_spec, B)
             for i in range(6):
                 p.g_scalars[i] = g_scal[i].data_ptr() if g_scal[i] is not None else None
             p.g_indiv_prob, p.g_indiv_prob_label = _ptr(g_prob), _ptr(g_prob_label)
@@ -126,8 +157,8 @@ class ProbitELBO(torch.autograd.Function):
             p.workspace, p.workspace_bytes = _ptr(ws), ws.numel()
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             _lib.check(lib.mpvae_probit_backward(C.byref(p), stream), "mpvae_probit_backward")
-        #       y     fe_out    fe_mu      fe_logvar  fx_out    fx_mu      fx_logvar  r32  noise nll_c c_c flags
-        return (None, g_fe_out, g_mulv[0], g_mulv[1], g_fx_out, g_mulv[2], g_mulv[3], g_r, None, None, None, None)
+        #       y     fe_out    fe_mu      fe_logvar  fx_out    fx_mu      fx_logvar  r32  noise nll_c c_c flags spec
+        return (None, g_fe_out, g_mulv[0], g_mulv[1], g_fx_out, g_mulv[2], g_mulv[3], g_r, None, None, None, None, None)
 
 
 def philox_normal(S, B, Z, *, seed, offset=0, device="cuda", global_batch=None, row0=0):
