@@ -46,6 +46,7 @@ enum { SLOT_COUNTER = 0, SLOT_ABSMAX_R = 1, SLOT_ABSMAX_GXS = 2 };
 bool use_tensor(uint32_t flags, int S, int B, int L, int Z) {
     if (flags & MPVAE_FLAG_CONTRACT_FMA) return false;
     if (!tc_available()) return false;
+    if (Z < 8 || L < 8) return false;   // the plane writers assume at least a few elements per row
     if (flags & MPVAE_FLAG_CONTRACT_TENSOR) return true;
     // dense-GEMM regime (north star: label / rank sets >= 128)
     return Z >= 128 && L >= 128 && (long long)S * B >= 128;
