@@ -100,7 +100,8 @@ int mpvae_philox_normal(float *noise, int32_t S, int32_t B, int32_t Z, int32_t B
                         uint64_t seed, uint64_t offset, void *cuda_stream);
 
 /* C[M,N] = A[M,K] . B[N,K]^T (fp32).  The contraction of mpvae.py:168 as a stand-alone entry
- * (A = noise viewed (S*B, Z), B = R).  engine: 0 = auto, 1 = CUDA-core FMA, 2 = tcgen05 3xTF32. */
+ * (A = noise viewed (S*B, Z), B = R).  engine: 0 = auto, 1 = CUDA-core FMA, 2 = tcgen05 split-precision,
+ * 3 = tcgen05 reusing the operand planes an engine-2 call left in the same workspace (GEMM kernel alone). */
 int mpvae_contract_nt(const float *A, const float *Bm, float *C, int32_t M, int32_t N, int32_t K, int32_t engine,
                       void *workspace, uint64_t workspace_bytes, void *cuda_stream);
 

@@ -253,9 +253,9 @@ int mpvae_contract_nt(const float* A, const float* Bm, float* C, int32_t M, int3
     if (!A || !Bm || !C || M <= 0 || N <= 0 || K <= 0) { set_error("contract_nt: bad arguments"); return 1; }
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     if (engine == 0) engine = use_tensor(0, 1, M, N, K) ? 2 : 1;
-    if (engine == 2) {
+    if (engine == 2 || engine == 3) {
         if (!tc_available()) { set_error("contract_nt: tensor engine not built"); return 7; }
-        return tc_contract_nt(A, Bm, C, M, N, K, workspace, workspace_bytes, stream);
+        return tc_contract_nt(A, Bm, C, M, N, K, workspace, workspace_bytes, stream, engine == 3);
     }
     return launch_contract_nt_fma(A, Bm, C, M, N, K, stream);
 }
@@ -265,9 +265,9 @@ int mpvae_contract_tn(const float* A, const float* Bm, float* C, int32_t M, int3
     if (!A || !Bm || !C || M <= 0 || N1 <= 0 || N2 <= 0) { set_error("contract_tn: bad arguments"); return 1; }
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     if (engine == 0) engine = use_tensor(0, 1, M, N1, N2) ? 2 : 1;
-    if (engine == 2) {
+    if (engine == 2 || engine == 3) {
         if (!tc_available()) { set_error("contract_tn: tensor engine not built"); return 7; }
-        return tc_contract_tn(A, Bm, C, M, N1, N2, workspace, workspace_bytes, stream);
+        return tc_contract_tn(A, Bm, C, M, N1, N2, workspace, workspace_bytes, stream, engine == 3);
     }
     return launch_contract_tn_fma(A, Bm, C, M, N1, N2, workspace, workspace_bytes, stream);
 }

@@ -758,14 +758,16 @@ size_t tc_workspace_tn(int M, int N1, int N2) {
 }
 
 int tc_contract_nt(const float* A, const float* Bm, float* C, int M, int N, int K, void* ws, size_t ws_bytes,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, int reuse_planes) {
     if (!ws || ws_bytes < tc_workspace_nt(M, N, K)) { set_error("tc_contract_nt: workspace too small"); return 5; }
     const bool f16 = use_f16();
     const int kp = pitch_of(K);
     const Scratch s = carve_scratch(ws, M, kp);
-    if (f16 && cudaMemsetAsync(s.absmax, 0, 256, stream) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return 2; }
-    if (int rc = split_operand(A, s.a, M, K, kp, f16, s.absmax, stream)) return rc;
-    if (int rc = split_operand(Bm, s.b, N, K, kp, f16, s.absmax + 1, stream)) return rc;
+    if (!reuse_planes) {
+        if (f16 && cudaMemsetAsync(s.absmax, 0, 256, stream) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return 2; }
+        if (int rc = split_operand(A, s.a, M, K, kp, f16, s.absmax, stream)) return rc;
+        if (int rc = split_operand(Bm, s.b, N, K, kp, f16, s.absmax + 1, stream)) return rc;
+    }
     CUtensorMap ma, mb;
     const int bk = f16 ? 64 : 32;
     if (int rc = make_map(&ma, s.a, f16, K, M, kp, bk, BM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
@@ -775,14 +777,16 @@ int tc_contract_nt(const float* A, const float* Bm, float* C, int M, int N, int 
 }
 
 int tc_contract_tn(const float* A, const float* Bm, float* C, int M, int N1, int N2, void* ws, size_t ws_bytes,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, int reuse_planes) {
     if (!ws || ws_bytes < tc_workspace_tn(M, N1, N2)) { set_error("tc_contract_tn: workspace too small"); return 5; }
     const bool f16 = use_f16();
     const int p1 = pitch_of(N1), p2 = pitch_of(N2);
     const Scratch s = carve_scratch(ws, M, p1);
-    if (f16 && cudaMemsetAsync(s.absmax, 0, 256, stream) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return 2; }
-    if (int rc = split_operand(A, s.a, M, N1, p1, f16, s.absmax, stream)) return rc;
-    if (int rc = split_operand(Bm, s.b, M, N2, p2, f16, s.absmax + 1, stream)) return rc;
+    if (!reuse_planes) {
+        if (f16 && cudaMemsetAsync(s.absmax, 0, 256, stream) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return 2; }
+        if (int rc = split_operand(A, s.a, M, N1, p1, f16, s.absmax, stream)) return rc;
+        if (int rc = split_operand(Bm, s.b, M, N2, p2, f16, s.absmax + 1, stream)) return rc;
+    }
     CUtensorMap ma, mb;
     const int bk = f16 ? 64 : 32, box_mn = f16 ? 64 : 32;
     const CUtensorMapSwizzle sw = f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;

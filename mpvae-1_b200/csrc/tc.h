@@ -13,11 +13,13 @@ bool tc_available();
 size_t tc_workspace_nt(int M, int N, int K);
 size_t tc_workspace_tn(int M, int N1, int N2);
 // C[M,N] = A[M,K] . B[N,K]^T
+// reuse_planes != 0: skip the split pre-pass and use the operand planes a previous call left in `ws`
+// (lets a caller time the GEMM kernel alone)
 int tc_contract_nt(const float* A, const float* Bm, float* C, int M, int N, int K, void* ws, size_t ws_bytes,
-                   cudaStream_t stream);
+                   cudaStream_t stream, int reuse_planes = 0);
 // C[N1,N2] = A[M,N1]^T . B[M,N2]
 int tc_contract_tn(const float* A, const float* Bm, float* C, int M, int N1, int N2, void* ws, size_t ws_bytes,
-                   cudaStream_t stream);
+                   cudaStream_t stream, int reuse_planes = 0);
 
 // ---- staged interface used by the probit forward / backward (operand planes persist between the two) ----
 // An operand is stored as two planes [2][rows][pitch] (hi | lo) of fp16 (default) or tf32-in-fp32.  A row-major

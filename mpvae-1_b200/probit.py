@@ -179,8 +179,9 @@ def philox_normal(S, B, Z, *, seed, offset=0, device="cuda", global_batch=None, 
     return out
 
 
-def contract_nt(a, b, engine=0):
-    """C[M,N] = A[M,K] . B[N,K]^T through the library (the product of mpvae.py:168)."""
+def contract_nt(a, b, engine=0, ws=None):
+    """C[M,N] = A[M,K] . B[N,K]^T through the library (the product of mpvae.py:168).  `ws` (a uint8 tensor from a
+    previous call, see `contract_workspace`) lets engine 3 reuse the operand planes engine 2 prepared."""
     lib = _lib.lib()
     a, b = a.contiguous(), b.contiguous()
     M, K = a.shape
@@ -189,11 +190,18 @@ def contract_nt(a, b, engine=0):
     out = torch.empty((M, N), dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
         nbytes = int(lib.mpvae_contract_workspace_bytes(M, N, K, engine))
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
+        if ws is None:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
         stream = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
         _lib.check(lib.mpvae_contract_nt(_ptr(a), _ptr(b), _ptr(out), M, N, K, engine, _ptr(ws), nbytes, stream),
                    "mpvae_contract_nt")
     return out
+
+
+def contract_workspace(M, N, K, device, engine=2):
+    """Scratch for contract_nt / contract_tn that can be handed back in to reuse the prepared operand planes."""
+    nbytes = int(_lib.lib().mpvae_contract_workspace_bytes(M, N, K, engine))
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
 
 
 def contract_tn(a, b, engine=0):
