@@ -331,32 +331,45 @@ def run_b200(a):
         np.random.seed(4)
         torch.manual_seed(0)
         vae = M.VAE(margs).to(dev)
-        opt = torch.optim.Adam(vae.parameters(), lr=1e-3, weight_decay=1e-5)
+        opt = torch.optim.Adam(vae.parameters(), lr=torch.tensor(1e-3, device=dev), weight_decay=1e-5, capturable=True)
         sched = torch.optim.lr_scheduler.StepLR(opt, 1000, 0.5)
         stepper = DataParallelStep(vae, opt, sched, margs, clip_norm=100.0)
         rng = np.random.RandomState(5)
         xg = torch.from_numpy(synth.features(Bg, sh.feature_dim, rng)).to(dev)
         yg = torch.from_numpy(synth.labels(Bg, L, sh.label_rate, rng)).to(dev)
-        for _ in range(3):
-            stepper.step(yg, xg)
-        barrier()
         k_train = max(3, min(a.steps, 20))
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_wall = time.perf_counter()
-        e0.record()
-        for _ in range(k_train):
-            out_t = stepper.step(yg, xg)
-        e1.record()
-        torch.cuda.synchronize()
-        t_wall = time.perf_counter() - t_wall
-        t_dev = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-        train = {"steps_per_s": k_train / (t_dev.item() * 1e-3), "ms_per_step": t_dev.item() / k_train,
-                 "wall_ms_per_step": t_wall * 1e3 / k_train, "steps": k_train, "global_batch": Bg,
-                 "params": int(sum(p.numel() for p in vae.parameters())), "loss": float(out_t.total_loss),
+
+        def time_steps(fn):
+            for _ in range(3):
+                fn(yg, xg)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_wall = time.perf_counter()
+            e0.record()
+            for _ in range(k_train):
+                out = fn(yg, xg)
+            e1.record()
+            torch.cuda.synchronize()
+            t_wall = time.perf_counter() - t_wall
+            t_dev = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+            return t_dev.item() / k_train, t_wall * 1e3 / k_train, out
+
+        eager_ms, eager_wall, out_t = time_steps(stepper.step)
+        train = {"steps_per_s": 1e3 / eager_ms, "ms_per_step": eager_ms, "wall_ms_per_step": eager_wall,
+                 "steps": k_train, "global_batch": Bg, "params": int(sum(p.numel() for p in vae.parameters())),
+                 "loss": float(out_t.total_loss),
                  "what": "zero_grad, VAE fwd (torch/cuBLAS), probit ELBO fwd+bwd (this library), MLP bwd, "
                          "grad all-reduce, clip_grad_norm_(100), Adam(wd=1e-5), StepLR; per-step host metrics excluded"}
+        try:   # the same step captured once as a CUDA graph and replayed (mpvae_b200.train.GraphedTrainStep)
+            from mpvae_b200.train import GraphedTrainStep
+            graphed = GraphedTrainStep(stepper)
+            g_ms, g_wall, out_g = time_steps(graphed.step)
+            train["cuda_graph"] = {"steps_per_s": 1e3 / g_ms, "ms_per_step": g_ms, "wall_ms_per_step": g_wall,
+                                   "loss": float(out_g.total_loss)}
+        except Exception as exc:   # noqa: BLE001 - the graph leg is informative, never fatal for the bench line
+            train["cuda_graph"] = {"error": repr(exc)[:200]}
         del vae, opt, stepper
 
     if rank != 0:

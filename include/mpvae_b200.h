@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPVAE_ABI_VERSION 4
+#define MPVAE_ABI_VERSION 5
 
 /* flags */
 #define MPVAE_FLAG_SANITIZE_DEGENERATE 0x1u /* rows with n_pos*n_neg == 0 get zero ranking gradient instead of
@@ -81,6 +81,8 @@ typedef struct mpvae_probit_params {
        regime).  The backward must be given the same values. ---- */
     uint64_t noise_seed, noise_offset;
     int32_t noise_b_global, noise_row0;
+    const uint64_t *noise_offset_dev; /* optional DEVICE counter added to noise_offset inside the kernel, so that a
+                                         captured CUDA graph draws fresh noise on every replay; NULL = unused */
 } mpvae_probit_params;
 
 /* Bytes of scratch for one forward(+backward) call.  want_backward=0 sizes the inference path. */

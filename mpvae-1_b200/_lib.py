@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmpvae_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 FLAG_SANITIZE_DEGENERATE = 0x1
 FLAG_CONTRACT_TENSOR = 0x2
 FLAG_CONTRACT_FMA = 0x4
@@ -42,6 +42,7 @@ class ProbitParams(C.Structure):
         ("workspace", _f), ("workspace_bytes", C.c_uint64),
         ("noise_seed", C.c_uint64), ("noise_offset", C.c_uint64),
         ("noise_b_global", C.c_int32), ("noise_row0", C.c_int32),
+        ("noise_offset_dev", _f),
     ]
 
 

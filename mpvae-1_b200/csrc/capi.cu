@@ -181,7 +181,7 @@ int mpvae_probit_forward(const mpvae_probit_params* p, void* cuda_stream) {
         void* npl = base + w.noise_planes;
         void* rpl = base + w.r_planes;
         if (p->noise) rc = tc_split(p->noise, M, p->Z, npl, nullptr, 0, stream);   // |N(0,1)| fits fp16 at scale 1
-        else rc = tc_philox_planes(npl, p->S, p->B, p->Z, p->noise_b_global, p->noise_row0, p->noise_seed, p->noise_offset, stream);
+        else rc = tc_philox_planes(npl, p->S, p->B, p->Z, p->noise_b_global, p->noise_row0, p->noise_seed, p->noise_offset, p->noise_offset_dev, stream);
         if (rc) return rc;
         if ((rc = tc_split(p->r, p->L, p->Z, rpl, slots + SLOT_ABSMAX_R, 1, stream))) return rc;
         rc = tc_gemm_nt(npl, rpl, nr, M, p->L, p->Z, nullptr, slots + SLOT_ABSMAX_R, stream);
@@ -190,7 +190,7 @@ int mpvae_probit_forward(const mpvae_probit_params* p, void* cuda_stream) {
         if (!nz) {
             float* gen = reinterpret_cast<float*>(base + w.noise_f32);
             if ((rc = launch_philox_normal(gen, p->S, p->B, p->Z, p->noise_b_global, p->noise_row0, p->noise_seed,
-                                           p->noise_offset, stream))) return rc;
+                                           p->noise_offset, p->noise_offset_dev, stream))) return rc;
             nz = gen;
         }
         rc = launch_contract_nt_fma(nz, p->r, nr, M, p->L, p->Z, stream);
@@ -234,7 +234,7 @@ int mpvae_philox_normal(float* noise, int32_t S, int32_t B, int32_t Z, int32_t B
         set_error("philox: bad sizes S=%d B=%d Z=%d B_global=%d row0=%d", S, B, Z, B_global, row0);
         return 1;
     }
-    return launch_philox_normal(noise, S, B, Z, B_global, row0, seed, offset, static_cast<cudaStream_t>(cuda_stream));
+    return launch_philox_normal(noise, S, B, Z, B_global, row0, seed, offset, nullptr, static_cast<cudaStream_t>(cuda_stream));
 }
 
 uint64_t mpvae_contract_workspace_bytes(int32_t M, int32_t N, int32_t K, int32_t engine) {

@@ -120,7 +120,8 @@ SplitPlan plan_tn(int M, int N1, int N2) {
     if (N2 <= 16) tiles = ceil_div(N2, 16) * ceil_div(N1, 128);
     else if (N2 <= 64 || N1 <= 64) tiles = ceil_div(N2, 64) * ceil_div(N1, 64);
     else tiles = ceil_div(N2, 128) * ceil_div(N1, 128);
-    int splits = ceil_div(2 * kNumSMs, tiles);
+    // the reduction streams gxs from HBM with no reuse when N2 is small: keep ~8 CTAs per SM in flight
+    int splits = ceil_div(8 * kNumSMs, tiles);
     const int max_splits = ceil_div(M, 64);
     if (splits > max_splits) splits = max_splits;
     if (splits > 64) splits = 64;

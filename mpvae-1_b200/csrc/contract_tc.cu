@@ -821,14 +821,15 @@ namespace {
 // counter -> element mapping as philox_normal_kernel, so the numbers are identical to the fp32 tensor it would write.
 template <bool F16>
 __global__ void __launch_bounds__(256)
-philox_planes_kernel(void* __restrict__ planes, int S, int B, int Z, int pitch, int Bg, int row0, uint2 key, uint2 off) {
+philox_planes_kernel(void* __restrict__ planes, int S, int B, int Z, int pitch, int Bg, int row0, uint2 key, uint2 off,
+                     const unsigned long long* __restrict__ off_dev) {
     const int s = blockIdx.y;
     const unsigned long long span_beg = ((unsigned long long)s * Bg + row0) * Z;
     const unsigned long long span_end = span_beg + (unsigned long long)B * Z;
     const unsigned long long c = (span_beg >> 2) + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     if ((c << 2) >= span_end) return;
     float n[4];
-    philox_normal4(c, key, off, n);
+    philox_normal4(c, key, philox_offset(off, off_dev), n);
     const size_t plane = (size_t)S * B * pitch;
     // position of flat index 4c inside this sample's (B, Z) block (B * Z < 2^31 is checked by the launcher);
     // one 32-bit division per thread, then walk the four elements
@@ -858,15 +859,16 @@ philox_planes_kernel(void* __restrict__ planes, int S, int B, int Z, int pitch, 
 }  // namespace
 
 int tc_philox_planes(void* planes, int S, int B, int Z, int Bg, int row0, uint64_t seed, uint64_t offset,
-                     cudaStream_t stream) {
+                     const uint64_t* offset_dev, cudaStream_t stream) {
     if (S > 65535) { set_error("philox: S=%d exceeds grid.y limit", S); return 6; }
     if ((long long)B * Z >= 0x7fffffffLL || Z < 4) { set_error("philox planes: B*Z=%lld, Z=%d out of range", (long long)B * Z, Z); return 6; }
     const unsigned long long counters = ((unsigned long long)B * Z + 3) / 4 + 1;
     dim3 grid((unsigned)((counters + 255) / 256), S);
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     const uint2 off = make_uint2((uint32_t)offset, (uint32_t)(offset >> 32));
-    if (use_f16()) philox_planes_kernel<true><<<grid, 256, 0, stream>>>(planes, S, B, Z, pitch_of(Z), Bg, row0, key, off);
-    else philox_planes_kernel<false><<<grid, 256, 0, stream>>>(planes, S, B, Z, pitch_of(Z), Bg, row0, key, off);
+    const unsigned long long* od = reinterpret_cast<const unsigned long long*>(offset_dev);
+    if (use_f16()) philox_planes_kernel<true><<<grid, 256, 0, stream>>>(planes, S, B, Z, pitch_of(Z), Bg, row0, key, off, od);
+    else philox_planes_kernel<false><<<grid, 256, 0, stream>>>(planes, S, B, Z, pitch_of(Z), Bg, row0, key, off, od);
     return check_launch("philox_planes_kernel");
 }
 

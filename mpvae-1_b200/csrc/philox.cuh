@@ -29,6 +29,13 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
     n1 = r * sn;
 }
 
+// Stream offset: the host value plus an optional device-side counter (CUDA-graph replays bump the counter).
+__device__ __forceinline__ uint2 philox_offset(uint2 off, const unsigned long long* off_dev) {
+    if (off_dev == nullptr) return off;
+    const unsigned long long o = (((unsigned long long)off.y << 32) | off.x) + *off_dev;
+    return make_uint2((uint32_t)o, (uint32_t)(o >> 32));
+}
+
 // The four standard normals of counter c (flat indices 4c .. 4c+3 of the GLOBAL (S, B_global, Z) tensor).
 __device__ __forceinline__ void philox_normal4(unsigned long long c, uint2 key, uint2 off, float (&n)[4]) {
     const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), off.x, off.y), key);

@@ -368,9 +368,11 @@ int launch_row_forward(RowArgs a, cudaStream_t stream) {
     a.nwl = pick_nwl(a.L);
     const size_t smem = row_smem_bytes(a.L);
     if (smem > 200 * 1024) { set_error("label_dim %d needs %zu B of shared memory per row (limit 200 KiB)", a.L, smem); return 3; }
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(probit_row_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static bool configured = false;   // once, to the cap: later launches (e.g. under CUDA-graph capture) make no driver calls
+    if (smem > 48 * 1024 && !configured) {
+        cudaError_t e = cudaFuncSetAttribute(probit_row_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(fwd): %s", cudaGetErrorString(e)); return 4; }
+        configured = true;
     }
     probit_row_fwd_kernel<<<a.B, kThreads, smem, stream>>>(a);
     return check_launch("probit_row_fwd_kernel");
@@ -380,9 +382,11 @@ int launch_row_backward(RowArgs a, cudaStream_t stream) {
     a.nwl = pick_nwl(a.L);
     const size_t smem = row_smem_bytes(a.L);
     if (smem > 200 * 1024) { set_error("label_dim %d needs %zu B of shared memory per row (limit 200 KiB)", a.L, smem); return 3; }
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(probit_row_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static bool configured = false;
+    if (smem > 48 * 1024 && !configured) {
+        cudaError_t e = cudaFuncSetAttribute(probit_row_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(bwd): %s", cudaGetErrorString(e)); return 4; }
+        configured = true;
     }
     probit_row_bwd_kernel<<<a.B, kThreads, smem, stream>>>(a);
     return check_launch("probit_row_bwd_kernel");

@@ -46,6 +46,6 @@ int launch_contract_tn_fma(const float* A, const float* Bm, float* C, int M, int
 
 // Philox noise (philox.cu)
 int launch_philox_normal(float* noise, int S, int B, int Z, int B_global, int row0, uint64_t seed, uint64_t offset,
-                         cudaStream_t stream);
+                         const uint64_t* offset_dev, cudaStream_t stream);
 
 }  // namespace mpv

@@ -31,7 +31,7 @@ size_t tc_planes_bytes(int rows, int cols);
 int tc_split(const float* src, int rows, int cols, void* planes, uint32_t* absmax, int compute_absmax, cudaStream_t stream);
 // standard normals (Philox4x32-10, same stream of numbers as philox_normal_kernel) written directly as planes
 int tc_philox_planes(void* planes, int S, int B, int Z, int B_global, int row0, uint64_t seed, uint64_t offset,
-                     cudaStream_t stream);
+                     const uint64_t* offset_dev, cudaStream_t stream);
 int tc_gemm_nt(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, const uint32_t* absmax_a,
                const uint32_t* absmax_b, cudaStream_t stream);
 int tc_gemm_tn(const void* a_planes, const void* b_planes, float* C, int M, int N1, int N2, const uint32_t* absmax_a,

@@ -131,7 +131,8 @@ def noise_plan(args, n_sample, n_batch, device, noise=None):
     if offset is None:
         offset = _state["offset"]
         _state["offset"] += 1
-    return None, (n_sample, seed, offset, getattr(args, "dp_global_batch", None), getattr(args, "dp_row0", 0))
+    return None, (n_sample, seed, offset, getattr(args, "dp_global_batch", None), getattr(args, "dp_row0", 0),
+                  getattr(args, "noise_offset_tensor", None))
 
 
 def draw_noise(args, n_sample, n_batch, device, noise=None):
@@ -139,7 +140,9 @@ def draw_noise(args, n_sample, n_batch, device, noise=None):
     tensor, spec = noise_plan(args, n_sample, n_batch, device, noise)
     if tensor is not None:
         return tensor
-    _, seed, offset, b_global, row0 = spec
+    _, seed, offset, b_global, row0, counter = spec
+    if counter is not None:
+        offset = int(offset) + int(counter.item())
     return philox_normal(n_sample, n_batch, args.z_dim, seed=seed, offset=offset, device=device,
                          global_batch=b_global, row0=row0)
 

@@ -52,11 +52,17 @@ def _check_inputs(y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, no
 
 
 def _set_noise_spec(p, spec, B):
+    p.noise_offset_dev = None
     if spec is None:
         p.noise_seed = p.noise_offset = 0
         p.noise_b_global, p.noise_row0 = B, 0
         return
-    _, seed, offset, b_global, row0 = spec
+    _, seed, offset, b_global, row0 = spec[:5]
+    if len(spec) > 5 and spec[5] is not None:     # device-side int64 counter added to the offset (CUDA graphs)
+        counter = spec[5]
+        if not (counter.is_cuda and counter.dtype == torch.int64 and counter.numel() == 1):
+            raise TypeError("noise offset counter must be a 1-element int64 CUDA tensor")
+        p.noise_offset_dev = counter.data_ptr()
     p.noise_seed = int(seed) & (2 ** 64 - 1)
     p.noise_offset = int(offset) & (2 ** 64 - 1)
     p.noise_b_global = int(b_global if b_global is not None else B)

@@ -186,3 +186,72 @@ def train_one_epoch(step: DataParallelStep, feats, labels, batch_size: int, orde
             continue          # the reference computes NaN losses on the empty batch and steps on them; we skip it
         outs.append(step.step(labels[idx], feats[idx]))
     return outs
+
+
+class GraphedTrainStep:
+    """The whole training step (train.py:103-129) captured ONCE per batch size as a CUDA graph and replayed.
+
+    For the reference's small configurations (yeast, mirflickr: 14-81 labels, batch 128) the step is a few hundred
+    tiny launches, so the GPU idles while Python dispatches them; replaying a captured graph removes that host work.
+    What makes the step capturable:
+      * inputs live in static device buffers (`step()` copies the batch in, then replays);
+      * the Philox stream offset is a DEVICE counter the noise kernel reads and the graph increments, so every replay
+        draws fresh noise (`mpvae_probit_params.noise_offset_dev`);
+      * Adam runs with `capturable=True` and a tensor learning rate; StepLR keeps running on the host between
+        replays and writes the new rate into that tensor;
+      * gradients are views into the flat bucket (no per-step allocation), the NCCL all-reduce is graph-capturable.
+    Not supported in graph mode: `skip_nonfinite` (needs a host decision) and Python-side regularisers that branch
+    on data.  Outputs are static tensors that the next replay overwrites."""
+
+    def __init__(self, stepper: DataParallelStep, warmup: int = 3):
+        if stepper.skip_nonfinite:
+            raise ValueError("GraphedTrainStep cannot skip non-finite steps (host decision); use DataParallelStep")
+        self.stepper = stepper
+        self.warmup = warmup
+        self.graphs = {}
+        dev = next(stepper.model.parameters()).device
+        self.device = dev
+        self.counter = torch.zeros(1, dtype=torch.int64, device=dev)      # Philox offset, bumped inside the graph
+        stepper.args.noise_offset_tensor = self.counter
+        stepper.args.noise_offset_auto = False
+        stepper.args.noise_offset = 0
+        for group in stepper.optimizer.param_groups:
+            if "capturable" in group and not group["capturable"]:
+                raise ValueError("construct the optimizer with capturable=True for graph capture")
+
+    def _capture(self, y, x):
+        st = self.stepper
+        static_y, static_x = y.clone(), x.clone()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):                                  # also initialises optimizer state
+                self._body(static_y, static_x)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self._body(static_y, static_x)
+        return {"graph": graph, "y": static_y, "x": static_x, "out": out}
+
+    def _body(self, y, x):
+        st = self.stepper
+        sched, st.scheduler = st.scheduler, None                          # the scheduler is stepped on the host
+        try:
+            out = st.step(y, x)
+        finally:
+            st.scheduler = sched
+        self.counter.add_(1)
+        return out
+
+    def step(self, input_label: torch.Tensor, input_feat: torch.Tensor) -> StepOutput:
+        key = (tuple(input_label.shape), tuple(input_feat.shape))
+        entry = self.graphs.get(key)
+        if entry is None:
+            entry = self.graphs[key] = self._capture(input_label, input_feat)
+            # the warm-up + capture already consumed this batch `warmup` times; from here on every call is one step
+        entry["y"].copy_(input_label)
+        entry["x"].copy_(input_feat)
+        entry["graph"].replay()
+        if self.stepper.scheduler is not None:
+            self.stepper.scheduler.step()
+        return entry["out"]

@@ -122,3 +122,39 @@ def test_inference_path_matches_oracle():
             got.append(mine[6])
     assert probs.shape == (200, 81)
     assert float(probs.min()) > 0 and float(probs.max()) < 1
+
+
+def test_graphed_step_equals_eager_step():
+    """GraphedTrainStep (CUDA-graph replay, device-side Philox counter) walks the same trajectory as the eager
+    DataParallelStep when the host-visible randomness is removed (no dropout, collapsed posteriors)."""
+    from mpvae_b200.mpvae import VAE
+    from mpvae_b200.train import DataParallelStep, GraphedTrainStep
+    x, y = yeast_data(640)
+
+    def build():
+        args = yeast_args(keep_prob=0.0, noise_seed=77)
+        np.random.seed(4); torch.manual_seed(0)
+        vae = VAE(args).to(DEV)
+        with torch.no_grad():
+            for head in (vae.fe_logvar, vae.fx_logvar):
+                head.weight.zero_(); head.bias.fill_(-30.0)
+        opt = torch.optim.Adam(vae.parameters(), lr=torch.tensor(1e-3, device=DEV), weight_decay=1e-5, capturable=True)
+        sched = torch.optim.lr_scheduler.StepLR(opt, 4, 0.5)
+        return vae, DataParallelStep(vae, opt, sched, args, clip_norm=100.0)
+
+    batches = [(y[i * 128:(i + 1) * 128], x[i * 128:(i + 1) * 128]) for i in range(5)]
+    vae_g, st_g = build()
+    graphed = GraphedTrainStep(st_g, warmup=3)
+    losses_g = [float(graphed.step(*b).total_loss) for b in batches]
+    vae_e, st_e = build()
+    # the graphed path spends `warmup` extra (scheduler-less) steps on the first batch before its first replay
+    sched, st_e.scheduler = st_e.scheduler, None
+    for _ in range(3):
+        st_e.step(*batches[0])
+    st_e.scheduler = sched
+    losses_e = [float(st_e.step(*b).total_loss) for b in batches]
+    for a, b in zip(losses_g, losses_e):
+        assert abs(a - b) <= 2e-4 * abs(b), (losses_g, losses_e)
+    for (n, p), (_, q) in zip(vae_g.named_parameters(), vae_e.named_parameters()):
+        assert torch.allclose(p.double(), q.double(), rtol=1e-3, atol=2e-5), n
+    assert float(st_g.optimizer.param_groups[0]["lr"]) == pytest.approx(float(st_e.optimizer.param_groups[0]["lr"]))
