@@ -77,13 +77,13 @@ class DataParallelStep:
 
     def __init__(self, model: nn.Module, optimizer, scheduler, args, *, clip_norm: float = 100.0,
                  skip_nonfinite: bool = False, group=None, loss_fn: Optional[Callable] = None,
-                 regulariser: Optional[Callable] = None):
+                 regulariser: Optional[Callable] = None, distributed: bool = True):
         self.model, self.optimizer, self.scheduler = model, optimizer, scheduler
         self.args = copy.copy(args)
         self.clip_norm = clip_norm                 # 100 in train.py:126, 10 in fairsoft_train.py:141
         self.skip_nonfinite = skip_nonfinite       # has_finite_grad guard of fairsoft_train.py:142
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.world = dist.get_world_size(group) if (distributed and dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         if loss_fn is None:
             from .mpvae import compute_loss as loss_fn
