@@ -43,6 +43,9 @@ struct Workspace {
 // 32-bit slots of the 256-byte `slots` block
 enum { SLOT_COUNTER = 0, SLOT_ABSMAX_R = 1, SLOT_ABSMAX_GXS = 2 };
 
+// row pitch (floats) of the (S,B,L) scratch cubes nr and gxs: 16-byte aligned rows for vector loads / stores
+int row_pitch(int L) { return (L + 3) & ~3; }
+
 bool use_tensor(uint32_t flags, int S, int B, int L, int Z) {
     if (flags & MPVAE_FLAG_CONTRACT_FMA) return false;
     if (!tc_available()) return false;
@@ -56,7 +59,7 @@ Workspace carve(int S, int B, int L, int Z, bool want_backward, uint32_t flags) 
     Workspace w{};
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    const size_t cube = (size_t)S * B * L;
+    const size_t cube = (size_t)S * B * row_pitch(L);
     w.nr = take(cube * sizeof(float));
     w.lp = take((size_t)B * S * 2 * sizeof(double));
     w.stat = take((size_t)B * S * 4 * sizeof(float));
@@ -127,6 +130,7 @@ RowArgs row_args(const mpvae_probit_params* p, const Workspace& w) {
     char* base = static_cast<char*>(p->workspace);
     RowArgs a{};
     a.S = p->S; a.B = p->B; a.L = p->L; a.D = p->D;
+    a.ldn = row_pitch(p->L);
     a.sanitize = (p->flags & MPVAE_FLAG_SANITIZE_DEGENERATE) ? 1 : 0;
     a.nll_coeff = p->nll_coeff; a.c_coeff = p->c_coeff;
     a.y = p->y; a.fe_out = p->fe_out; a.fx_out = p->fx_out;
@@ -184,7 +188,7 @@ int mpvae_probit_forward(const mpvae_probit_params* p, void* cuda_stream) {
         else rc = tc_philox_planes(npl, p->S, p->B, p->Z, p->noise_b_global, p->noise_row0, p->noise_seed, p->noise_offset, p->noise_offset_dev, stream);
         if (rc) return rc;
         if ((rc = tc_split(p->r, p->L, p->Z, rpl, slots + SLOT_ABSMAX_R, 1, stream))) return rc;
-        rc = tc_gemm_nt(npl, rpl, nr, M, p->L, p->Z, nullptr, slots + SLOT_ABSMAX_R, stream);
+        rc = tc_gemm_nt(npl, rpl, nr, M, p->L, p->Z, nullptr, slots + SLOT_ABSMAX_R, stream, row_pitch(p->L));
     } else {
         const float* nz = p->noise;
         if (!nz) {
@@ -193,7 +197,7 @@ int mpvae_probit_forward(const mpvae_probit_params* p, void* cuda_stream) {
                                            p->noise_offset, p->noise_offset_dev, stream))) return rc;
             nz = gen;
         }
-        rc = launch_contract_nt_fma(nz, p->r, nr, M, p->L, p->Z, stream);
+        rc = launch_contract_nt_fma(nz, p->r, nr, M, p->L, p->Z, stream, row_pitch(p->L));
     }
     if (rc) return rc;
     return launch_row_forward(row_args(p, w), stream);
@@ -219,12 +223,13 @@ int mpvae_probit_backward(const mpvae_probit_params* p, void* cuda_stream) {
     const int M = p->S * p->B;
     if (tensor) {
         void* gpl = base + w.gxs_planes;
-        if (int rc = tc_split(a.gxs, M, p->L, gpl, slots + SLOT_ABSMAX_GXS, 0, stream)) return rc;   // absmax came from the row kernel
+        if (int rc = tc_split(a.gxs, M, p->L, gpl, slots + SLOT_ABSMAX_GXS, 0, stream, row_pitch(p->L))) return rc;   // absmax: row kernel
         // the noise planes the forward left in the workspace are the MN-major B operand as they are
         return tc_gemm_tn(gpl, base + w.noise_planes, p->g_r, M, p->L, p->Z, slots + SLOT_ABSMAX_GXS, nullptr, stream);
     }
     const float* nz = p->noise ? p->noise : reinterpret_cast<const float*>(base + w.noise_f32);
-    return launch_contract_tn_fma(a.gxs, nz, p->g_r, M, p->L, p->Z, base + w.fma_partials, w.total - w.fma_partials, stream);
+    return launch_contract_tn_fma(a.gxs, nz, p->g_r, M, p->L, p->Z, base + w.fma_partials, w.total - w.fma_partials, stream,
+                                  row_pitch(p->L));
 }
 
 int mpvae_philox_normal(float* noise, int32_t S, int32_t B, int32_t Z, int32_t B_global, int32_t row0, uint64_t seed,

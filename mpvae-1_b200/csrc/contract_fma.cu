@@ -133,8 +133,8 @@ SplitPlan plan_tn(int M, int N1, int N2) {
 
 }  // namespace
 
-int launch_contract_nt_fma(const float* A, const float* Bm, float* C, int M, int N, int K, cudaStream_t stream) {
-    return launch_gemm<true, true>(A, Bm, C, M, N, K, K, K, N, 1, K, 0, stream);
+int launch_contract_nt_fma(const float* A, const float* Bm, float* C, int M, int N, int K, cudaStream_t stream, int ldc) {
+    return launch_gemm<true, true>(A, Bm, C, M, N, K, K, K, ldc > 0 ? ldc : N, 1, K, 0, stream);
 }
 
 size_t contract_tn_fma_workspace(int M, int N1, int N2) {
@@ -143,16 +143,17 @@ size_t contract_tn_fma_workspace(int M, int N1, int N2) {
 }
 
 int launch_contract_tn_fma(const float* A, const float* Bm, float* C, int M, int N1, int N2, void* ws, size_t ws_bytes,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, int lda) {
     const SplitPlan p = plan_tn(M, N1, N2);
     const size_t n = (size_t)N1 * N2;
-    if (p.splits == 1) return launch_gemm<false, false>(A, Bm, C, N1, N2, M, N1, N2, N2, 1, M, 0, stream);
+    if (lda <= 0) lda = N1;
+    if (p.splits == 1) return launch_gemm<false, false>(A, Bm, C, N1, N2, M, lda, N2, N2, 1, M, 0, stream);
     if (ws == nullptr || ws_bytes < (size_t)p.splits * n * sizeof(float)) {
         set_error("contract_tn: workspace too small (%zu < %zu)", ws_bytes, (size_t)p.splits * n * sizeof(float));
         return 5;
     }
     float* part = static_cast<float*>(ws);
-    int rc = launch_gemm<false, false>(A, Bm, part, N1, N2, M, N1, N2, N2, p.splits, p.k_per_split, n, stream);
+    int rc = launch_gemm<false, false>(A, Bm, part, N1, N2, M, lda, N2, N2, p.splits, p.k_per_split, n, stream);
     if (rc) return rc;
     const int blocks = (int)((n + 255) / 256 < 4 * kNumSMs ? (n + 255) / 256 : 4 * kNumSMs);
     splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(part, C, n, p.splits);

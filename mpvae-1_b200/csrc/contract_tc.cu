@@ -287,6 +287,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const float sb = absmax_b ? scale_from_absmax_bits(*absmax_b) : 1.0f;
             inv_scale = 1.0f / (sa * sb);                        // powers of two: exact
         }
+        const bool vec_store = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15u) == 0;
         float acc[64];
 #pragma unroll
         for (int j = 0; j < 64; ++j) acc[j] = 0.0f;
@@ -315,9 +316,17 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int col0 = (tile % tiles_n) * BN + h * 64;
             if (row < Mc) {
                 float* __restrict__ crow = C + (size_t)row * ldc;
+                if (vec_store && col0 + 64 <= ldc) {
+                    // 16-byte stores: rows are 16 B aligned (ldc % 4 == 0); columns in [Nc, ldc) are pitch padding
 #pragma unroll
-                for (int j = 0; j < 64; ++j)
-                    if (col0 + j < Nc) crow[col0 + j] = acc[j] * inv_scale;
+                    for (int j = 0; j < 64; j += 4)
+                        *reinterpret_cast<float4*>(crow + col0 + j) =
+                            make_float4(acc[j] * inv_scale, acc[j + 1] * inv_scale, acc[j + 2] * inv_scale, acc[j + 3] * inv_scale);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 64; ++j)
+                        if (col0 + j < Nc) crow[col0 + j] = acc[j] * inv_scale;
+                }
             }
 #pragma unroll
             for (int j = 0; j < 64; ++j) acc[j] = 0.0f;
@@ -518,6 +527,7 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const float sb = absmax_b ? scale_from_absmax_bits(*absmax_b) : 1.0f;
             inv_scale = 1.0f / (sa * sb);
         }
+        const bool vec_store = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15u) == 0;
         float acc[64];
 #pragma unroll
         for (int j = 0; j < 64; ++j) acc[j] = 0.0f;
@@ -546,9 +556,17 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const int col0 = (tile % tiles_n) * BN + h * 64;
             if (row < Mc) {
                 float* __restrict__ crow = C + (size_t)row * ldc;
+                if (vec_store && col0 + 64 <= ldc) {
+                    // 16-byte stores: rows are 16 B aligned (ldc % 4 == 0); columns in [Nc, ldc) are pitch padding
 #pragma unroll
-                for (int j = 0; j < 64; ++j)
-                    if (col0 + j < Nc) crow[col0 + j] = acc[j] * inv_scale;
+                    for (int j = 0; j < 64; j += 4)
+                        *reinterpret_cast<float4*>(crow + col0 + j) =
+                            make_float4(acc[j] * inv_scale, acc[j + 1] * inv_scale, acc[j + 2] * inv_scale, acc[j + 3] * inv_scale);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 64; ++j)
+                        if (col0 + j < Nc) crow[col0 + j] = acc[j] * inv_scale;
+                }
             }
 #pragma unroll
             for (int j = 0; j < 64; ++j) acc[j] = 0.0f;
@@ -566,13 +584,14 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 // ------------------------------------------------------------------------------------------------ pre-passes
 // hi = tf32(x) (round to nearest, ties away), lo = tf32(x - hi); dst planes are [rows][dpitch], pad columns zero.
 __global__ void __launch_bounds__(256)
-split_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, int dpitch, size_t plane) {
+split_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, int spitch, int dpitch,
+                  size_t plane) {
     const size_t n = (size_t)rows * dpitch;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / dpitch), c = (int)(i % dpitch);
         float hi = 0.0f, lo = 0.0f;
         if (c < cols) {
-            const float x = src[(size_t)r * cols + c];
+            const float x = src[(size_t)r * spitch + c];
             uint32_t h, l;
             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
             hi = __uint_as_float(h);
@@ -602,16 +621,16 @@ absmax_kernel(const float* __restrict__ src, size_t n, uint32_t* __restrict__ ou
 
 // hi = fp16(x * s), lo = fp16(x * s - hi) with s from the tensor's absmax; two elements per thread.
 __global__ void __launch_bounds__(256)
-split_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int rows, int cols, int dpitch, size_t plane,
-                 const uint32_t* __restrict__ absmax) {
+split_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int rows, int cols, int spitch, int dpitch,
+                 size_t plane, const uint32_t* __restrict__ absmax) {
     const float s = absmax ? scale_from_absmax_bits(*absmax) : 1.0f;
     const size_t n2 = (size_t)rows * dpitch / 2;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
         const size_t e = 2 * i;
         const int r = (int)(e / dpitch), c = (int)(e % dpitch);
         float x0 = 0.0f, x1 = 0.0f;
-        if (c < cols) x0 = src[(size_t)r * cols + c] * s;
-        if (c + 1 < cols) x1 = src[(size_t)r * cols + c + 1] * s;
+        if (c < cols) x0 = src[(size_t)r * spitch + c] * s;
+        if (c + 1 < cols) x1 = src[(size_t)r * spitch + c + 1] * s;
         const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
         const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
         reinterpret_cast<__half2*>(dst)[i] = __halves2half2(h0, h1);
@@ -690,14 +709,14 @@ Scratch carve_scratch(void* ws, size_t rows_a, size_t pitch_a) {
 int split_operand(const float* src, void* dst, int rows, int cols, int pitch, bool f16, uint32_t* absmax, cudaStream_t stream) {
     const size_t n = (size_t)rows * pitch;
     if (!f16) {
-        split_tf32_kernel<<<grid_for(n), 256, 0, stream>>>(src, static_cast<float*>(dst), rows, cols, pitch, n);
+        split_tf32_kernel<<<grid_for(n), 256, 0, stream>>>(src, static_cast<float*>(dst), rows, cols, cols, pitch, n);
         return check_launch("split_tf32_kernel");
     }
     if (absmax) {
         absmax_kernel<<<grid_for((size_t)rows * cols), 256, 0, stream>>>(src, (size_t)rows * cols, absmax);
         if (int rc = check_launch("absmax_kernel")) return rc;
     }
-    split_f16_kernel<<<grid_for(n / 2), 256, 0, stream>>>(src, static_cast<__half*>(dst), rows, cols, pitch, n, absmax);
+    split_f16_kernel<<<grid_for(n / 2), 256, 0, stream>>>(src, static_cast<__half*>(dst), rows, cols, cols, pitch, n, absmax);
     return check_launch("split_f16_kernel");
 }
 
@@ -799,19 +818,21 @@ int tc_contract_tn(const float* A, const float* Bm, float* C, int M, int N1, int
 // ------------------------------------------------------------------------------------------------ staged interface
 size_t tc_planes_bytes(int rows, int cols) { return planes_bytes((size_t)rows, (size_t)pitch_of(cols)); }
 
-int tc_split(const float* src, int rows, int cols, void* planes, uint32_t* absmax, int compute_absmax, cudaStream_t stream) {
+int tc_split(const float* src, int rows, int cols, void* planes, uint32_t* absmax, int compute_absmax, cudaStream_t stream,
+             int src_pitch) {
     const bool f16 = use_f16();
+    if (src_pitch <= 0) src_pitch = cols;
     const int pitch = pitch_of(cols);
     const size_t n = (size_t)rows * pitch;
     if (!f16) {
-        split_tf32_kernel<<<grid_for(n), 256, 0, stream>>>(src, static_cast<float*>(planes), rows, cols, pitch, n);
+        split_tf32_kernel<<<grid_for(n), 256, 0, stream>>>(src, static_cast<float*>(planes), rows, cols, src_pitch, pitch, n);
         return check_launch("split_tf32_kernel");
     }
     if (absmax && compute_absmax) {
         absmax_kernel<<<grid_for((size_t)rows * cols), 256, 0, stream>>>(src, (size_t)rows * cols, absmax);
         if (int rc = check_launch("absmax_kernel")) return rc;
     }
-    split_f16_kernel<<<grid_for(n / 2), 256, 0, stream>>>(src, static_cast<__half*>(planes), rows, cols, pitch, n, absmax);
+    split_f16_kernel<<<grid_for(n / 2), 256, 0, stream>>>(src, static_cast<__half*>(planes), rows, cols, src_pitch, pitch, n, absmax);
     return check_launch("split_f16_kernel");
 }
 
@@ -873,14 +894,15 @@ int tc_philox_planes(void* planes, int S, int B, int Z, int Bg, int row0, uint64
 }
 
 int tc_gemm_nt(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, const uint32_t* absmax_a,
-               const uint32_t* absmax_b, cudaStream_t stream) {
+               const uint32_t* absmax_b, cudaStream_t stream, int ldc) {
+    if (ldc <= 0) ldc = N;
     const bool f16 = use_f16();
     const int kp = pitch_of(K), bk = f16 ? 64 : 32;
     CUtensorMap ma, mb;
     if (int rc = make_map(&ma, a_planes, f16, K, M, kp, bk, BM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     if (int rc = make_map(&mb, b_planes, f16, K, N, kp, bk, (cta_group() == 2 ? BN / 2 : BN), CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    if (f16) return launch_gemm<false, true>(ma, mb, C, M, N, K, N, absmax_a, absmax_b, stream);
-    return launch_gemm<false, false>(ma, mb, C, M, N, K, N, nullptr, nullptr, stream);
+    if (f16) return launch_gemm<false, true>(ma, mb, C, M, N, K, ldc, absmax_a, absmax_b, stream);
+    return launch_gemm<false, false>(ma, mb, C, M, N, K, ldc, nullptr, nullptr, stream);
 }
 
 int tc_gemm_tn(const void* a_planes, const void* b_planes, float* C, int M, int N1, int N2, const uint32_t* absmax_a,

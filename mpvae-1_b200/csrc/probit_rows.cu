@@ -31,13 +31,13 @@ struct RowChunk { float y, fe, fx, nr[kST]; };
 
 __device__ __forceinline__ void load_chunk(RowChunk& in, const float* __restrict__ nr, const float* __restrict__ yrow,
                                            const float* __restrict__ ferow, const float* __restrict__ fxrow, int c, int lane,
-                                           int L, int S, int B, int b, int s0) {
+                                           int L, int ldn, int S, int B, int b, int s0) {
     const int l = (c << 5) + lane;
     if (l < L) {
         in.y = yrow[l]; in.fe = ferow[l]; in.fx = fxrow[l];
 #pragma unroll
         for (int i = 0; i < kST; ++i)
-            in.nr[i] = (s0 + i < S) ? nr[((size_t)(s0 + i) * B + b) * L + l] : 0.0f;
+            in.nr[i] = (s0 + i < S) ? nr[((size_t)(s0 + i) * B + b) * ldn + l] : 0.0f;
     }
 }
 
@@ -98,9 +98,9 @@ probit_row_fwd_kernel(const RowArgs a) {
             // (ncu: 31 % of the stall samples of the unpipelined loop sat on the first use of nr)
             RowChunk cur, nxt;
             int c = wl;
-            if (c < nchunks) load_chunk(cur, a.nr, yrow, ferow, fxrow, c, lane, L, S, B, b, s0);
+            if (c < nchunks) load_chunk(cur, a.nr, yrow, ferow, fxrow, c, lane, L, a.ldn, S, B, b, s0);
             for (; c < nchunks; c += nwl) {
-                if (c + nwl < nchunks) load_chunk(nxt, a.nr, yrow, ferow, fxrow, c + nwl, lane, L, S, B, b, s0);
+                if (c + nwl < nchunks) load_chunk(nxt, a.nr, yrow, ferow, fxrow, c + nwl, lane, L, a.ldn, S, B, b, s0);
                 const int l = (c << 5) + lane;
                 if (l < L) {
                     float pl = 0.0f, px = 0.0f;
@@ -295,9 +295,9 @@ probit_row_bwd_kernel(const RowArgs a) {
         float* __restrict__ gacc = s_gacc + (size_t)ws * 2 * L;
         RowChunk cur, nxt;
         int c = wl;
-        if (c < nchunks) load_chunk(cur, a.nr, yrow, ferow, fxrow, c, lane, L, S, B, b, s0);
+        if (c < nchunks) load_chunk(cur, a.nr, yrow, ferow, fxrow, c, lane, L, a.ldn, S, B, b, s0);
         for (; c < nchunks; c += nwl) {
-            if (c + nwl < nchunks) load_chunk(nxt, a.nr, yrow, ferow, fxrow, c + nwl, lane, L, S, B, b, s0);
+            if (c + nwl < nchunks) load_chunk(nxt, a.nr, yrow, ferow, fxrow, c + nwl, lane, L, a.ldn, S, B, b, s0);
             const int l = (c << 5) + lane;
             if (l < L) {
                 const float gpl = has_gpl ? a.g_indiv_prob_label[(size_t)b * L + l] / fS : 0.0f;
@@ -311,7 +311,7 @@ probit_row_bwd_kernel(const RowArgs a) {
                         gl += dl; gx += dx;
                         if (a.gxs) {
                             const float g = dl + dx;
-                            a.gxs[((size_t)(s0 + i) * B + b) * L + l] = g;
+                            a.gxs[((size_t)(s0 + i) * B + b) * a.ldn + l] = g;
                             const unsigned int gb = __float_as_uint(g) & 0x7FFFFFFFu;   // |g| as ordered bits, NaN highest
                             gmax = gb > gmax ? gb : gmax;
                         }

@@ -13,7 +13,8 @@ struct RowArgs {
     int sanitize;   // MPVAE_FLAG_SANITIZE_DEGENERATE
     float nll_coeff, c_coeff;
     const float *y, *fe_out, *fx_out, *fe_mu, *fe_logvar, *fx_mu, *fx_logvar;
-    const float* nr;   // (S,B,L) noise.R^T
+    int ldn;           // row pitch (floats) of nr and gxs: L rounded up to a multiple of 4 (16-byte aligned rows)
+    const float* nr;   // (S,B,ldn) noise.R^T
     // saved statistics (workspace)
     double* lp;        // (B,S,2)  Bernoulli log-likelihood per sample: label branch, feature branch
     float* stat;       // (B,S,4)  pos_l, neg_l, pos_x, neg_x ranking factors
@@ -39,10 +40,11 @@ int launch_row_backward(RowArgs a, cudaStream_t stream);
 // CUDA-core contraction (contract_fma.cu)
 //   nt: C[M,N] = A[M,K] . B[N,K]^T
 //   tn: C[N1,N2] = A[M,N1]^T . B[M,N2]   (split over M, partials reduced in a fixed order)
-int launch_contract_nt_fma(const float* A, const float* Bm, float* C, int M, int N, int K, cudaStream_t stream);
+int launch_contract_nt_fma(const float* A, const float* Bm, float* C, int M, int N, int K, cudaStream_t stream,
+                           int ldc = 0);   // ldc: row pitch of C in floats (0 = N)
 size_t contract_tn_fma_workspace(int M, int N1, int N2);
 int launch_contract_tn_fma(const float* A, const float* Bm, float* C, int M, int N1, int N2, void* ws, size_t ws_bytes,
-                           cudaStream_t stream);
+                           cudaStream_t stream, int lda = 0);   // lda: row pitch of A in floats (0 = N1)
 
 // Philox noise (philox.cu)
 int launch_philox_normal(float* noise, int S, int B, int Z, int B_global, int row0, uint64_t seed, uint64_t offset,

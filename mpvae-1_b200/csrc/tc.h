@@ -28,12 +28,13 @@ int tc_contract_tn(const float* A, const float* Bm, float* C, int M, int N1, int
 size_t tc_planes_bytes(int rows, int cols);
 // absmax: device slot holding max|x| as fp32 bits (the fp16 kind scales by 2^-exponent of it); nullptr = scale 1.
 // compute_absmax != 0 runs the reduction first (slot must be zeroed by the caller).
-int tc_split(const float* src, int rows, int cols, void* planes, uint32_t* absmax, int compute_absmax, cudaStream_t stream);
+int tc_split(const float* src, int rows, int cols, void* planes, uint32_t* absmax, int compute_absmax, cudaStream_t stream,
+             int src_pitch = 0);   // src_pitch: row pitch of src in floats (0 = cols)
 // standard normals (Philox4x32-10, same stream of numbers as philox_normal_kernel) written directly as planes
 int tc_philox_planes(void* planes, int S, int B, int Z, int B_global, int row0, uint64_t seed, uint64_t offset,
                      const uint64_t* offset_dev, cudaStream_t stream);
 int tc_gemm_nt(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, const uint32_t* absmax_a,
-               const uint32_t* absmax_b, cudaStream_t stream);
+               const uint32_t* absmax_b, cudaStream_t stream, int ldc = 0);   // ldc: row pitch of C in floats (0 = N)
 int tc_gemm_tn(const void* a_planes, const void* b_planes, float* C, int M, int N1, int N2, const uint32_t* absmax_a,
                const uint32_t* absmax_b, cudaStream_t stream);
 
