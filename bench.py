@@ -211,10 +211,7 @@ def run_b200(a):
     def one_step(src, from_host):
         args.noise_offset = step_no[0]
         step_no[0] += 1
-        if from_host:
-            t = {k: host[k].to(dev, non_blocking=True) for k in row_keys}
-        else:
-            t = src
+        t = src
         leaves = {k: (t[k] if k == "y" else t[k].requires_grad_(True)) for k in row_keys}
         r32.grad = None
         out = M.compute_loss(leaves["y"], leaves["fe_out"], leaves["fe_mu"], leaves["fe_logvar"], leaves["fx_out"],
@@ -230,6 +227,25 @@ def run_b200(a):
                 t[k].grad = None
                 t[k].requires_grad_(False)
         return out
+
+    def timed_e2e(n_steps):
+        """K steps through the public API starting from pinned HOST buffers: every step's inputs cross PCIe inside the
+        timed region (double-buffered on a side stream by mpvae_b200.train.HostBatchPrefetcher) and the loss comes
+        back to the host.  One event pair around all K steps; the 0.8 GB working set is far larger than L2."""
+        from mpvae_b200.train import HostBatchPrefetcher
+        pf = HostBatchPrefetcher(dev, depth=2)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pf.push(host)
+        for i in range(n_steps):
+            batch = pf.next()
+            if i + 1 < n_steps:
+                pf.push(host)
+            one_step(batch, True)
+            pf.release()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
 
     def timed(n_steps, from_host):
         evs = []
@@ -260,12 +276,10 @@ def run_b200(a):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     total_ms = sum(ms)
-    for _ in range(2):
-        one_step(devt, True)
+    timed_e2e(2)
     barrier()
-    ms_e2e = timed(a.steps, True)
+    total_e2e = timed_e2e(a.steps)
     barrier()
-    total_e2e = sum(ms_e2e)
     if world > 1:
         t = torch.tensor([total_ms, total_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -388,6 +402,7 @@ def run_b200(a):
                    "exchange": "NCCL all-reduce of g_R (fp32) per step" if world > 1 else "none (1 GPU)"},
         "clocks": clocks,
         "e2e": {"value": units / (total_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": bi, "d2h_bytes_per_step": 4,
+                "how": "mpvae_b200.compute_loss + backward from pinned host buffers; H2D double-buffered on a side stream",
                 "ms_per_step": total_e2e / a.steps},
         "gpu_launches": int(launches),
         "loss_steps_per_s": a.steps / (total_ms * 1e-3),

@@ -255,3 +255,49 @@ class GraphedTrainStep:
         if self.stepper.scheduler is not None:
             self.stepper.scheduler.step()
         return entry["out"]
+
+
+class HostBatchPrefetcher:
+    """Double-buffered host -> device staging of a step's inputs (train.py:106-111 does a blocking
+    `torch.from_numpy(...).to(device)` per step).  Batches are copied from PINNED host tensors on a side stream into
+    one of `depth` device slots while the previous step computes; `next()` makes the compute stream wait for the
+    copy and hands out the slot, whose reuse in turn waits for that step's compute to finish."""
+
+    def __init__(self, device, depth: int = 2):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.depth = depth
+        self.slots = [None] * depth
+        self.ready = [None] * depth        # copy finished (recorded on the side stream)
+        self.free = [None] * depth         # compute finished with the slot (recorded on the compute stream)
+        self.head = self.tail = 0          # next slot to fill / to hand out
+
+    def push(self, host_batch: dict):
+        """Start copying `host_batch` (name -> pinned CPU tensor).  At most `depth` batches may be in flight."""
+        i = self.head % self.depth
+        if self.slots[i] is None:
+            self.slots[i] = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host_batch.items()}
+        if self.free[i] is not None:
+            self.stream.wait_event(self.free[i])
+        with torch.cuda.stream(self.stream):
+            for k, v in host_batch.items():
+                self.slots[i][k].copy_(v, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.ready[i] = ev
+        self.head += 1
+
+    def next(self) -> dict:
+        """The oldest staged batch as device tensors; valid until `depth` more batches have been pushed."""
+        assert self.tail < self.head, "nothing staged"
+        i = self.tail % self.depth
+        torch.cuda.current_stream(self.device).wait_event(self.ready[i])
+        self.tail += 1
+        self._last = i
+        return self.slots[i]
+
+    def release(self):
+        """Call after the step that consumed the last `next()` has been enqueued: lets the slot be refilled."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.free[self._last] = ev

@@ -345,3 +345,17 @@ def test_deterministic_and_reusable():
     total += 3.0 * out[6].mean()
     total.backward()
     assert torch.isfinite(t["fx_out"].grad).all()
+
+
+def test_inference_with_many_samples():
+    """main.py:33 defaults n_test_sample to 10000: the sample axis is streamed, not held; checked at S = 2000."""
+    from mpvae_b200 import synth
+    L, Z, B, S = 38, 38, 12, 2000
+    inp = synth.loss_inputs(L, Z, B, S, seed=77, sigma=1.0)
+    noise = inp.pop("noise")
+    got_o, _ = run_cuda(inp, noise, 0.5, 10.0, mode="test")
+    dev_o, _ = run_oracle(inp, noise, 0.5, 10.0, mode="test", device="cuda:0")
+    for k in H.SCALAR_KEYS:
+        assert H.rel_err(got_o[k], dev_o[k]) <= 1e-5, (k, H.rel_err(got_o[k], dev_o[k]))
+    assert H.threshold_mismatches(got_o["indiv_prob"], dev_o["indiv_prob"], tie=2.5e-7) == 0
+    assert float(np.max(np.abs(got_o["indiv_prob"] - dev_o["indiv_prob"]))) <= 2e-6   # S = 2000 fp32 mean
