@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPVAE_ABI_VERSION 5
+#define MPVAE_ABI_VERSION 6
 
 /* flags */
 #define MPVAE_FLAG_SANITIZE_DEGENERATE 0x1u /* rows with n_pos*n_neg == 0 get zero ranking gradient instead of
@@ -111,6 +111,14 @@ int mpvae_contract_nt(const float *A, const float *Bm, float *C, int32_t M, int3
 int mpvae_contract_tn(const float *A, const float *Bm, float *C, int32_t M, int32_t N1, int32_t N2, int32_t engine,
                       void *workspace, uint64_t workspace_bytes, void *cuda_stream);
 uint64_t mpvae_contract_workspace_bytes(int32_t M, int32_t N, int32_t K, int32_t engine);
+
+/* Per-step metrics on the device: replaces evals.compute_metrics(indiv_prob.cpu(), input_label.cpu(), threshold,
+ * all_metrics=False) of train.py:131 / fairsoft_train.py:149 (reference evals.py:178-239).
+ * out[8] (device, fp64) = ACC, HA, ebF1, miF1, maF1, p@1, p@3, p@5.  workspace >= mpvae_batch_metrics_workspace. */
+enum { MPVAE_M_ACC = 0, MPVAE_M_HA, MPVAE_M_EBF1, MPVAE_M_MIF1, MPVAE_M_MAF1, MPVAE_M_P1, MPVAE_M_P3, MPVAE_M_P5 };
+uint64_t mpvae_batch_metrics_workspace(int32_t B, int32_t L);
+int mpvae_batch_metrics(const float *indiv_prob, const float *input_label, int32_t B, int32_t L, float threshold,
+                        double *out, void *workspace, uint64_t workspace_bytes, void *cuda_stream);
 
 const char *mpvae_last_error(void);
 int mpvae_abi_version(void);

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmpvae_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 FLAG_SANITIZE_DEGENERATE = 0x1
 FLAG_CONTRACT_TENSOR = 0x2
 FLAG_CONTRACT_FMA = 0x4
@@ -21,7 +21,7 @@ FLAG_CONTRACT_FMA = 0x4
 EXPORTS = (
     "mpvae_workspace_bytes", "mpvae_probit_forward", "mpvae_probit_backward", "mpvae_philox_normal",
     "mpvae_contract_nt", "mpvae_contract_tn", "mpvae_contract_workspace_bytes", "mpvae_last_error",
-    "mpvae_abi_version", "mpvae_launch_count",
+    "mpvae_abi_version", "mpvae_launch_count", "mpvae_batch_metrics", "mpvae_batch_metrics_workspace",
 )
 
 _f = C.c_void_p  # device pointer
@@ -74,6 +74,11 @@ def _load():
     lib.mpvae_philox_normal.argtypes = [C.c_void_p] + [C.c_int32] * 5 + [C.c_uint64, C.c_uint64, C.c_void_p]
     lib.mpvae_contract_workspace_bytes.restype = C.c_uint64
     lib.mpvae_contract_workspace_bytes.argtypes = [C.c_int32] * 4
+    lib.mpvae_batch_metrics_workspace.restype = C.c_uint64
+    lib.mpvae_batch_metrics_workspace.argtypes = [C.c_int32, C.c_int32]
+    lib.mpvae_batch_metrics.restype = C.c_int
+    lib.mpvae_batch_metrics.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
+                                        C.c_uint64, C.c_void_p]
     for fn in (lib.mpvae_contract_nt, lib.mpvae_contract_tn):
         fn.restype = C.c_int
         fn.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_void_p, C.c_uint64, C.c_void_p]

@@ -242,6 +242,18 @@ int mpvae_philox_normal(float* noise, int32_t S, int32_t B, int32_t Z, int32_t B
     return launch_philox_normal(noise, S, B, Z, B_global, row0, seed, offset, nullptr, static_cast<cudaStream_t>(cuda_stream));
 }
 
+uint64_t mpvae_batch_metrics_workspace(int32_t B, int32_t L) {
+    if (B <= 0 || L <= 0) return 256;
+    return batch_metrics_workspace(B, L);
+}
+
+int mpvae_batch_metrics(const float* indiv_prob, const float* input_label, int32_t B, int32_t L, float threshold, double* out,
+                        void* workspace, uint64_t workspace_bytes, void* cuda_stream) {
+    if (!indiv_prob || !input_label || !out || !workspace || B <= 0 || L <= 0) { set_error("batch_metrics: bad arguments"); return 1; }
+    if (workspace_bytes < batch_metrics_workspace(B, L)) { set_error("batch_metrics: workspace too small"); return 1; }
+    return launch_batch_metrics(indiv_prob, input_label, B, L, threshold, out, workspace, static_cast<cudaStream_t>(cuda_stream));
+}
+
 uint64_t mpvae_contract_workspace_bytes(int32_t M, int32_t N, int32_t K, int32_t engine) {
     // covers both orientations: nt (M,N,K) and tn (M = reduction, N1 = N, N2 = K)
     size_t a = contract_tn_fma_workspace(M, N, K);

@@ -1,0 +1,133 @@
+// On-device per-step metrics: what the reference computes on the host every training step with
+// `evals.compute_metrics(indiv_prob.cpu().data.numpy(), input_label.cpu().data.numpy(), 0.5, all_metrics=False)`
+// (train.py:131, fairsoft_train.py:149; evals.py:178-239) -- a device->host sync, a deepcopy and a numpy pass per step.
+// Here: integer tp / fp / fn per label and per-row statistics in two small kernels, a third one folds them into
+// ACC, HA, ebF1, miF1, maF1 and p@1/3/5 as device scalars (no host sync).  Counts are integers, hence exact.
+#include "common.cuh"
+#include "rows.h"
+
+namespace mpv {
+namespace {
+
+// thread per label: walk the batch (coalesced across threads for a fixed row)
+__global__ void __launch_bounds__(256)
+label_counts_kernel(const float* __restrict__ prob, const float* __restrict__ y, int B, int L, float thr,
+                    int* __restrict__ counts /* [3][L]: tp, fp, fn */) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    int tp = 0, fp = 0, fn = 0;
+    const int b0 = blockIdx.y * 64, b1 = min(B, b0 + 64);     // 64-row slabs; integer atomics keep the sum exact
+    for (int b = b0; b < b1; ++b) {
+        const bool p = prob[(size_t)b * L + l] >= thr;          // evals.py:201-202
+        const bool t = y[(size_t)b * L + l] != 0.0f;            // targets are {0,1}: t * p, !t * p, t * !p (evals.py:61-67)
+        tp += (t && p); fp += (!t && p); fn += (t && !p);
+    }
+    if (tp) atomicAdd(&counts[l], tp);
+    if (fp) atomicAdd(&counts[L + l], fp);
+    if (fn) atomicAdd(&counts[2 * L + l], fn);
+}
+
+// warp per row: exact-match flag, xor count, tp, |pred|, |target|, and the hits among the top-1/3/5 scores
+__global__ void __launch_bounds__(256)
+row_stats_kernel(const float* __restrict__ prob, const float* __restrict__ y, int B, int L, float thr,
+                 int* __restrict__ rows /* [B][8]: xor, tp, npred, ntarg, hit1, hit3, hit5, - */) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const float* __restrict__ pr = prob + (size_t)b * L;
+    const float* __restrict__ yr = y + (size_t)b * L;
+    int nx = 0, tp = 0, np = 0, nt = 0;
+    for (int l = lane; l < L; l += 32) {
+        const bool p = pr[l] >= thr, t = yr[l] != 0.0f;
+        nx += (p != t); tp += (p && t); np += p; nt += t;
+    }
+    nx = warp_sum(nx); tp = warp_sum(tp); np = warp_sum(np); nt = warp_sum(nt);
+    // top-5 by score, ties broken towards the HIGHER index (np.argsort ascending, then reversed: evals.py:37)
+    int hits[3] = {0, 0, 0};
+    float last_v = INFINITY;
+    int last_i = L;     // everything strictly "before" (last_v, last_i) in the descending order is already taken
+    const int kmax = L < 5 ? L : 5;
+    for (int k = 0; k < kmax; ++k) {
+        float bv = -INFINITY;
+        int bi = -1;
+        for (int l = lane; l < L; l += 32) {
+            const float v = pr[l];
+            const bool avail = (v < last_v) || (v == last_v && l < last_i);
+            if (avail && (v > bv || (v == bv && l > bi))) { bv = v; bi = l; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi > bi)) { bv = ov; bi = oi; }
+        }
+        last_v = bv; last_i = bi;
+        const int rel = (bi >= 0 && yr[bi] != 0.0f) ? 1 : 0;
+        if (k < 1) hits[0] += rel;
+        if (k < 3) hits[1] += rel;
+        hits[2] += rel;
+    }
+    if (lane == 0) {
+        int* r = rows + (size_t)b * 8;
+        r[0] = nx; r[1] = tp; r[2] = np; r[3] = nt; r[4] = hits[0]; r[5] = hits[1]; r[6] = hits[2]; r[7] = 0;
+    }
+}
+
+// one CTA: fold the integer statistics into the eight scalars (fixed order, fp64 accumulation)
+__global__ void __launch_bounds__(256)
+metrics_finalize_kernel(const int* __restrict__ counts, const int* __restrict__ rows, int B, int L, double* __restrict__ out) {
+    __shared__ double s_red[8][9];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double acc = 0, ham = 0, ebf = 0, ebn = 0, p1 = 0, p3 = 0, p5 = 0;
+    for (int b = tid; b < B; b += 256) {
+        const int* r = rows + (size_t)b * 8;
+        acc += (r[0] == 0);
+        ham += (double)r[0] / (double)L;
+        const int den = r[2] + r[3];
+        if (den != 0) { ebf += (double)(2.0f * (float)r[1] / (float)den); ebn += 1.0; }     // fp32 ratio as evals.py:84
+        p1 += (double)r[4]; p3 += (double)r[5] / 3.0; p5 += (double)r[6] / 5.0;
+    }
+    double stp = 0, sfp = 0, sfn = 0, maf = 0, man = 0;
+    for (int l = tid; l < L; l += 256) {
+        const float tp = (float)counts[l], fp = (float)counts[L + l], fn = (float)counts[2 * L + l];
+        stp += tp; sfp += fp; sfn += fn;
+        const float c = (2.0f * tp) / (2.0f * tp + fp + fn + 1e-6f);                           // evals.py:108, fp32
+        if (isfinite(c)) { maf += (double)c; man += 1.0; }
+    }
+    double v[12] = {acc, ham, ebf, ebn, p1, p3, p5, stp, sfp, sfn, maf, man};
+#pragma unroll
+    for (int i = 0; i < 12; ++i) v[i] = warp_sum(v[i]);
+    __shared__ double s_all[8][12];
+    if (lane == 0)
+        for (int i = 0; i < 12; ++i) s_all[warp][i] = v[i];
+    __syncthreads();
+    if (tid == 0) {
+        double t[12];
+        for (int i = 0; i < 12; ++i) { t[i] = 0; for (int w = 0; w < 8; ++w) t[i] += s_all[w][i]; }
+        out[0] = t[0] / B;                                   // ACC   subset accuracy
+        out[1] = 1.0 - t[1] / B;                             // HA    1 - hamming loss
+        out[2] = t[3] > 0 ? t[2] / t[3] : NAN;               // ebF1
+        out[3] = (double)((float)(2.0 * t[7]) / (float)(2.0 * t[7] + t[8] + t[9]));   // miF1 (evals.py:97-99)
+        out[4] = t[11] > 0 ? t[10] / t[11] : NAN;            // maF1
+        out[5] = t[4] / B; out[6] = t[5] / B; out[7] = t[6] / B;   // p@1, p@3, p@5
+    }
+    (void)s_red;
+}
+
+}  // namespace
+
+size_t batch_metrics_workspace(int B, int L) { return align_up((size_t)3 * L * sizeof(int), 256) + (size_t)B * 8 * sizeof(int); }
+
+int launch_batch_metrics(const float* prob, const float* y, int B, int L, float thr, double* out, void* ws, cudaStream_t stream) {
+    int* counts = static_cast<int*>(ws);
+    int* rows = reinterpret_cast<int*>(static_cast<char*>(ws) + align_up((size_t)3 * L * sizeof(int), 256));
+    if (cudaMemsetAsync(counts, 0, (size_t)3 * L * sizeof(int), stream) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return 2; }
+    label_counts_kernel<<<dim3(ceil_div(L, 256), ceil_div(B, 64)), 256, 0, stream>>>(prob, y, B, L, thr, counts);
+    if (int rc = check_launch("label_counts_kernel")) return rc;
+    row_stats_kernel<<<ceil_div(B, 8), 256, 0, stream>>>(prob, y, B, L, thr, rows);
+    if (int rc = check_launch("row_stats_kernel")) return rc;
+    metrics_finalize_kernel<<<1, 256, 0, stream>>>(counts, rows, B, L, out);
+    return check_launch("metrics_finalize_kernel");
+}
+
+}  // namespace mpv

@@ -46,6 +46,10 @@ size_t contract_tn_fma_workspace(int M, int N1, int N2);
 int launch_contract_tn_fma(const float* A, const float* Bm, float* C, int M, int N1, int N2, void* ws, size_t ws_bytes,
                            cudaStream_t stream, int lda = 0);   // lda: row pitch of A in floats (0 = N1)
 
+// per-step metrics (metrics.cu)
+size_t batch_metrics_workspace(int B, int L);
+int launch_batch_metrics(const float* prob, const float* y, int B, int L, float thr, double* out, void* ws, cudaStream_t stream);
+
 // Philox noise (philox.cu)
 int launch_philox_normal(float* noise, int S, int B, int Z, int B_global, int row0, uint64_t seed, uint64_t offset,
                          const uint64_t* offset_dev, cudaStream_t stream);
