@@ -195,8 +195,9 @@ def run_b200(a):
     sh, L, Z, B, S = workload(a)
     Bg = B * world
     flags = {"auto": 0, "fma": _lib.FLAG_CONTRACT_FMA, "tensor": _lib.FLAG_CONTRACT_TENSOR}[a.engine]
-    args = orc.make_args(L, Z, n_train_sample=S, mode="train", nll_coeff=0.5, c_coeff=10.0, mpvae_flags=flags,
-                         noise_seed=1234, dp_global_batch=Bg, dp_row0=rank * B)
+    infer = sh.mode == "test"       # BASELINE configs[2] (nuswide) is the test-time path: forward only, no_grad, S = n_test_sample
+    args = orc.make_args(L, Z, n_train_sample=S, n_test_sample=S, mode=sh.mode, nll_coeff=0.5, c_coeff=10.0,
+                         mpvae_flags=flags, noise_seed=1234, dp_global_batch=Bg, dp_row0=rank * B)
 
     inp = synth.loss_inputs(L, Z, B, S, seed=100 + rank, label_rate=sh.label_rate, with_noise=False)
     row_keys = ["y", "fe_out", "fe_mu", "fe_logvar", "fx_out", "fx_mu", "fx_logvar"]
@@ -212,6 +213,13 @@ def run_b200(a):
         args.noise_offset = step_no[0]
         step_no[0] += 1
         t = src
+        if infer:
+            with torch.no_grad():
+                out = M.compute_loss(t["y"], t["fe_out"], t["fe_mu"], t["fe_logvar"], t["fx_out"], t["fx_mu"],
+                                     t["fx_logvar"], r32, args)
+            if from_host:
+                loss_host.copy_(out[0], non_blocking=True)
+            return out
         leaves = {k: (t[k] if k == "y" else t[k].requires_grad_(True)) for k in row_keys}
         r32.grad = None
         out = M.compute_loss(leaves["y"], leaves["fe_out"], leaves["fe_mu"], leaves["fe_logvar"], leaves["fx_out"],
@@ -335,7 +343,7 @@ def run_b200(a):
 
     # ---- full training step (train.py:103-129: VAE fwd -> loss -> bwd -> all-reduce -> clip -> Adam -> StepLR) ----
     train = None
-    if not a.no_train_step:
+    if not a.no_train_step and not infer:
         import numpy as np
         from types import SimpleNamespace
         from mpvae_b200.train import DataParallelStep
@@ -396,7 +404,8 @@ def run_b200(a):
         "metric": METRIC, "value": units / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": max(3, a.warmup), "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{sh.name}-shaped S{S} B{B} L{L} Z{Z} fwd+bwd", "S": S, "B_per_gpu": B, "B_global": Bg,
+        "config": {"workload": f"{sh.name}-shaped S{S} B{B} L{L} Z{Z} " + ("inference (forward, no_grad)" if infer else "fwd+bwd"),
+                   "S": S, "B_per_gpu": B, "B_global": Bg,
                    "L": L, "Z": Z, "D": 50, "noise": "philox (on device, inside the step)", "engine": a.engine,
                    "l2": "L2 flushed between timed iterations (252 MB written); per-step CUDA events summed",
                    "exchange": "NCCL all-reduce of g_R (fp32) per step" if world > 1 else "none (1 GPU)"},
