@@ -385,6 +385,8 @@ def run_b200(a):
                  "what": "zero_grad, VAE fwd (torch/cuBLAS), probit ELBO fwd+bwd (this library), MLP bwd, "
                          "grad all-reduce, clip_grad_norm_(100), Adam(wd=1e-5), StepLR; per-step host metrics excluded"}
         try:   # the same step captured once as a CUDA graph and replayed (mpvae_b200.train.GraphedTrainStep)
+            if world > 1:
+                raise NotImplementedError("graph capture is single-process only")
             from mpvae_b200.train import GraphedTrainStep
             graphed = GraphedTrainStep(stepper)
             g_ms, g_wall, out_g = time_steps(graphed.step)

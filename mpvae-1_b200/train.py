@@ -199,13 +199,17 @@ class GraphedTrainStep:
         draws fresh noise (`mpvae_probit_params.noise_offset_dev`);
       * Adam runs with `capturable=True` and a tensor learning rate; StepLR keeps running on the host between
         replays and writes the new rate into that tensor;
-      * gradients are views into the flat bucket (no per-step allocation), the NCCL all-reduce is graph-capturable.
-    Not supported in graph mode: `skip_nonfinite` (needs a host decision) and Python-side regularisers that branch
+      * gradients are views into the flat bucket (no per-step allocation).
+    Not supported in graph mode: world_size > 1 (see __init__), `skip_nonfinite` (needs a host decision) and Python-side regularisers that branch
     on data.  Outputs are static tensors that the next replay overwrites."""
 
     def __init__(self, stepper: DataParallelStep, warmup: int = 3):
         if stepper.skip_nonfinite:
             raise ValueError("GraphedTrainStep cannot skip non-finite steps (host decision); use DataParallelStep")
+        if stepper.world > 1:
+            # capturing the NCCL all-reduces (one of them issued from an autograd hook thread) hung a 2-rank run on
+            # B200; until that is understood the graph path is single-process only
+            raise NotImplementedError("GraphedTrainStep is single-process only; use DataParallelStep under torchrun")
         self.stepper = stepper
         self.warmup = warmup
         self.graphs = {}
