@@ -298,16 +298,19 @@ def run_b200(a):
     if rank == 0:
         peaks = measured_peaks()
         M_rows = S * B
-        noise = torch.randn(M_rows, Z, device=dev)
+        noise = torch.randn(M_rows, Z, device=dev).half().float()     # on the fp16 grid, like the library's Philox noise
         dense = Z >= 128 and L >= 128 and a.engine != "fma"
         from mpvae_b200.probit import contract_workspace
         reps = 5
         if dense:
-            # engine 2 prepares the hi/lo operand planes (timed separately as `prepass_ms`), engine 3 re-runs the
-            # tcgen05 GEMM kernel alone on them: that launch is the dominant kernel of the step
+            # engine 4 prepares the operand planes, engine 5 re-runs the tcgen05 GEMM kernel alone on them: that launch
+            # (noise as ONE fp16 piece, R as hi|lo: two MMA passes) is the dominant kernel of the Philox-noise step.
+            # MPVAE_TC_CTA=1 has no single-piece variant: engines 2/3, three passes.
+            passes = 2 if os.environ.get("MPVAE_TC_CTA", "2") != "1" else 3
+            e_prep, e_run = (4, 5) if passes == 2 else (2, 3)
             wsk = contract_workspace(M_rows, L, Z, dev, 2)
-            contract_nt(noise, r32.detach(), engine=2, ws=wsk)
-            run = lambda: contract_nt(noise, r32.detach(), engine=3, ws=wsk)
+            contract_nt(noise, r32.detach(), engine=e_prep, ws=wsk)
+            run = lambda: contract_nt(noise, r32.detach(), engine=e_run, ws=wsk)
         else:
             eng = {"auto": 0, "fma": 1, "tensor": 2}[a.engine]
             run = lambda: contract_nt(noise, r32.detach(), engine=eng)
@@ -324,16 +327,16 @@ def run_b200(a):
         flops = 2.0 * M_rows * L * Z
         if dense:
             kind = os.environ.get("MPVAE_TC_KIND", "f16")
-            # split-precision product = 3 tensor-core passes; fp16 pieces run at the bf16 rate, tf32 pieces at half of it
-            div = 3.0 if kind != "tf32" else 6.0
+            # split-precision product = `passes` tensor-core passes; fp16 pieces run at the bf16 rate, tf32 at half of it
+            div = float(passes) if kind != "tf32" else 2.0 * passes
             peak = peaks["bf16_tflops"] / div
             roof = {"bound": "tensor", "achieved": flops / t_k / 1e12, "peak": peak, "unit": "TFLOP/s",
                     "frac": flops / t_k / 1e12 / peak, "traffic": None,
-                    "kernel": "gemm_split_2sm_kernel<nt> (noise.R^T, mpvae.py:168), tcgen05 " + kind + " hi/lo split, 3 MMA passes",
+                    "kernel": "gemm_split_2sm_kernel<nt> (noise.R^T, mpvae.py:168), tcgen05 " + kind + f" hi/lo split, {passes} MMA passes",
                     "kernel_ms": t_k * 1e3,
                     "peak_basis": f"{peaks['_source']} bf16 burst {peaks['bf16_tflops']} TFLOP/s / {div:g} "
-                                  "(fp32-equivalent flops of a 3-pass split-precision product)",
-                    "algorithmic_flops_per_launch": flops, "raw_tensor_tflops": 3.0 * flops / t_k / 1e12}
+                                  f"(fp32-equivalent flops of a {passes}-pass split-precision product)",
+                    "algorithmic_flops_per_launch": flops, "raw_tensor_tflops": passes * flops / t_k / 1e12}
         else:
             bytes_alg = 4.0 * (M_rows * Z + L * Z + M_rows * L)
             roof = {"bound": "hbm", "achieved": bytes_alg / t_k / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",

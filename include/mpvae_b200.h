@@ -78,7 +78,8 @@ typedef struct mpvae_probit_params {
 
     /* ---- library-side noise (noise == NULL): the numbers of mpvae_philox_normal(seed, offset, B_global, row0),
        generated straight into the layout the contraction engine wants (never materialised as fp32 in the dense
-       regime).  The backward must be given the same values. ---- */
+       regime).  These normals lie on the fp16 grid (Box-Muller in fp32, rounded to nearest fp16), which lets the
+       tensor engine treat them as a single operand piece.  The backward must be given the same values. ---- */
     uint64_t noise_seed, noise_offset;
     int32_t noise_b_global, noise_row0;
     const uint64_t *noise_offset_dev; /* optional DEVICE counter added to noise_offset inside the kernel, so that a
@@ -103,7 +104,10 @@ int mpvae_philox_normal(float *noise, int32_t S, int32_t B, int32_t Z, int32_t B
 
 /* C[M,N] = A[M,K] . B[N,K]^T (fp32).  The contraction of mpvae.py:168 as a stand-alone entry
  * (A = noise viewed (S*B, Z), B = R).  engine: 0 = auto, 1 = CUDA-core FMA, 2 = tcgen05 split-precision,
- * 3 = tcgen05 reusing the operand planes an engine-2 call left in the same workspace (GEMM kernel alone). */
+ * 3 = tcgen05 reusing the operand planes an engine-2 call left in the same workspace (GEMM kernel alone),
+ * 4 = tcgen05 with the NOISE operand (A here, B of mpvae_contract_tn) promised to lie on the fp16 grid, as the
+ * library's own Philox noise does: that operand is one piece and the product takes two MMA passes instead of three;
+ * 5 = engine 4 reusing the planes of a previous engine-2/4 call. */
 int mpvae_contract_nt(const float *A, const float *Bm, float *C, int32_t M, int32_t N, int32_t K, int32_t engine,
                       void *workspace, uint64_t workspace_bytes, void *cuda_stream);
 

@@ -188,7 +188,9 @@ int mpvae_probit_forward(const mpvae_probit_params* p, void* cuda_stream) {
         else rc = tc_philox_planes(npl, p->S, p->B, p->Z, p->noise_b_global, p->noise_row0, p->noise_seed, p->noise_offset, p->noise_offset_dev, stream);
         if (rc) return rc;
         if ((rc = tc_split(p->r, p->L, p->Z, rpl, slots + SLOT_ABSMAX_R, 1, stream))) return rc;
-        rc = tc_gemm_nt(npl, rpl, nr, M, p->L, p->Z, nullptr, slots + SLOT_ABSMAX_R, stream, row_pitch(p->L));
+        // library noise sits on the fp16 grid: one plane, two MMA passes
+        rc = tc_gemm_nt(npl, rpl, nr, M, p->L, p->Z, nullptr, slots + SLOT_ABSMAX_R, stream, row_pitch(p->L),
+                        (!p->noise && tc_exact_supported()) ? 1 : 0);
     } else {
         const float* nz = p->noise;
         if (!nz) {
@@ -225,7 +227,8 @@ int mpvae_probit_backward(const mpvae_probit_params* p, void* cuda_stream) {
         void* gpl = base + w.gxs_planes;
         if (int rc = tc_split(a.gxs, M, p->L, gpl, slots + SLOT_ABSMAX_GXS, 0, stream, row_pitch(p->L))) return rc;   // absmax: row kernel
         // the noise planes the forward left in the workspace are the MN-major B operand as they are
-        return tc_gemm_tn(gpl, base + w.noise_planes, p->g_r, M, p->L, p->Z, slots + SLOT_ABSMAX_GXS, nullptr, stream);
+        return tc_gemm_tn(gpl, base + w.noise_planes, p->g_r, M, p->L, p->Z, slots + SLOT_ABSMAX_GXS, nullptr, stream,
+                          (!p->noise && tc_exact_supported()) ? 1 : 0);
     }
     const float* nz = p->noise ? p->noise : reinterpret_cast<const float*>(base + w.noise_f32);
     return launch_contract_tn_fma(a.gxs, nz, p->g_r, M, p->L, p->Z, base + w.fma_partials, w.total - w.fma_partials, stream,
@@ -270,9 +273,10 @@ int mpvae_contract_nt(const float* A, const float* Bm, float* C, int32_t M, int3
     if (!A || !Bm || !C || M <= 0 || N <= 0 || K <= 0) { set_error("contract_nt: bad arguments"); return 1; }
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     if (engine == 0) engine = use_tensor(0, 1, M, N, K) ? 2 : 1;
-    if (engine == 2 || engine == 3) {
+    if (engine >= 2 && engine <= 5) {
         if (!tc_available()) { set_error("contract_nt: tensor engine not built"); return 7; }
-        return tc_contract_nt(A, Bm, C, M, N, K, workspace, workspace_bytes, stream, engine == 3);
+        if (engine >= 4 && !tc_exact_supported()) { set_error("contract_nt: engines 4/5 need the CTA-pair kernel"); return 7; }
+        return tc_contract_nt(A, Bm, C, M, N, K, workspace, workspace_bytes, stream, engine == 3 || engine == 5, engine >= 4);
     }
     return launch_contract_nt_fma(A, Bm, C, M, N, K, stream);
 }
@@ -282,9 +286,10 @@ int mpvae_contract_tn(const float* A, const float* Bm, float* C, int32_t M, int3
     if (!A || !Bm || !C || M <= 0 || N1 <= 0 || N2 <= 0) { set_error("contract_tn: bad arguments"); return 1; }
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     if (engine == 0) engine = use_tensor(0, 1, M, N1, N2) ? 2 : 1;
-    if (engine == 2 || engine == 3) {
+    if (engine >= 2 && engine <= 5) {
         if (!tc_available()) { set_error("contract_tn: tensor engine not built"); return 7; }
-        return tc_contract_tn(A, Bm, C, M, N1, N2, workspace, workspace_bytes, stream, engine == 3);
+        if (engine >= 4 && !tc_exact_supported()) { set_error("contract_tn: engines 4/5 need the CTA-pair kernel"); return 7; }
+        return tc_contract_tn(A, Bm, C, M, N1, N2, workspace, workspace_bytes, stream, engine == 3 || engine == 5, engine >= 4);
     }
     return launch_contract_tn_fma(A, Bm, C, M, N1, N2, workspace, workspace_bytes, stream);
 }

@@ -351,9 +351,20 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 //   empty[s]  (per CTA)      tcgen05.commit multicast to both CTAs
 //   tfull[b]  (per CTA)      tcgen05.commit multicast to both CTAs
 //   tempty[b] (leader only)  one arrive per promotion warp of both CTAs (remote arrive from the peer)
-constexpr int STAGES2 = 3;
-constexpr int STAGE2_BYTES = 2 * A_BYTES + 2 * A_BYTES;   // A hi|lo + half-B hi|lo = 64 KiB
-constexpr int SMEM2_BYTES = 1024 + STAGES2 * STAGE2_BYTES + BAR_BYTES;
+//
+// EX names an operand that is EXACTLY representable in the 11-bit piece format (no lo plane): 1 = A, 2 = B.
+// The library's own Philox noise is drawn on the fp16 grid, so the forward (A = noise) and the backward
+// (B = noise) products need only two MMA passes and three 16 KiB tiles per stage (48 KiB, 4-deep ring).
+template <int EX>
+struct Ring2 {
+    static constexpr int NA = (EX == 1) ? 1 : 2, NB = (EX == 2) ? 1 : 2;       // planes staged per operand
+    static constexpr int STAGE_BYTES = (NA + NB) * A_BYTES;                       // 64 KiB (EX = 0) or 48 KiB
+    static constexpr int STAGES = (EX == 0) ? 3 : 4;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES;
+    static constexpr int MMAS_PER_KSTEP = (EX == 0) ? 3 : 2;
+    // measured truncation bias per k-block relative to the 3-pass constant (profiles/r01_exact_operand.md): 1.30e-7 / 1.85e-7
+    static constexpr float BIAS_SCALE = (EX == 0) ? 1.0f : 0.70f;
+};
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -403,12 +414,14 @@ __device__ __forceinline__ void tc_mma_2sm(uint32_t d_tmem, uint64_t adesc, uint
     }
 }
 
-template <bool MN, bool F16>
+template <bool MN, bool F16, int EX>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       float* __restrict__ C, int Mc, int Nc, int K, int ldc, int tiles_m, int tiles_n, int kc,
                       const uint32_t* __restrict__ absmax_a, const uint32_t* __restrict__ absmax_b, int dbg) {
     using G = Geo<MN, F16>;
+    using R2 = Ring2<EX>;
+    constexpr int STAGES2 = R2::STAGES, STAGE2_BYTES = R2::STAGE_BYTES;
     constexpr int HB = BN / 2;                                // B-tile columns staged by each CTA
     // M = 256 across the pair: same descriptor fields as Geo::idesc with the M field set to 256 >> 4
     constexpr uint32_t idesc2 = (G::idesc & ~(0x1Fu << 24)) | ((uint32_t)(256 >> 4) << 24);
@@ -463,24 +476,24 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         continue;
                     }
                     if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE2_BYTES);
-                    const uint32_t sa = base + stage * STAGE2_BYTES, sb = sa + 2 * A_BYTES;
+                    const uint32_t sa = base + stage * STAGE2_BYTES, sb = sa + R2::NA * A_BYTES;
                     if (!MN) {
-                        tma_load_3d_2sm(sa, &tmA, fb, kb * G::BK, m0, 0);
-                        tma_load_3d_2sm(sa + A_BYTES, &tmA, fb, kb * G::BK, m0, 1);
-                        tma_load_3d_2sm(sb, &tmB, fb, kb * G::BK, n0, 0);
-                        tma_load_3d_2sm(sb + A_BYTES, &tmB, fb, kb * G::BK, n0, 1);
+#pragma unroll
+                        for (int pl = 0; pl < R2::NA; ++pl) tma_load_3d_2sm(sa + pl * A_BYTES, &tmA, fb, kb * G::BK, m0, pl);
+#pragma unroll
+                        for (int pl = 0; pl < R2::NB; ++pl) tma_load_3d_2sm(sb + pl * A_BYTES, &tmB, fb, kb * G::BK, n0, pl);
                     } else {
                         constexpr int box = G::BK * 128;
 #pragma unroll
-                        for (int j = 0; j < BM / G::BOX_MN; ++j) {
-                            tma_load_3d_2sm(sa + j * box, &tmA, fb, m0 + j * G::BOX_MN, kb * G::BK, 0);
-                            tma_load_3d_2sm(sa + A_BYTES + j * box, &tmA, fb, m0 + j * G::BOX_MN, kb * G::BK, 1);
-                        }
+                        for (int j = 0; j < BM / G::BOX_MN; ++j)
 #pragma unroll
-                        for (int j = 0; j < HB / G::BOX_MN; ++j) {
-                            tma_load_3d_2sm(sb + j * box, &tmB, fb, n0 + j * G::BOX_MN, kb * G::BK, 0);
-                            tma_load_3d_2sm(sb + A_BYTES + j * box, &tmB, fb, n0 + j * G::BOX_MN, kb * G::BK, 1);
-                        }
+                            for (int pl = 0; pl < R2::NA; ++pl)
+                                tma_load_3d_2sm(sa + pl * A_BYTES + j * box, &tmA, fb, m0 + j * G::BOX_MN, kb * G::BK, pl);
+#pragma unroll
+                        for (int j = 0; j < HB / G::BOX_MN; ++j)
+#pragma unroll
+                            for (int pl = 0; pl < R2::NB; ++pl)
+                                tma_load_3d_2sm(sb + pl * A_BYTES + j * box, &tmB, fb, n0 + j * G::BOX_MN, kb * G::BK, pl);
                     }
                     if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
                 }
@@ -499,16 +512,25 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
-                        const uint32_t sa = base + stage * STAGE2_BYTES, sb = sa + 2 * A_BYTES;
+                        const uint32_t sa = base + stage * STAGE2_BYTES, sb = sa + R2::NA * A_BYTES;
 #pragma unroll
                         for (int kk = 0; kk < G::BK / G::UK; ++kk) {
                             if (dbg == 2) break;   // timing probe: no MMAs
+                            const uint32_t first = (kb != kb0 || kk != 0) ? 1u : 0u;
                             const uint64_t a_hi = umma_desc(sa + kk * G::kstep, G::lbo, G::sbo, G::layout);
-                            const uint64_t a_lo = umma_desc(sa + A_BYTES + kk * G::kstep, G::lbo, G::sbo, G::layout);
                             const uint64_t b_hi = umma_desc(sb + kk * G::kstep, G::lbo, G::sbo, G::layout);
-                            const uint64_t b_lo = umma_desc(sb + A_BYTES + kk * G::kstep, G::lbo, G::sbo, G::layout);
-                            tc_mma_2sm<F16>(d, a_lo, b_hi, idesc2, (kb != kb0 || kk != 0) ? 1u : 0u);
-                            tc_mma_2sm<F16>(d, a_hi, b_lo, idesc2, 1u);
+                            if (EX == 1) {          // A exact: A.B_lo + A.B_hi
+                                const uint64_t b_lo = umma_desc(sb + A_BYTES + kk * G::kstep, G::lbo, G::sbo, G::layout);
+                                tc_mma_2sm<F16>(d, a_hi, b_lo, idesc2, first);
+                            } else if (EX == 2) {   // B exact: A_lo.B + A_hi.B
+                                const uint64_t a_lo = umma_desc(sa + A_BYTES + kk * G::kstep, G::lbo, G::sbo, G::layout);
+                                tc_mma_2sm<F16>(d, a_lo, b_hi, idesc2, first);
+                            } else {                // small terms first
+                                const uint64_t a_lo = umma_desc(sa + A_BYTES + kk * G::kstep, G::lbo, G::sbo, G::layout);
+                                const uint64_t b_lo = umma_desc(sb + A_BYTES + kk * G::kstep, G::lbo, G::sbo, G::layout);
+                                tc_mma_2sm<F16>(d, a_lo, b_hi, idesc2, first);
+                                tc_mma_2sm<F16>(d, a_hi, b_lo, idesc2, 1u);
+                            }
                             tc_mma_2sm<F16>(d, a_hi, b_hi, idesc2, 1u);
                         }
                         tc_commit_2sm(empty_bar(stage));         // frees the stage in BOTH CTAs
@@ -538,7 +560,7 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 mbar_wait(tfull_bar(buf), bphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + h * 64);
-                const float unbias = 1.0f + G::trunc_bias * (float)(min(kb0 + kc, num_kb) - kb0);
+                const float unbias = 1.0f + G::trunc_bias * R2::BIAS_SCALE * (float)(min(kb0 + kc, num_kb) - kb0);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     uint32_t v[16];
@@ -659,11 +681,11 @@ EncodeTiledFn encode_fn() {
 
 // 3-D map over a split operand [2][rows][pitch]: dims {cols, rows, 2}, 128B swizzle, zero OOB fill.
 int make_map(CUtensorMap* map, const void* ptr, bool f16, int cols, int rows, int pitch, int box_cols, int box_rows,
-             CUtensorMapSwizzle swizzle) {
+             CUtensorMapSwizzle swizzle, int planes = 2) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled unavailable from the driver"); return 8; }
     const cuuint64_t esz = f16 ? 2 : 4;
-    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)planes};
     cuuint64_t strides[2] = {(cuuint64_t)pitch * esz, (cuuint64_t)rows * pitch * esz};
     cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
@@ -730,26 +752,40 @@ int cta_group() {
     return v;
 }
 
+template <bool MN, bool F16, int EX>
+int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc, int Nc, int K, int ldc, const uint32_t* ma,
+                    const uint32_t* mb, int kc, int dbg, cudaStream_t stream) {
+    static bool configured2 = false;
+    if (!configured2) {
+        const cudaError_t e = cudaFuncSetAttribute(gemm_split_2sm_kernel<MN, F16, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   Ring2<EX>::SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(gemm_split_2sm): %s", cudaGetErrorString(e)); return 4; }
+        configured2 = true;
+    }
+    const int tiles_m = ceil_div(Mc, 256), tiles_n = ceil_div(Nc, BN);
+    const int tiles = tiles_m * tiles_n;
+    const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
+    gemm_split_2sm_kernel<MN, F16, EX><<<2 * pairs, kThreads, Ring2<EX>::SMEM_BYTES, stream>>>(a, b, C, Mc, Nc, K, ldc, tiles_m, tiles_n,
+                                                                                              kc, ma, mb, dbg);
+    return check_launch("gemm_split_2sm_kernel");
+}
+
+// ex: 0 = both operands carry hi|lo planes, 1 = A is exact (single plane), 2 = B is exact.  Exact operands need the
+// CTA-pair kernel (tc_exact_supported()).
 template <bool MN, bool F16>
 int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc, int Nc, int K, int ldc, const uint32_t* ma,
-                const uint32_t* mb, cudaStream_t stream) {
-    const int kc = chunk_kblocks(Geo<MN, F16>::default_kc);
+                const uint32_t* mb, cudaStream_t stream, int ex = 0) {
+    // k-blocks per TMEM chunk: the same number of truncating MMAs per chunk (48) whether a k-step is 3 or 2 MMAs
+    const int kc = chunk_kblocks(ex == 0 ? Geo<MN, F16>::default_kc : (Geo<MN, F16>::default_kc * 3) / 2);
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("MPVAE_TC_DEBUG"); dbg = e ? atoi(e) : 0; }   // timing probes, results invalid
     if (dbg == 3) return 0;                                                               // pre-passes only
     if (cta_group() == 2) {
-        static bool configured2 = false;
-        if (!configured2) {
-            const cudaError_t e = cudaFuncSetAttribute(gemm_split_2sm_kernel<MN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
-            if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(gemm_split_2sm): %s", cudaGetErrorString(e)); return 4; }
-            configured2 = true;
-        }
-        const int tiles_m = ceil_div(Mc, 256), tiles_n = ceil_div(Nc, BN);
-        const int tiles = tiles_m * tiles_n;
-        const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
-        gemm_split_2sm_kernel<MN, F16><<<2 * pairs, kThreads, SMEM2_BYTES, stream>>>(a, b, C, Mc, Nc, K, ldc, tiles_m, tiles_n, kc, ma, mb, dbg);
-        return check_launch("gemm_split_2sm_kernel");
+        if (ex == 1) return launch_gemm_2sm<MN, F16, 1>(a, b, C, Mc, Nc, K, ldc, ma, mb, kc, dbg, stream);
+        if (ex == 2) return launch_gemm_2sm<MN, F16, 2>(a, b, C, Mc, Nc, K, ldc, ma, mb, kc, dbg, stream);
+        return launch_gemm_2sm<MN, F16, 0>(a, b, C, Mc, Nc, K, ldc, ma, mb, kc, dbg, stream);
     }
+    if (ex != 0) { set_error("exact-operand products need the CTA-pair kernel"); return 7; }
     static bool configured = false;
     if (!configured) {
         const cudaError_t e = cudaFuncSetAttribute(gemm_split_kernel<MN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -777,8 +813,9 @@ size_t tc_workspace_tn(int M, int N1, int N2) {
 }
 
 int tc_contract_nt(const float* A, const float* Bm, float* C, int M, int N, int K, void* ws, size_t ws_bytes,
-                   cudaStream_t stream, int reuse_planes) {
+                   cudaStream_t stream, int reuse_planes, int exact) {
     if (!ws || ws_bytes < tc_workspace_nt(M, N, K)) { set_error("tc_contract_nt: workspace too small"); return 5; }
+    const int ex = exact ? 1 : 0;
     const bool f16 = use_f16();
     const int kp = pitch_of(K);
     const Scratch s = carve_scratch(ws, M, kp);
@@ -789,15 +826,16 @@ int tc_contract_nt(const float* A, const float* Bm, float* C, int M, int N, int 
     }
     CUtensorMap ma, mb;
     const int bk = f16 ? 64 : 32;
-    if (int rc = make_map(&ma, s.a, f16, K, M, kp, bk, BM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_map(&ma, s.a, f16, K, M, kp, bk, BM, CU_TENSOR_MAP_SWIZZLE_128B, ex ? 1 : 2)) return rc;
     if (int rc = make_map(&mb, s.b, f16, K, N, kp, bk, (cta_group() == 2 ? BN / 2 : BN), CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    if (f16) return launch_gemm<false, true>(ma, mb, C, M, N, K, N, s.absmax, s.absmax + 1, stream);
-    return launch_gemm<false, false>(ma, mb, C, M, N, K, N, nullptr, nullptr, stream);
+    if (f16) return launch_gemm<false, true>(ma, mb, C, M, N, K, N, s.absmax, s.absmax + 1, stream, ex);
+    return launch_gemm<false, false>(ma, mb, C, M, N, K, N, nullptr, nullptr, stream, ex);
 }
 
 int tc_contract_tn(const float* A, const float* Bm, float* C, int M, int N1, int N2, void* ws, size_t ws_bytes,
-                   cudaStream_t stream, int reuse_planes) {
+                   cudaStream_t stream, int reuse_planes, int exact) {
     if (!ws || ws_bytes < tc_workspace_tn(M, N1, N2)) { set_error("tc_contract_tn: workspace too small"); return 5; }
+    const int ex = exact ? 2 : 0;
     const bool f16 = use_f16();
     const int p1 = pitch_of(N1), p2 = pitch_of(N2);
     const Scratch s = carve_scratch(ws, M, p1);
@@ -810,9 +848,9 @@ int tc_contract_tn(const float* A, const float* Bm, float* C, int M, int N1, int
     const int bk = f16 ? 64 : 32, box_mn = f16 ? 64 : 32;
     const CUtensorMapSwizzle sw = f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     if (int rc = make_map(&ma, s.a, f16, N1, M, p1, box_mn, bk, sw)) return rc;
-    if (int rc = make_map(&mb, s.b, f16, N2, M, p2, box_mn, bk, sw)) return rc;
-    if (f16) return launch_gemm<true, true>(ma, mb, C, N1, N2, M, N2, s.absmax, s.absmax + 1, stream);
-    return launch_gemm<true, false>(ma, mb, C, N1, N2, M, N2, nullptr, nullptr, stream);
+    if (int rc = make_map(&mb, s.b, f16, N2, M, p2, box_mn, bk, sw, ex ? 1 : 2)) return rc;
+    if (f16) return launch_gemm<true, true>(ma, mb, C, N1, N2, M, N2, s.absmax, s.absmax + 1, stream, ex);
+    return launch_gemm<true, false>(ma, mb, C, N1, N2, M, N2, nullptr, nullptr, stream, ex);
 }
 
 // ------------------------------------------------------------------------------------------------ staged interface
@@ -843,7 +881,7 @@ namespace {
 template <bool F16>
 __global__ void __launch_bounds__(256)
 philox_planes_kernel(void* __restrict__ planes, int S, int B, int Z, int pitch, int Bg, int row0, uint2 key, uint2 off,
-                     const unsigned long long* __restrict__ off_dev) {
+                     const unsigned long long* __restrict__ off_dev, int write_lo) {
     const int s = blockIdx.y;
     const unsigned long long span_beg = ((unsigned long long)s * Bg + row0) * Z;
     const unsigned long long span_end = span_beg + (unsigned long long)B * Z;
@@ -863,16 +901,13 @@ philox_planes_kernel(void* __restrict__ planes, int S, int B, int Z, int pitch, 
         if (++col == Z) { col = 0; ++row; }
         if (r < 0 || r >= B) continue;
         const size_t o = ((size_t)s * B + (size_t)r) * pitch + (size_t)cc;
+        // n[j] already lies on the fp16 grid (philox_normal4), so hi = n and lo = 0 in both kinds
         if (F16) {
-            const __half h = __float2half_rn(n[j]);
-            static_cast<__half*>(planes)[o] = h;
-            static_cast<__half*>(planes)[plane + o] = __float2half_rn(n[j] - __half2float(h));
+            static_cast<__half*>(planes)[o] = __float2half_rn(n[j]);
+            if (write_lo) static_cast<__half*>(planes)[plane + o] = __float2half_rn(0.0f);
         } else {
-            uint32_t h, l;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(n[j]));
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(n[j] - __uint_as_float(h)));
-            static_cast<uint32_t*>(planes)[o] = h;
-            static_cast<uint32_t*>(planes)[plane + o] = l;
+            static_cast<float*>(planes)[o] = n[j];
+            if (write_lo) static_cast<float*>(planes)[plane + o] = 0.0f;
         }
     }
 }
@@ -888,34 +923,37 @@ int tc_philox_planes(void* planes, int S, int B, int Z, int Bg, int row0, uint64
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     const uint2 off = make_uint2((uint32_t)offset, (uint32_t)(offset >> 32));
     const unsigned long long* od = reinterpret_cast<const unsigned long long*>(offset_dev);
-    if (use_f16()) philox_planes_kernel<true><<<grid, 256, 0, stream>>>(planes, S, B, Z, pitch_of(Z), Bg, row0, key, off, od);
-    else philox_planes_kernel<false><<<grid, 256, 0, stream>>>(planes, S, B, Z, pitch_of(Z), Bg, row0, key, off, od);
+    const int write_lo = tc_exact_supported() ? 0 : 1;   // the single-CTA kernel still reads a (zero) lo plane
+    if (use_f16()) philox_planes_kernel<true><<<grid, 256, 0, stream>>>(planes, S, B, Z, pitch_of(Z), Bg, row0, key, off, od, write_lo);
+    else philox_planes_kernel<false><<<grid, 256, 0, stream>>>(planes, S, B, Z, pitch_of(Z), Bg, row0, key, off, od, write_lo);
     return check_launch("philox_planes_kernel");
 }
 
+bool tc_exact_supported() { return cta_group() == 2; }
+
 int tc_gemm_nt(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, const uint32_t* absmax_a,
-               const uint32_t* absmax_b, cudaStream_t stream, int ldc) {
+               const uint32_t* absmax_b, cudaStream_t stream, int ldc, int a_exact) {
     if (ldc <= 0) ldc = N;
     const bool f16 = use_f16();
     const int kp = pitch_of(K), bk = f16 ? 64 : 32;
     CUtensorMap ma, mb;
-    if (int rc = make_map(&ma, a_planes, f16, K, M, kp, bk, BM, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_map(&ma, a_planes, f16, K, M, kp, bk, BM, CU_TENSOR_MAP_SWIZZLE_128B, a_exact ? 1 : 2)) return rc;
     if (int rc = make_map(&mb, b_planes, f16, K, N, kp, bk, (cta_group() == 2 ? BN / 2 : BN), CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    if (f16) return launch_gemm<false, true>(ma, mb, C, M, N, K, ldc, absmax_a, absmax_b, stream);
-    return launch_gemm<false, false>(ma, mb, C, M, N, K, ldc, nullptr, nullptr, stream);
+    if (f16) return launch_gemm<false, true>(ma, mb, C, M, N, K, ldc, absmax_a, absmax_b, stream, a_exact ? 1 : 0);
+    return launch_gemm<false, false>(ma, mb, C, M, N, K, ldc, nullptr, nullptr, stream, a_exact ? 1 : 0);
 }
 
 int tc_gemm_tn(const void* a_planes, const void* b_planes, float* C, int M, int N1, int N2, const uint32_t* absmax_a,
-               const uint32_t* absmax_b, cudaStream_t stream) {
+               const uint32_t* absmax_b, cudaStream_t stream, int b_exact) {
     const bool f16 = use_f16();
     const int p1 = pitch_of(N1), p2 = pitch_of(N2);
     const int bk = f16 ? 64 : 32, box_mn = f16 ? 64 : 32;
     const CUtensorMapSwizzle sw = f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     CUtensorMap ma, mb;
     if (int rc = make_map(&ma, a_planes, f16, N1, M, p1, box_mn, bk, sw)) return rc;
-    if (int rc = make_map(&mb, b_planes, f16, N2, M, p2, box_mn, bk, sw)) return rc;
-    if (f16) return launch_gemm<true, true>(ma, mb, C, N1, N2, M, N2, absmax_a, absmax_b, stream);
-    return launch_gemm<true, false>(ma, mb, C, N1, N2, M, N2, nullptr, nullptr, stream);
+    if (int rc = make_map(&mb, b_planes, f16, N2, M, p2, box_mn, bk, sw, b_exact ? 1 : 2)) return rc;
+    if (f16) return launch_gemm<true, true>(ma, mb, C, N1, N2, M, N2, absmax_a, absmax_b, stream, b_exact ? 2 : 0);
+    return launch_gemm<true, false>(ma, mb, C, N1, N2, M, N2, nullptr, nullptr, stream, b_exact ? 2 : 0);
 }
 
 }  // namespace mpv

@@ -1,5 +1,6 @@
 // Philox4x32-10 (Salmon et al., SC'11) + Box-Muller, shared by the noise kernels.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -41,6 +42,11 @@ __device__ __forceinline__ void philox_normal4(unsigned long long c, uint2 key, 
     const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), off.x, off.y), key);
     box_muller(r.x, r.y, n[0], n[1]);
     box_muller(r.z, r.w, n[2], n[3]);
+    // The library's noise is DEFINED on the fp16 grid (11-bit mantissa): still standard normal to ~2e-4 relative
+    // per sample, identical whichever engine consumes it, and exactly representable as a single tensor-core
+    // operand piece -- the dense products with it need two MMA passes instead of three (contract_tc.cu).
+#pragma unroll
+    for (int j = 0; j < 4; ++j) n[j] = __half2float(__float2half_rn(n[j]));
 }
 
 }  // namespace mpv

@@ -16,10 +16,10 @@ size_t tc_workspace_tn(int M, int N1, int N2);
 // reuse_planes != 0: skip the split pre-pass and use the operand planes a previous call left in `ws`
 // (lets a caller time the GEMM kernel alone)
 int tc_contract_nt(const float* A, const float* Bm, float* C, int M, int N, int K, void* ws, size_t ws_bytes,
-                   cudaStream_t stream, int reuse_planes = 0);
+                   cudaStream_t stream, int reuse_planes = 0, int exact = 0);
 // C[N1,N2] = A[M,N1]^T . B[M,N2]
 int tc_contract_tn(const float* A, const float* Bm, float* C, int M, int N1, int N2, void* ws, size_t ws_bytes,
-                   cudaStream_t stream, int reuse_planes = 0);
+                   cudaStream_t stream, int reuse_planes = 0, int exact = 0);
 
 // ---- staged interface used by the probit forward / backward (operand planes persist between the two) ----
 // An operand is stored as two planes [2][rows][pitch] (hi | lo) of fp16 (default) or tf32-in-fp32.  A row-major
@@ -33,9 +33,12 @@ int tc_split(const float* src, int rows, int cols, void* planes, uint32_t* absma
 // standard normals (Philox4x32-10, same stream of numbers as philox_normal_kernel) written directly as planes
 int tc_philox_planes(void* planes, int S, int B, int Z, int B_global, int row0, uint64_t seed, uint64_t offset,
                      const uint64_t* offset_dev, cudaStream_t stream);
+// a_exact / b_exact: that operand lies exactly on the 11-bit piece grid and is stored as ONE plane (the library's own
+// Philox noise): two MMA passes instead of three.  Needs tc_exact_supported().
+bool tc_exact_supported();
 int tc_gemm_nt(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, const uint32_t* absmax_a,
-               const uint32_t* absmax_b, cudaStream_t stream, int ldc = 0);   // ldc: row pitch of C in floats (0 = N)
+               const uint32_t* absmax_b, cudaStream_t stream, int ldc = 0, int a_exact = 0);   // ldc: pitch of C (0 = N)
 int tc_gemm_tn(const void* a_planes, const void* b_planes, float* C, int M, int N1, int N2, const uint32_t* absmax_a,
-               const uint32_t* absmax_b, cudaStream_t stream);
+               const uint32_t* absmax_b, cudaStream_t stream, int b_exact = 0);
 
 }  // namespace mpv

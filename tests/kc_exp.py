@@ -10,6 +10,7 @@ from mpvae_b200.probit import contract_nt, contract_tn
 
 kc, kind = os.environ.get("MPVAE_TC_KC"), os.environ.get("MPVAE_TC_KIND")
 dev = "cuda:0"
+ENGINES = tuple(int(e) for e in os.environ.get("KC_EXP_ENGINES", "2,4,1").split(","))
 
 
 def stats(out, want):
@@ -32,18 +33,18 @@ def timed(fn):
 
 for (M, N, K) in [(10240, 983, 983), (10240, 3993, 3993)]:
     g = torch.Generator(device="cpu").manual_seed(1)
-    a = torch.randn(M, K, generator=g).to(dev)
+    a = torch.randn(M, K, generator=g).half().float().to(dev)     # noise on the fp16 grid, like the library's own
     b = ((torch.rand(N, K, generator=g) - 0.5) * 0.06).to(dev)
     want = a[:512].double() @ b.double().T
     res = {}
-    for eng in (2, 1):
+    for eng in ENGINES:
         out, ms = timed(lambda: contract_nt(a, b, engine=eng))
         res["nt%d" % eng] = dict(ms=ms, **stats(out[:512], want))
     # tn: C[N1, N2] = A[M, N1]^T B[M, N2] with gradient-like magnitudes on A
     ga = (torch.randn(M, N, generator=g) * 1e-4 * torch.rand(M, 1, generator=g)).to(dev)
-    nb = torch.randn(M, K, generator=g).to(dev)
+    nb = torch.randn(M, K, generator=g).half().float().to(dev)
     want_t = ga[:, :256].double().T @ nb.double()
-    for eng in (2, 1):
+    for eng in ENGINES:
         out, ms = timed(lambda: contract_tn(ga, nb, engine=eng))
         res["tn%d" % eng] = dict(ms=ms, **stats(out[:256], want_t))
     print(json.dumps(dict(kind=kind, kc=kc, M=M, N=N, K=K, res=res)))

@@ -48,7 +48,12 @@ def test_philox_matches_numpy_reference():
     S, B, Z = 3, 7, 13
     got = philox_normal(S, B, Z, seed=1234567890123, offset=5, device=DEV).cpu().numpy()
     want = philox_normals_numpy(S * B * Z, 1234567890123, 5).reshape(S, B, Z)
-    np.testing.assert_allclose(got, want, rtol=0, atol=2e-6)
+    # the library's noise is defined on the fp16 grid (philox.cuh): Box-Muller in fp32, then round-to-nearest fp16
+    assert np.array_equal(got, got.astype(np.float16).astype(np.float32))
+    want16 = want.astype(np.float16).astype(np.float32)
+    # libdevice vs numpy transcendental ulps can move a value across an fp16 rounding boundary: rare, and then by one step
+    assert (got != want16).mean() <= 0.02
+    np.testing.assert_allclose(got, want, rtol=2.0 ** -11, atol=2e-6)
 
 
 def test_philox_is_shard_invariant_and_deterministic():
