@@ -361,7 +361,6 @@ struct Ring2 {
     static constexpr int STAGE_BYTES = (NA + NB) * A_BYTES;                       // 64 KiB (EX = 0) or 48 KiB
     static constexpr int STAGES = (EX == 0) ? 3 : 4;
     static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES;
-    static constexpr int MMAS_PER_KSTEP = (EX == 0) ? 3 : 2;
     // measured truncation bias per k-block relative to the 3-pass constant (profiles/r01_exact_operand.md): 1.30e-7 / 1.85e-7
     static constexpr float BIAS_SCALE = (EX == 0) ? 1.0f : 0.70f;
 };
@@ -389,10 +388,20 @@ __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap*
         ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
+// same box delivered to every CTA of `mask` (same CTA-relative smem offset); each destination's bytes are counted
+// on the barrier of ITS pair's leader (the peer bit of `leader_bar` is 0)
+__device__ __forceinline__ void tma_load_3d_2sm_mc(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2,
+                                                   uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar, uint16_t mask) {
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        ::"r"(bar), "h"((uint16_t)3)
+        ::"r"(bar), "h"(mask)
         : "memory");
 }
 template <bool F16>
@@ -414,8 +423,17 @@ __device__ __forceinline__ void tc_mma_2sm(uint32_t d_tmem, uint64_t adesc, uint
     }
 }
 
-template <bool MN, bool F16, int EX>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+//
+// CL = 2 puts TWO pairs in one cluster of four CTAs.  The pairs work on neighbouring tiles that share the operand
+// which costs two planes (B = R for A-exact / plain products: tiles stacked along M; A = gxs for the B-exact
+// backward: tiles side by side along N).  Each CTA fetches only half of its share of that operand and multicasts
+// it to the CTA of the same parity in the other pair, so L2 -> shared-memory traffic per pair drops from 96 to
+// 64 KiB per k-block.  (Opt-in, MPVAE_TC_CLUSTER=2: it did not pay on B200, see cluster_pairs().)
+//   empty[s] then counts one tcgen05.commit per PAIR (multicast to all four CTAs): a stage is rewritten only
+//   after both pairs have consumed it, because either pair's producers write into both pairs' shared memory.
+// A cluster whose second tile falls outside the matrix runs it on zero-filled boxes and stores nothing.
+template <bool MN, bool F16, int EX, int CL>
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       float* __restrict__ C, int Mc, int Nc, int K, int ldc, int tiles_m, int tiles_n, int kc,
                       const uint32_t* __restrict__ absmax_a, const uint32_t* __restrict__ absmax_b, int dbg) {
@@ -437,11 +455,24 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + STAGES2 * STAGE2_BYTES + 128);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
+    const uint32_t crank = cluster_ctarank();
+    const uint32_t rank = crank & 1u;                         // position inside the pair (0 = leader)
+    const uint32_t cpair = crank >> 1;                        // which pair of the cluster
+    const uint32_t leader_rank = crank & ~1u;                 // cluster rank of this pair's leader
     const bool leader = rank == 0;
-    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int cluster = blockIdx.x / (2 * CL), num_clusters = gridDim.x / (2 * CL);
+    constexpr bool SHARE_A = (EX == 2);                       // operand multicast between the pairs (CL == 2)
+    // super-tiles: CL neighbouring pair tiles along M (B shared) or along N (A shared)
+    const int sup_m = SHARE_A ? tiles_m : (tiles_m + CL - 1) / CL;
+    const int sup_n = SHARE_A ? (tiles_n + CL - 1) / CL : tiles_n;
+    const int num_super = sup_m * sup_n;
+    auto tile_m_of = [&](int st) { return SHARE_A ? st / sup_n : (st / sup_n) * CL + (int)cpair; };
+    auto tile_n_of = [&](int st) { return SHARE_A ? (st % sup_n) * CL + (int)cpair : st % sup_n; };
+    const uint16_t mask_all = (uint16_t)((1u << (2 * CL)) - 1u);
+    const uint16_t mask_pair = (uint16_t)(3u << (2 * cpair));
+    const uint16_t mask_share = (uint16_t)((1u << rank) | (1u << (rank + 2)));   // same parity in both pairs
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -457,19 +488,18 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_tiles = tiles_m * tiles_n;                  // 256 x 256 pair tiles
     const int num_kb = (K + G::BK - 1) / G::BK;
 
     if (warp == 0) {
-        if (lane == 0) {   // ------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {   // ------------------------------------------------ TMA producer (every CTA)
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-                const int m0 = (tile / tiles_n) * 256 + (int)rank * BM;       // this CTA's 128 rows of A
-                const int n0 = (tile % tiles_n) * BN + (int)rank * HB;        // this CTA's half of the B tile
+            for (int st = cluster; st < num_super; st += num_clusters) {
+                const int m0 = tile_m_of(st) * 256 + (int)rank * BM;          // this CTA's 128 rows of A
+                const int n0 = tile_n_of(st) * BN + (int)rank * HB;           // this CTA's half of the B tile
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
-                    const uint32_t fb = map_to_cta(full_bar(stage), 0);       // the leader's barrier collects both CTAs' bytes
+                    const uint32_t fb = map_to_cta(full_bar(stage), leader_rank);   // the pair leader's barrier collects both CTAs' bytes
                     if (dbg == 1) {   // timing probe: no loads
                         if (leader) mbar_arrive(full_bar(stage));
                         if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
@@ -478,22 +508,49 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE2_BYTES);
                     const uint32_t sa = base + stage * STAGE2_BYTES, sb = sa + R2::NA * A_BYTES;
                     if (!MN) {
+                        // K-major tiles are [rows][128 B]; the shared operand's map has boxes of rows / CL
+                        constexpr int ra = SHARE_A ? BM / CL : BM, rb = SHARE_A ? HB : HB / CL;
 #pragma unroll
-                        for (int pl = 0; pl < R2::NA; ++pl) tma_load_3d_2sm(sa + pl * A_BYTES, &tmA, fb, kb * G::BK, m0, pl);
+                        for (int pl = 0; pl < R2::NA; ++pl) {
+                            if (CL > 1 && SHARE_A)
+                                tma_load_3d_2sm_mc(sa + pl * A_BYTES + cpair * ra * 128, &tmA, fb, kb * G::BK, m0 + cpair * ra, pl, mask_share);
+                            else
+                                tma_load_3d_2sm(sa + pl * A_BYTES, &tmA, fb, kb * G::BK, m0, pl);
+                        }
 #pragma unroll
-                        for (int pl = 0; pl < R2::NB; ++pl) tma_load_3d_2sm(sb + pl * A_BYTES, &tmB, fb, kb * G::BK, n0, pl);
+                        for (int pl = 0; pl < R2::NB; ++pl) {
+                            if (CL > 1 && !SHARE_A)
+                                tma_load_3d_2sm_mc(sb + pl * A_BYTES + cpair * rb * 128, &tmB, fb, kb * G::BK, n0 + cpair * rb, pl, mask_share);
+                            else
+                                tma_load_3d_2sm(sb + pl * A_BYTES, &tmB, fb, kb * G::BK, n0, pl);
+                        }
                     } else {
+                        // MN-major tiles are BOX_MN-wide column boxes of BK k-rows; the shared operand's boxes are
+                        // dealt out between the pairs
                         constexpr int box = G::BK * 128;
+                        constexpr int nba = BM / G::BOX_MN, nbb = HB / G::BOX_MN;
 #pragma unroll
-                        for (int j = 0; j < BM / G::BOX_MN; ++j)
+                        for (int j = 0; j < nba; ++j) {
+                            if (CL > 1 && SHARE_A && (j / (nba / CL)) != (int)cpair) continue;
 #pragma unroll
-                            for (int pl = 0; pl < R2::NA; ++pl)
-                                tma_load_3d_2sm(sa + pl * A_BYTES + j * box, &tmA, fb, m0 + j * G::BOX_MN, kb * G::BK, pl);
+                            for (int pl = 0; pl < R2::NA; ++pl) {
+                                if (CL > 1 && SHARE_A)
+                                    tma_load_3d_2sm_mc(sa + pl * A_BYTES + j * box, &tmA, fb, m0 + j * G::BOX_MN, kb * G::BK, pl, mask_share);
+                                else
+                                    tma_load_3d_2sm(sa + pl * A_BYTES + j * box, &tmA, fb, m0 + j * G::BOX_MN, kb * G::BK, pl);
+                            }
+                        }
 #pragma unroll
-                        for (int j = 0; j < HB / G::BOX_MN; ++j)
+                        for (int j = 0; j < nbb; ++j) {
+                            if (CL > 1 && !SHARE_A && (j / (nbb / CL)) != (int)cpair) continue;
 #pragma unroll
-                            for (int pl = 0; pl < R2::NB; ++pl)
-                                tma_load_3d_2sm(sb + pl * A_BYTES + j * box, &tmB, fb, n0 + j * G::BOX_MN, kb * G::BK, pl);
+                            for (int pl = 0; pl < R2::NB; ++pl) {
+                                if (CL > 1 && !SHARE_A)
+                                    tma_load_3d_2sm_mc(sb + pl * A_BYTES + j * box, &tmB, fb, n0 + j * G::BOX_MN, kb * G::BK, pl, mask_share);
+                                else
+                                    tma_load_3d_2sm(sb + pl * A_BYTES + j * box, &tmB, fb, n0 + j * G::BOX_MN, kb * G::BK, pl);
+                            }
+                        }
                     }
                     if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
                 }
@@ -503,7 +560,7 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (lane == 0 && leader) {   // ------------------------------------- MMA issuer (leader CTA only)
             int stage = 0, buf = 0;
             uint32_t phase = 0, bphase = 0;
-            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            for (int st = cluster; st < num_super; st += num_clusters) {
                 for (int kb0 = 0; kb0 < num_kb; kb0 += kc) {
                     mbar_wait(tempty_bar(buf), bphase ^ 1u);     // both CTAs' promotion warps have drained this buffer
                     tc_fence_after();
@@ -533,10 +590,10 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                             }
                             tc_mma_2sm<F16>(d, a_hi, b_hi, idesc2, 1u);
                         }
-                        tc_commit_2sm(empty_bar(stage));         // frees the stage in BOTH CTAs
+                        tc_commit_2sm(empty_bar(stage), mask_all);   // this pair is done with the stage: tell every CTA of the cluster
                         if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
                     }
-                    tc_commit_2sm(tfull_bar(buf));               // chunk complete in both CTAs' tensor memory
+                    tc_commit_2sm(tfull_bar(buf), mask_pair);    // chunk complete in both CTAs' tensor memory
                     if (++buf == 2) { buf = 0; bphase ^= 1u; }
                 }
             }
@@ -555,7 +612,7 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int j = 0; j < 64; ++j) acc[j] = 0.0f;
         int buf = 0;
         uint32_t bphase = 0;
-        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        for (int st = cluster; st < num_super; st += num_clusters) {
             for (int kb0 = 0; kb0 < num_kb; kb0 += kc) {
                 mbar_wait(tfull_bar(buf), bphase);
                 tc_fence_after();
@@ -571,12 +628,12 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(map_to_cta(tempty_bar(buf), 0));
+                if (lane == 0) mbar_arrive_cluster(map_to_cta(tempty_bar(buf), leader_rank));
                 if (++buf == 2) { buf = 0; bphase ^= 1u; }
             }
-            const int row = (tile / tiles_n) * 256 + (int)rank * BM + q * 32 + lane;
-            const int col0 = (tile % tiles_n) * BN + h * 64;
-            if (row < Mc) {
+            const int row = tile_m_of(st) * 256 + (int)rank * BM + q * 32 + lane;
+            const int col0 = tile_n_of(st) * BN + h * 64;
+            if (row < Mc && col0 < Nc) {
                 float* __restrict__ crow = C + (size_t)row * ldc;
                 if (vec_store && col0 + 64 <= ldc) {
                     // 16-byte stores: rows are 16 B aligned (ldc % 4 == 0); columns in [Nc, ldc) are pitch padding
@@ -752,22 +809,61 @@ int cta_group() {
     return v;
 }
 
+// MPVAE_TC_CLUSTER = 1 | 2: pairs per cluster.  2 = four-CTA clusters with the two-plane operand multicast; kept as
+// an experiment, NOT the default: measured on B200 (profiles/r01_multicast_probe.txt) the load-only time does not
+// move (0.49 -> 0.51 ms: the cap is on bytes DELIVERED to the SMs, ~8 TB/s, not on L2 reads) and only 33 of 37
+// four-CTA clusters are co-resident (GPC sizes), so the kernel gets slower (0.645 -> 0.666 ms).
+int cluster_pairs() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MPVAE_TC_CLUSTER");
+        v = (e && atoi(e) == 2) ? 2 : 1;
+    }
+    return v;
+}
+
+// rows of one TMA box of the K-major B operand (R in noise.R^T): the whole tile for single CTAs, half of it per CTA
+// of a pair, a quarter when two pairs share the tile by multicast (the nt products never have an exact B)
+int nt_b_box_rows() { return cta_group() == 2 ? BN / 2 / cluster_pairs() : BN; }
+
+template <bool MN, bool F16, int EX, int CL>
+int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc, int Nc, int K, int ldc, const uint32_t* ma,
+                    const uint32_t* mb, int kc, int dbg, cudaStream_t stream) {
+    auto kernel = gemm_split_2sm_kernel<MN, F16, EX, CL>;
+    static int max_clusters = 0;     // co-resident clusters (a cluster must fit inside one GPC)
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2 * CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Ring2<EX>::SMEM_BYTES;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (max_clusters == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Ring2<EX>::SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(gemm_split_2sm): %s", cudaGetErrorString(e)); return 4; }
+        cfg.gridDim = dim3(kNumSMs / (2 * CL) * (2 * CL));
+        int n = 0;
+        e = cudaOccupancyMaxActiveClusters(&n, kernel, &cfg);
+        if (e != cudaSuccess || n <= 0) { set_error("cudaOccupancyMaxActiveClusters: %s", cudaGetErrorString(e)); return 4; }
+        max_clusters = n < kNumSMs / (2 * CL) ? n : kNumSMs / (2 * CL);
+        if (dbg) fprintf(stderr, "[mpvae tc] cluster of %d CTAs: %d co-resident (of %d)\n", 2 * CL, n, kNumSMs / (2 * CL));
+    }
+    const int tiles_m = ceil_div(Mc, 256), tiles_n = ceil_div(Nc, BN);
+    const int supers = (EX == 2) ? tiles_m * ceil_div(tiles_n, CL) : ceil_div(tiles_m, CL) * tiles_n;
+    const int clusters = supers < max_clusters ? supers : max_clusters;
+    cfg.gridDim = dim3(2 * CL * clusters);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, a, b, C, Mc, Nc, K, ldc, tiles_m, tiles_n, kc, ma, mb, dbg);
+    if (e != cudaSuccess) { set_error("gemm_split_2sm_kernel launch: %s", cudaGetErrorString(e)); return 3; }
+    return check_launch("gemm_split_2sm_kernel");
+}
+
 template <bool MN, bool F16, int EX>
 int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc, int Nc, int K, int ldc, const uint32_t* ma,
                     const uint32_t* mb, int kc, int dbg, cudaStream_t stream) {
-    static bool configured2 = false;
-    if (!configured2) {
-        const cudaError_t e = cudaFuncSetAttribute(gemm_split_2sm_kernel<MN, F16, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   Ring2<EX>::SMEM_BYTES);
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(gemm_split_2sm): %s", cudaGetErrorString(e)); return 4; }
-        configured2 = true;
-    }
-    const int tiles_m = ceil_div(Mc, 256), tiles_n = ceil_div(Nc, BN);
-    const int tiles = tiles_m * tiles_n;
-    const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
-    gemm_split_2sm_kernel<MN, F16, EX><<<2 * pairs, kThreads, Ring2<EX>::SMEM_BYTES, stream>>>(a, b, C, Mc, Nc, K, ldc, tiles_m, tiles_n,
-                                                                                              kc, ma, mb, dbg);
-    return check_launch("gemm_split_2sm_kernel");
+    if (cluster_pairs() == 2) return launch_gemm_2sm<MN, F16, EX, 2>(a, b, C, Mc, Nc, K, ldc, ma, mb, kc, dbg, stream);
+    return launch_gemm_2sm<MN, F16, EX, 1>(a, b, C, Mc, Nc, K, ldc, ma, mb, kc, dbg, stream);
 }
 
 // ex: 0 = both operands carry hi|lo planes, 1 = A is exact (single plane), 2 = B is exact.  Exact operands need the
@@ -827,7 +923,7 @@ int tc_contract_nt(const float* A, const float* Bm, float* C, int M, int N, int 
     CUtensorMap ma, mb;
     const int bk = f16 ? 64 : 32;
     if (int rc = make_map(&ma, s.a, f16, K, M, kp, bk, BM, CU_TENSOR_MAP_SWIZZLE_128B, ex ? 1 : 2)) return rc;
-    if (int rc = make_map(&mb, s.b, f16, K, N, kp, bk, (cta_group() == 2 ? BN / 2 : BN), CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_map(&mb, s.b, f16, K, N, kp, bk, nt_b_box_rows(), CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     if (f16) return launch_gemm<false, true>(ma, mb, C, M, N, K, N, s.absmax, s.absmax + 1, stream, ex);
     return launch_gemm<false, false>(ma, mb, C, M, N, K, N, nullptr, nullptr, stream, ex);
 }
@@ -938,7 +1034,7 @@ int tc_gemm_nt(const void* a_planes, const void* b_planes, float* C, int M, int 
     const int kp = pitch_of(K), bk = f16 ? 64 : 32;
     CUtensorMap ma, mb;
     if (int rc = make_map(&ma, a_planes, f16, K, M, kp, bk, BM, CU_TENSOR_MAP_SWIZZLE_128B, a_exact ? 1 : 2)) return rc;
-    if (int rc = make_map(&mb, b_planes, f16, K, N, kp, bk, (cta_group() == 2 ? BN / 2 : BN), CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_map(&mb, b_planes, f16, K, N, kp, bk, nt_b_box_rows(), CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     if (f16) return launch_gemm<false, true>(ma, mb, C, M, N, K, ldc, absmax_a, absmax_b, stream, a_exact ? 1 : 0);
     return launch_gemm<false, false>(ma, mb, C, M, N, K, ldc, nullptr, nullptr, stream, a_exact ? 1 : 0);
 }
