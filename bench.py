@@ -309,8 +309,9 @@ def run_b200(a):
             passes = 2 if os.environ.get("MPVAE_TC_CTA", "2") != "1" else 3
             e_prep, e_run = (4, 5) if passes == 2 else (2, 3)
             wsk = contract_workspace(M_rows, L, Z, dev, 2)
-            contract_nt(noise, r32.detach(), engine=e_prep, ws=wsk)
-            run = lambda: contract_nt(noise, r32.detach(), engine=e_run, ws=wsk)
+            # pitched = rows of the output padded to 16 bytes, exactly as the loss step stores noise.R^T
+            contract_nt(noise, r32.detach(), engine=e_prep, ws=wsk, pitched=True)
+            run = lambda: contract_nt(noise, r32.detach(), engine=e_run, ws=wsk, pitched=True)
         else:
             eng = {"auto": 0, "fma": 1, "tensor": 2}[a.engine]
             run = lambda: contract_nt(noise, r32.detach(), engine=eng)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPVAE_ABI_VERSION 6
+#define MPVAE_ABI_VERSION 7
 
 /* flags */
 #define MPVAE_FLAG_SANITIZE_DEGENERATE 0x1u /* rows with n_pos*n_neg == 0 get zero ranking gradient instead of
@@ -110,6 +110,10 @@ int mpvae_philox_normal(float *noise, int32_t S, int32_t B, int32_t Z, int32_t B
  * 5 = engine 4 reusing the planes of a previous engine-2/4 call. */
 int mpvae_contract_nt(const float *A, const float *Bm, float *C, int32_t M, int32_t N, int32_t K, int32_t engine,
                       void *workspace, uint64_t workspace_bytes, void *cuda_stream);
+/* Same with a row pitch of ldc >= N floats for C.  The loss kernels keep noise.R^T in rows padded to 16 bytes
+ * (ldc = N rounded up to 4) so that the GEMM epilogue can use 16-byte stores; this entry times exactly that variant. */
+int mpvae_contract_nt_pitched(const float *A, const float *Bm, float *C, int32_t M, int32_t N, int32_t K, int32_t ldc,
+                              int32_t engine, void *workspace, uint64_t workspace_bytes, void *cuda_stream);
 
 /* C[N1,N2] = A[M,N1]^T . B[M,N2] (fp32): g_R = gx^T . noise of SURVEY 8(a-12). Same engine codes. */
 int mpvae_contract_tn(const float *A, const float *Bm, float *C, int32_t M, int32_t N1, int32_t N2, int32_t engine,

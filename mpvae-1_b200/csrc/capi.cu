@@ -38,10 +38,14 @@ struct Workspace {
     size_t noise_f32;                             // FMA engine, library-side noise
     size_t noise_planes, r_planes, gxs_planes;    // tensor engine operand planes (noise planes persist fwd -> bwd)
     size_t fma_partials;                          // FMA engine split-K partials of g_R
+    size_t tn_tail;                               // tensor engine: K-slices of the g_R product's last wave
     size_t total;
 };
 // 32-bit slots of the 256-byte `slots` block
-enum { SLOT_COUNTER = 0, SLOT_ABSMAX_R = 1, SLOT_ABSMAX_GXS = 2 };
+enum { SLOT_COUNTER = 0, SLOT_ABSMAX_R = 1, SLOT_ABSMAX_GXS = 2, SLOT_ABSMAX_GP = 3 /* and 4 */ };
+
+// fp16 operand kind: the row backward writes gxs straight as operand planes (no fp32 cube, no split pass)
+bool direct_gxs_planes() { return tc_f16_kind(); }
 
 // row pitch (floats) of the (S,B,L) scratch cubes nr and gxs: 16-byte aligned rows for vector loads / stores
 int row_pitch(int L) { return (L + 3) & ~3; }
@@ -78,9 +82,14 @@ Workspace carve(int S, int B, int L, int Z, bool want_backward, uint32_t flags) 
         w.noise_f32 = take((size_t)M * Z * sizeof(float));
     }
     if (want_backward) {
-        w.gxs = take(cube * sizeof(float));
-        if (tensor) w.gxs_planes = take(tc_planes_bytes(M, L));
-        else w.fma_partials = take(contract_tn_fma_workspace(M, L, Z));
+        if (tensor) {
+            if (direct_gxs_planes()) w.tn_tail = take(tc_tail_scratch_bytes());
+            else w.gxs = take(cube * sizeof(float));       // doubles as the tail scratch once it has been split
+            w.gxs_planes = take(tc_planes_bytes(M, L));
+        } else {
+            w.gxs = take(cube * sizeof(float));
+            w.fma_partials = take(contract_tn_fma_workspace(M, L, Z));
+        }
     }
     w.total = off;
     return w;
@@ -149,6 +158,10 @@ RowArgs row_args(const mpvae_probit_params* p, const Workspace& w) {
     a.g_fe_mu = p->g_fe_mu; a.g_fe_logvar = p->g_fe_logvar; a.g_fx_mu = p->g_fx_mu; a.g_fx_logvar = p->g_fx_logvar;
     a.gxs = nullptr;
     a.gxs_absmax = nullptr;
+    a.gxs_planes = nullptr;
+    a.gxs_plane_elems = 0;
+    a.gxs_pitch = 0;
+    a.gxs_scale = nullptr;
     return a;
 }
 
@@ -189,6 +202,8 @@ int mpvae_probit_forward(const mpvae_probit_params* p, void* cuda_stream) {
         if (rc) return rc;
         if ((rc = tc_split(p->r, p->L, p->Z, rpl, slots + SLOT_ABSMAX_R, 1, stream))) return rc;
         // library noise sits on the fp16 grid: one plane, two MMA passes
+        // no tail scratch here: K-slicing the last wave would make the summation order of x = noise.R^T depend on
+        // how many rows the call holds, and a row's predictions must not change with the shard it is computed in
         rc = tc_gemm_nt(npl, rpl, nr, M, p->L, p->Z, nullptr, slots + SLOT_ABSMAX_R, stream, row_pitch(p->L),
                         (!p->noise && tc_exact_supported()) ? 1 : 0);
     } else {
@@ -213,22 +228,39 @@ int mpvae_probit_backward(const mpvae_probit_params* p, void* cuda_stream) {
     uint32_t* slots = reinterpret_cast<uint32_t*>(base + w.slots);
     const bool tensor = use_tensor(p->flags, p->S, p->B, p->L, p->Z);
     RowArgs a = row_args(p, w);
-    if (p->g_r) {
+    const int M = p->S * p->B;
+    const bool direct = tensor && p->g_r && direct_gxs_planes();
+    if (p->g_r && tensor) {
+        // slots 2..4: scale source of the gxs planes, max |g_indiv_prob|, max |g_indiv_prob_label|
+        if (cudaMemsetAsync(slots + SLOT_ABSMAX_GXS, 0, 3 * sizeof(uint32_t), stream) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return 2; }
+    }
+    if (direct) {
+        // the plane scale comes from an upper bound of |gxs| computed from the saved row statistics, so the row
+        // kernel can write the operand planes itself
+        if (p->g_indiv_prob) { if (int rc = tc_absmax(p->g_indiv_prob, (size_t)p->B * p->L, slots + SLOT_ABSMAX_GP, stream)) return rc; }
+        if (p->g_indiv_prob_label) { if (int rc = tc_absmax(p->g_indiv_prob_label, (size_t)p->B * p->L, slots + SLOT_ABSMAX_GP + 1, stream)) return rc; }
+        if (int rc = launch_gxs_bound(a, slots + SLOT_ABSMAX_GP, slots + SLOT_ABSMAX_GXS, stream)) return rc;
+        a.gxs_planes = reinterpret_cast<__half*>(base + w.gxs_planes);
+        a.gxs_pitch = tc_pitch(p->L);
+        a.gxs_plane_elems = (size_t)M * a.gxs_pitch;
+        a.gxs_scale = slots + SLOT_ABSMAX_GXS;
+    } else if (p->g_r) {
         a.gxs = reinterpret_cast<float*>(base + w.gxs);
-        if (tensor) {
-            a.gxs_absmax = slots + SLOT_ABSMAX_GXS;
-            if (cudaMemsetAsync(a.gxs_absmax, 0, sizeof(uint32_t), stream) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return 2; }
-        }
+        if (tensor) a.gxs_absmax = slots + SLOT_ABSMAX_GXS;
     }
     if (int rc = launch_row_backward(a, stream)) return rc;
     if (!p->g_r) return 0;
-    const int M = p->S * p->B;
     if (tensor) {
         void* gpl = base + w.gxs_planes;
-        if (int rc = tc_split(a.gxs, M, p->L, gpl, slots + SLOT_ABSMAX_GXS, 0, stream, row_pitch(p->L))) return rc;   // absmax: row kernel
-        // the noise planes the forward left in the workspace are the MN-major B operand as they are
+        void* tail = direct ? static_cast<void*>(base + w.tn_tail) : static_cast<void*>(a.gxs);
+        const size_t tail_bytes = direct ? tc_tail_scratch_bytes() : (size_t)M * row_pitch(p->L) * sizeof(float);
+        if (!direct) {
+            if (int rc = tc_split(a.gxs, M, p->L, gpl, slots + SLOT_ABSMAX_GXS, 0, stream, row_pitch(p->L))) return rc;   // absmax: row kernel
+        }
+        // the noise planes the forward left in the workspace are the MN-major B operand as they are; the fp32 gxs
+        // cube (when there is one) is dead once it has been split: scratch for the K-sliced tail wave
         return tc_gemm_tn(gpl, base + w.noise_planes, p->g_r, M, p->L, p->Z, slots + SLOT_ABSMAX_GXS, nullptr, stream,
-                          (!p->noise && tc_exact_supported()) ? 1 : 0);
+                          (!p->noise && tc_exact_supported()) ? 1 : 0, tail, tail_bytes);
     }
     const float* nz = p->noise ? p->noise : reinterpret_cast<const float*>(base + w.noise_f32);
     return launch_contract_tn_fma(a.gxs, nz, p->g_r, M, p->L, p->Z, base + w.fma_partials, w.total - w.fma_partials, stream,
@@ -270,15 +302,20 @@ uint64_t mpvae_contract_workspace_bytes(int32_t M, int32_t N, int32_t K, int32_t
 
 int mpvae_contract_nt(const float* A, const float* Bm, float* C, int32_t M, int32_t N, int32_t K, int32_t engine,
                       void* workspace, uint64_t workspace_bytes, void* cuda_stream) {
-    if (!A || !Bm || !C || M <= 0 || N <= 0 || K <= 0) { set_error("contract_nt: bad arguments"); return 1; }
+    return mpvae_contract_nt_pitched(A, Bm, C, M, N, K, N, engine, workspace, workspace_bytes, cuda_stream);
+}
+
+int mpvae_contract_nt_pitched(const float* A, const float* Bm, float* C, int32_t M, int32_t N, int32_t K, int32_t ldc,
+                              int32_t engine, void* workspace, uint64_t workspace_bytes, void* cuda_stream) {
+    if (!A || !Bm || !C || M <= 0 || N <= 0 || K <= 0 || ldc < N) { set_error("contract_nt: bad arguments"); return 1; }
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     if (engine == 0) engine = use_tensor(0, 1, M, N, K) ? 2 : 1;
     if (engine >= 2 && engine <= 5) {
         if (!tc_available()) { set_error("contract_nt: tensor engine not built"); return 7; }
         if (engine >= 4 && !tc_exact_supported()) { set_error("contract_nt: engines 4/5 need the CTA-pair kernel"); return 7; }
-        return tc_contract_nt(A, Bm, C, M, N, K, workspace, workspace_bytes, stream, engine == 3 || engine == 5, engine >= 4);
+        return tc_contract_nt(A, Bm, C, M, N, K, workspace, workspace_bytes, stream, engine == 3 || engine == 5, engine >= 4, ldc);
     }
-    return launch_contract_nt_fma(A, Bm, C, M, N, K, stream);
+    return launch_contract_nt_fma(A, Bm, C, M, N, K, stream, ldc);
 }
 
 int mpvae_contract_tn(const float* A, const float* Bm, float* C, int32_t M, int32_t N1, int32_t N2, int32_t engine,

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <string.h>
 
 namespace mpv {
 
@@ -17,6 +18,25 @@ constexpr int kNumSMs = 148;   // B200
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Per-tensor power-of-two scale of the fp16 operand split (contract_tc.cu): s = 2^(14 - e) with e the exponent of
+// `bits` (max |x|, or an upper bound of it, as raw fp32 bits), so that max|x| * s lies in [2^14, 2^15): one binade
+// under the fp16 maximum, which keeps the hi piece normal for elements down to 2^-28 of the maximum and the lo piece
+// normal down to 2^-17 of it.  0, Inf or NaN (e.g. the NaN gradients of degenerate rows) -> s = 1, values pass through.
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+static inline float scale_from_absmax_bits(uint32_t bits) {
+    bits &= 0x7FFFFFFFu;
+    if (bits == 0u || bits >= 0x7F800000u) return 1.0f;
+    int e = (int)(bits >> 23) - 127;
+    if (e < -100) e = -100;
+    if (e > 100) e = 100;
+    const uint32_t sb = (uint32_t)(127 + 14 - e) << 23;
+    float f;
+    memcpy(&f, &sb, 4);
+    return f;
+}
 
 #ifdef __CUDACC__
 __device__ __forceinline__ float warp_sum(float v) {

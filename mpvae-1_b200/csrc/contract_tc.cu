@@ -151,24 +151,6 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo16, ui
            (1ull << 46) | ((uint64_t)layout << 61);
 }
 
-// Per-tensor power-of-two scale for the fp16 split: s = 2^-e with e = exponent of max|x|, so max|x| * s is in
-// [1, 2).  max == 0, Inf or NaN (e.g. the NaN gradients of degenerate rows) -> s = 1 and the values pass through.
-__host__ __device__ __forceinline__ float scale_from_absmax_bits(uint32_t bits) {
-    bits &= 0x7FFFFFFFu;
-    if (bits == 0u || bits >= 0x7F800000u) return 1.0f;
-    int e = (int)(bits >> 23) - 127;
-    if (e < -100) e = -100;
-    if (e > 100) e = 100;
-    const uint32_t sb = (uint32_t)(127 - e) << 23;
-#if defined(__CUDA_ARCH__)
-    return __uint_as_float(sb);
-#else
-    float f;
-    memcpy(&f, &sb, 4);
-    return f;
-#endif
-}
-
 // ------------------------------------------------------------------------------------------------ GEMM
 // C[Mc, Nc] (row-major, pitch ldc) = inv_scale * sum_k A(m, k) * B(n, k); operands come pre-split as [2][.][.]
 // planes (0 = hi, 1 = lo) through 3-D TMA maps.
@@ -436,7 +418,8 @@ template <bool MN, bool F16, int EX, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       float* __restrict__ C, int Mc, int Nc, int K, int ldc, int tiles_m, int tiles_n, int kc,
-                      const uint32_t* __restrict__ absmax_a, const uint32_t* __restrict__ absmax_b, int dbg) {
+                      const uint32_t* __restrict__ absmax_a, const uint32_t* __restrict__ absmax_b, int dbg,
+                      int full_tiles, int ksplit, float* __restrict__ partials) {
     using G = Geo<MN, F16>;
     using R2 = Ring2<EX>;
     constexpr int STAGES2 = R2::STAGES, STAGE2_BYTES = R2::STAGE_BYTES;
@@ -468,6 +451,22 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int num_super = sup_m * sup_n;
     auto tile_m_of = [&](int st) { return SHARE_A ? st / sup_n : (st / sup_n) * CL + (int)cpair; };
     auto tile_n_of = [&](int st) { return SHARE_A ? (st % sup_n) * CL + (int)cpair : st % sup_n; };
+    // Work items.  Tiles [0, full_tiles) fill whole waves of the persistent grid and run over all of K.  Each tile of
+    // the last, partial wave is cut into `ksplit` slices of K so that the wave keeps every pair busy for 1/ksplit of
+    // a tile time instead of leaving most of them idle for a whole one: slice 0 writes C, slice j > 0 writes a
+    // 256 x 256 scratch tile that tail_fixup_kernel adds to C afterwards (fixed order -> reproducible).
+    const int num_items = (ksplit > 1) ? full_tiles + (num_super - full_tiles) * ksplit : num_super;
+    struct Item { int st, kb_lo, kb_hi, slice; };
+    auto item_of = [&](int w, int num_kb) {
+        Item it;
+        if (ksplit <= 1 || w < full_tiles) { it.st = w; it.kb_lo = 0; it.kb_hi = num_kb; it.slice = 0; return it; }
+        const int r = w - full_tiles;
+        it.st = full_tiles + r / ksplit;
+        it.slice = r % ksplit;
+        it.kb_lo = (int)(((long long)num_kb * it.slice) / ksplit);
+        it.kb_hi = (int)(((long long)num_kb * (it.slice + 1)) / ksplit);
+        return it;
+    };
     const uint16_t mask_all = (uint16_t)((1u << (2 * CL)) - 1u);
     const uint16_t mask_pair = (uint16_t)(3u << (2 * cpair));
     const uint16_t mask_share = (uint16_t)((1u << rank) | (1u << (rank + 2)));   // same parity in both pairs
@@ -494,10 +493,12 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (lane == 0) {   // ------------------------------------------------ TMA producer (every CTA)
             int stage = 0;
             uint32_t phase = 0;
-            for (int st = cluster; st < num_super; st += num_clusters) {
+            for (int w = cluster; w < num_items; w += num_clusters) {
+                const Item it = item_of(w, num_kb);
+                const int st = it.st;
                 const int m0 = tile_m_of(st) * 256 + (int)rank * BM;          // this CTA's 128 rows of A
                 const int n0 = tile_n_of(st) * BN + (int)rank * HB;           // this CTA's half of the B tile
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = it.kb_lo; kb < it.kb_hi; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t fb = map_to_cta(full_bar(stage), leader_rank);   // the pair leader's barrier collects both CTAs' bytes
                     if (dbg == 1) {   // timing probe: no loads
@@ -560,12 +561,13 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (lane == 0 && leader) {   // ------------------------------------- MMA issuer (leader CTA only)
             int stage = 0, buf = 0;
             uint32_t phase = 0, bphase = 0;
-            for (int st = cluster; st < num_super; st += num_clusters) {
-                for (int kb0 = 0; kb0 < num_kb; kb0 += kc) {
+            for (int w = cluster; w < num_items; w += num_clusters) {
+                const Item it = item_of(w, num_kb);
+                for (int kb0 = it.kb_lo; kb0 < it.kb_hi; kb0 += kc) {
                     mbar_wait(tempty_bar(buf), bphase ^ 1u);     // both CTAs' promotion warps have drained this buffer
                     tc_fence_after();
                     const uint32_t d = tmem_base + (uint32_t)(buf * BN);
-                    const int kb1 = min(kb0 + kc, num_kb);
+                    const int kb1 = min(kb0 + kc, it.kb_hi);
                     for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
@@ -612,12 +614,14 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int j = 0; j < 64; ++j) acc[j] = 0.0f;
         int buf = 0;
         uint32_t bphase = 0;
-        for (int st = cluster; st < num_super; st += num_clusters) {
-            for (int kb0 = 0; kb0 < num_kb; kb0 += kc) {
+        for (int w = cluster; w < num_items; w += num_clusters) {
+            const Item it = item_of(w, num_kb);
+            const int st = it.st;
+            for (int kb0 = it.kb_lo; kb0 < it.kb_hi; kb0 += kc) {
                 mbar_wait(tfull_bar(buf), bphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + h * 64);
-                const float unbias = 1.0f + G::trunc_bias * R2::BIAS_SCALE * (float)(min(kb0 + kc, num_kb) - kb0);
+                const float unbias = 1.0f + G::trunc_bias * R2::BIAS_SCALE * (float)(min(kb0 + kc, it.kb_hi) - kb0);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     uint32_t v[16];
@@ -633,7 +637,16 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             }
             const int row = tile_m_of(st) * 256 + (int)rank * BM + q * 32 + lane;
             const int col0 = tile_n_of(st) * BN + h * 64;
-            if (row < Mc && col0 < Nc) {
+            if (it.slice > 0) {
+                // K-slice of a tail tile: the whole 256 x 256 scratch tile is written (rows / columns beyond the
+                // matrix hold sums of zero-filled boxes, i.e. zeros)
+                float* __restrict__ prow = partials + ((size_t)(st - full_tiles) * (ksplit - 1) + (it.slice - 1)) * (256 * BN) +
+                                           (size_t)((int)rank * BM + q * 32 + lane) * BN + h * 64;
+#pragma unroll
+                for (int j = 0; j < 64; j += 4)
+                    *reinterpret_cast<float4*>(prow + j) =
+                        make_float4(acc[j] * inv_scale, acc[j + 1] * inv_scale, acc[j + 2] * inv_scale, acc[j + 3] * inv_scale);
+            } else if (row < Mc && col0 < Nc) {
                 float* __restrict__ crow = C + (size_t)row * ldc;
                 if (vec_store && col0 + 64 <= ldc) {
                     // 16-byte stores: rows are 16 B aligned (ldc % 4 == 0); columns in [Nc, ldc) are pitch padding
@@ -657,6 +670,27 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// C += the K-slices 1 .. ksplit-1 of the tail tiles (see Item above), slice order fixed.  32 CTAs per tail tile,
+// each 8 rows of 256 columns.
+__global__ void __launch_bounds__(256)
+tail_fixup_kernel(float* __restrict__ C, int Mc, int Nc, int ldc, int tiles_n, int full_tiles, int ksplit,
+                  const float* __restrict__ partials) {
+    const int t = blockIdx.x >> 5, rows0 = (blockIdx.x & 31) * 8;
+    const int st = full_tiles + t;
+    const int m0 = (st / tiles_n) * 256, n0 = (st % tiles_n) * BN;
+    const float* __restrict__ p = partials + (size_t)t * (ksplit - 1) * (256 * BN);
+    const int c = threadIdx.x;                      // BN == 256 columns, one per thread
+    if (n0 + c >= Nc) return;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = rows0 + i;
+        if (m0 + r >= Mc) break;
+        float v = C[(size_t)(m0 + r) * ldc + n0 + c];
+        for (int j = 0; j < ksplit - 1; ++j) v += p[(size_t)j * (256 * BN) + r * BN + c];
+        C[(size_t)(m0 + r) * ldc + n0 + c] = v;
     }
 }
 
@@ -686,7 +720,19 @@ split_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, int ro
 __global__ void __launch_bounds__(256)
 absmax_kernel(const float* __restrict__ src, size_t n, uint32_t* __restrict__ out) {
     uint32_t m = 0;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+    size_t done = 0;
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {      // 16-byte loads over the aligned bulk
+        const size_t n4 = n / 4;
+        const uint4* __restrict__ s4 = reinterpret_cast<const uint4*>(src);
+        for (size_t i = tid; i < n4; i += nthr) {
+            const uint4 v = s4[i];
+            const uint32_t a = max(max(v.x & 0x7FFFFFFFu, v.y & 0x7FFFFFFFu), max(v.z & 0x7FFFFFFFu, v.w & 0x7FFFFFFFu));
+            m = a > m ? a : m;
+        }
+        done = n4 * 4;
+    }
+    for (size_t i = done + tid; i < n; i += nthr) {
         const uint32_t b = __float_as_uint(src[i]) & 0x7FFFFFFFu;
         m = b > m ? b : m;
     }
@@ -828,7 +874,7 @@ int nt_b_box_rows() { return cta_group() == 2 ? BN / 2 / cluster_pairs() : BN; }
 
 template <bool MN, bool F16, int EX, int CL>
 int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc, int Nc, int K, int ldc, const uint32_t* ma,
-                    const uint32_t* mb, int kc, int dbg, cudaStream_t stream) {
+                    const uint32_t* mb, int kc, int dbg, cudaStream_t stream, float* partials, size_t partials_bytes) {
     auto kernel = gemm_split_2sm_kernel<MN, F16, EX, CL>;
     static int max_clusters = 0;     // co-resident clusters (a cluster must fit inside one GPC)
     cudaLaunchConfig_t cfg = {};
@@ -852,34 +898,56 @@ int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc
     }
     const int tiles_m = ceil_div(Mc, 256), tiles_n = ceil_div(Nc, BN);
     const int supers = (EX == 2) ? tiles_m * ceil_div(tiles_n, CL) : ceil_div(tiles_m, CL) * tiles_n;
-    const int clusters = supers < max_clusters ? supers : max_clusters;
+    // K-split of the last, partial wave (plain pairs only): worth it when the wave would leave at least half of the
+    // pairs idle and the caller gave scratch for the slices
+    int full_tiles = supers, ksplit = 1;
+    static const bool no_split = getenv("MPVAE_TC_NO_KSPLIT") != nullptr;
+    if (CL == 1 && partials != nullptr && !no_split) {
+        const int tail = supers % max_clusters, num_kb = ceil_div(K, Geo<MN, F16>::BK);
+        if (tail > 0) {
+            int f = max_clusters / tail;
+            if (f > num_kb / kc) f = num_kb / kc;                      // a slice keeps at least one full TMEM chunk
+            if (f > 8) f = 8;
+            if (f >= 2 && (size_t)tail * (f - 1) * 256 * BN * sizeof(float) <= partials_bytes) { full_tiles = supers - tail; ksplit = f; }
+        }
+    }
+    const int items = full_tiles + (supers - full_tiles) * ksplit;
+    const int clusters = items < max_clusters ? items : max_clusters;
     cfg.gridDim = dim3(2 * CL * clusters);
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, a, b, C, Mc, Nc, K, ldc, tiles_m, tiles_n, kc, ma, mb, dbg);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, a, b, C, Mc, Nc, K, ldc, tiles_m, tiles_n, kc, ma, mb, dbg, full_tiles, ksplit,
+                                             partials);
     if (e != cudaSuccess) { set_error("gemm_split_2sm_kernel launch: %s", cudaGetErrorString(e)); return 3; }
-    return check_launch("gemm_split_2sm_kernel");
+    if (int rc = check_launch("gemm_split_2sm_kernel")) return rc;
+    if (ksplit > 1 && dbg == 0) {
+        static_assert(BN == 256, "tail_fixup_kernel maps one thread to one tile column");
+        tail_fixup_kernel<<<(supers - full_tiles) * 32, 256, 0, stream>>>(C, Mc, Nc, ldc, tiles_n, full_tiles, ksplit, partials);
+        return check_launch("tail_fixup_kernel");
+    }
+    return 0;
 }
 
 template <bool MN, bool F16, int EX>
 int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc, int Nc, int K, int ldc, const uint32_t* ma,
-                    const uint32_t* mb, int kc, int dbg, cudaStream_t stream) {
-    if (cluster_pairs() == 2) return launch_gemm_2sm<MN, F16, EX, 2>(a, b, C, Mc, Nc, K, ldc, ma, mb, kc, dbg, stream);
-    return launch_gemm_2sm<MN, F16, EX, 1>(a, b, C, Mc, Nc, K, ldc, ma, mb, kc, dbg, stream);
+                    const uint32_t* mb, int kc, int dbg, cudaStream_t stream, float* partials, size_t partials_bytes) {
+    if (cluster_pairs() == 2)
+        return launch_gemm_2sm<MN, F16, EX, 2>(a, b, C, Mc, Nc, K, ldc, ma, mb, kc, dbg, stream, partials, partials_bytes);
+    return launch_gemm_2sm<MN, F16, EX, 1>(a, b, C, Mc, Nc, K, ldc, ma, mb, kc, dbg, stream, partials, partials_bytes);
 }
 
 // ex: 0 = both operands carry hi|lo planes, 1 = A is exact (single plane), 2 = B is exact.  Exact operands need the
 // CTA-pair kernel (tc_exact_supported()).
 template <bool MN, bool F16>
 int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc, int Nc, int K, int ldc, const uint32_t* ma,
-                const uint32_t* mb, cudaStream_t stream, int ex = 0) {
+                const uint32_t* mb, cudaStream_t stream, int ex = 0, float* partials = nullptr, size_t partials_bytes = 0) {
     // k-blocks per TMEM chunk: the same number of truncating MMAs per chunk (48) whether a k-step is 3 or 2 MMAs
     const int kc = chunk_kblocks(ex == 0 ? Geo<MN, F16>::default_kc : (Geo<MN, F16>::default_kc * 3) / 2);
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("MPVAE_TC_DEBUG"); dbg = e ? atoi(e) : 0; }   // timing probes, results invalid
     if (dbg == 3) return 0;                                                               // pre-passes only
     if (cta_group() == 2) {
-        if (ex == 1) return launch_gemm_2sm<MN, F16, 1>(a, b, C, Mc, Nc, K, ldc, ma, mb, kc, dbg, stream);
-        if (ex == 2) return launch_gemm_2sm<MN, F16, 2>(a, b, C, Mc, Nc, K, ldc, ma, mb, kc, dbg, stream);
-        return launch_gemm_2sm<MN, F16, 0>(a, b, C, Mc, Nc, K, ldc, ma, mb, kc, dbg, stream);
+        if (ex == 1) return launch_gemm_2sm<MN, F16, 1>(a, b, C, Mc, Nc, K, ldc, ma, mb, kc, dbg, stream, partials, partials_bytes);
+        if (ex == 2) return launch_gemm_2sm<MN, F16, 2>(a, b, C, Mc, Nc, K, ldc, ma, mb, kc, dbg, stream, partials, partials_bytes);
+        return launch_gemm_2sm<MN, F16, 0>(a, b, C, Mc, Nc, K, ldc, ma, mb, kc, dbg, stream, partials, partials_bytes);
     }
     if (ex != 0) { set_error("exact-operand products need the CTA-pair kernel"); return 7; }
     static bool configured = false;
@@ -899,18 +967,20 @@ int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc, in
 
 bool tc_available() { return true; }
 
+// [absmax slots] [A planes] [B planes] [tail-wave scratch (tn only)]
 size_t tc_workspace_nt(int M, int N, int K) {
     const size_t kp = pitch_of(K);
     return 256 + planes_bytes(M, kp) + planes_bytes(N, kp);
 }
 
 size_t tc_workspace_tn(int M, int N1, int N2) {
-    return 256 + planes_bytes(M, pitch_of(N1)) + planes_bytes(M, pitch_of(N2));
+    return 256 + planes_bytes(M, pitch_of(N1)) + planes_bytes(M, pitch_of(N2)) + tc_tail_scratch_bytes();
 }
 
 int tc_contract_nt(const float* A, const float* Bm, float* C, int M, int N, int K, void* ws, size_t ws_bytes,
-                   cudaStream_t stream, int reuse_planes, int exact) {
+                   cudaStream_t stream, int reuse_planes, int exact, int ldc) {
     if (!ws || ws_bytes < tc_workspace_nt(M, N, K)) { set_error("tc_contract_nt: workspace too small"); return 5; }
+    if (ldc <= 0) ldc = N;
     const int ex = exact ? 1 : 0;
     const bool f16 = use_f16();
     const int kp = pitch_of(K);
@@ -924,8 +994,9 @@ int tc_contract_nt(const float* A, const float* Bm, float* C, int M, int N, int 
     const int bk = f16 ? 64 : 32;
     if (int rc = make_map(&ma, s.a, f16, K, M, kp, bk, BM, CU_TENSOR_MAP_SWIZZLE_128B, ex ? 1 : 2)) return rc;
     if (int rc = make_map(&mb, s.b, f16, K, N, kp, bk, nt_b_box_rows(), CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    if (f16) return launch_gemm<false, true>(ma, mb, C, M, N, K, N, s.absmax, s.absmax + 1, stream, ex);
-    return launch_gemm<false, false>(ma, mb, C, M, N, K, N, nullptr, nullptr, stream, ex);
+    // no K-sliced tail wave for nt: each element's summation order stays a function of K alone (shard invariance)
+    if (f16) return launch_gemm<false, true>(ma, mb, C, M, N, K, ldc, s.absmax, s.absmax + 1, stream, ex);
+    return launch_gemm<false, false>(ma, mb, C, M, N, K, ldc, nullptr, nullptr, stream, ex);
 }
 
 int tc_contract_tn(const float* A, const float* Bm, float* C, int M, int N1, int N2, void* ws, size_t ws_bytes,
@@ -945,8 +1016,9 @@ int tc_contract_tn(const float* A, const float* Bm, float* C, int M, int N1, int
     const CUtensorMapSwizzle sw = f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     if (int rc = make_map(&ma, s.a, f16, N1, M, p1, box_mn, bk, sw)) return rc;
     if (int rc = make_map(&mb, s.b, f16, N2, M, p2, box_mn, bk, sw, ex ? 1 : 2)) return rc;
-    if (f16) return launch_gemm<true, true>(ma, mb, C, N1, N2, M, N2, s.absmax, s.absmax + 1, stream, ex);
-    return launch_gemm<true, false>(ma, mb, C, N1, N2, M, N2, nullptr, nullptr, stream, ex);
+    float* tail = reinterpret_cast<float*>(s.b + planes_bytes(M, p2));
+    if (f16) return launch_gemm<true, true>(ma, mb, C, N1, N2, M, N2, s.absmax, s.absmax + 1, stream, ex, tail, tc_tail_scratch_bytes());
+    return launch_gemm<true, false>(ma, mb, C, N1, N2, M, N2, nullptr, nullptr, stream, ex, tail, tc_tail_scratch_bytes());
 }
 
 // ------------------------------------------------------------------------------------------------ staged interface
@@ -991,13 +1063,34 @@ philox_planes_kernel(void* __restrict__ planes, int S, int B, int Z, int pitch, 
     const long long e0 = (long long)((c << 2) - span_beg);               // may be -3..-1 for the first counter
     int row = e0 >= 0 ? (int)((unsigned)e0 / (unsigned)Z) : -1;
     int col = e0 >= 0 ? (int)((unsigned)e0 % (unsigned)Z) : Z + (int)e0;
+    // n[j] already lies on the fp16 grid (philox_normal4), so hi = n and lo = 0 in both kinds
+    if (F16 && !write_lo && row >= 0 && row < B && col + 4 <= Z) {
+        // the common case: four neighbours of one row; as few stores as the alignment of the destination allows
+        // (it is the same for every thread of a row, so a warp does not diverge here)
+        __half* dst = static_cast<__half*>(planes) + ((size_t)s * B + (size_t)row) * pitch + (size_t)col;
+        const __half2 p01 = __floats2half2_rn(n[0], n[1]), p23 = __floats2half2_rn(n[2], n[3]);
+        const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
+        if ((a & 7u) == 0) {
+            uint2 v;
+            v.x = *reinterpret_cast<const uint32_t*>(&p01);
+            v.y = *reinterpret_cast<const uint32_t*>(&p23);
+            *reinterpret_cast<uint2*>(dst) = v;
+        } else if ((a & 3u) == 0) {
+            *reinterpret_cast<__half2*>(dst) = p01;
+            *reinterpret_cast<__half2*>(dst + 2) = p23;
+        } else {
+            dst[0] = __low2half(p01);
+            *reinterpret_cast<__half2*>(dst + 1) = __halves2half2(__high2half(p01), __low2half(p23));
+            dst[3] = __high2half(p23);
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int r = row, cc = col;
         if (++col == Z) { col = 0; ++row; }
         if (r < 0 || r >= B) continue;
         const size_t o = ((size_t)s * B + (size_t)r) * pitch + (size_t)cc;
-        // n[j] already lies on the fp16 grid (philox_normal4), so hi = n and lo = 0 in both kinds
         if (F16) {
             static_cast<__half*>(planes)[o] = __float2half_rn(n[j]);
             if (write_lo) static_cast<__half*>(planes)[plane + o] = __float2half_rn(0.0f);
@@ -1027,20 +1120,30 @@ int tc_philox_planes(void* planes, int S, int B, int Z, int Bg, int row0, uint64
 
 bool tc_exact_supported() { return cta_group() == 2; }
 
+bool tc_f16_kind() { return use_f16(); }
+int tc_pitch(int cols) { return pitch_of(cols); }
+int tc_absmax(const float* src, size_t n, uint32_t* out_bits, cudaStream_t stream) {
+    absmax_kernel<<<grid_for(n), 256, 0, stream>>>(src, n, out_bits);
+    return check_launch("absmax_kernel");
+}
+
+size_t tc_tail_scratch_bytes() { return (size_t)(kNumSMs / 2 - 1) * 256 * BN * sizeof(float); }
+
 int tc_gemm_nt(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, const uint32_t* absmax_a,
-               const uint32_t* absmax_b, cudaStream_t stream, int ldc, int a_exact) {
+               const uint32_t* absmax_b, cudaStream_t stream, int ldc, int a_exact, void* tail_scratch, size_t tail_scratch_bytes) {
     if (ldc <= 0) ldc = N;
     const bool f16 = use_f16();
     const int kp = pitch_of(K), bk = f16 ? 64 : 32;
     CUtensorMap ma, mb;
     if (int rc = make_map(&ma, a_planes, f16, K, M, kp, bk, BM, CU_TENSOR_MAP_SWIZZLE_128B, a_exact ? 1 : 2)) return rc;
     if (int rc = make_map(&mb, b_planes, f16, K, N, kp, bk, nt_b_box_rows(), CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    if (f16) return launch_gemm<false, true>(ma, mb, C, M, N, K, ldc, absmax_a, absmax_b, stream, a_exact ? 1 : 0);
-    return launch_gemm<false, false>(ma, mb, C, M, N, K, ldc, nullptr, nullptr, stream, a_exact ? 1 : 0);
+    float* ts = static_cast<float*>(tail_scratch);
+    if (f16) return launch_gemm<false, true>(ma, mb, C, M, N, K, ldc, absmax_a, absmax_b, stream, a_exact ? 1 : 0, ts, tail_scratch_bytes);
+    return launch_gemm<false, false>(ma, mb, C, M, N, K, ldc, nullptr, nullptr, stream, a_exact ? 1 : 0, ts, tail_scratch_bytes);
 }
 
 int tc_gemm_tn(const void* a_planes, const void* b_planes, float* C, int M, int N1, int N2, const uint32_t* absmax_a,
-               const uint32_t* absmax_b, cudaStream_t stream, int b_exact) {
+               const uint32_t* absmax_b, cudaStream_t stream, int b_exact, void* tail_scratch, size_t tail_scratch_bytes) {
     const bool f16 = use_f16();
     const int p1 = pitch_of(N1), p2 = pitch_of(N2);
     const int bk = f16 ? 64 : 32, box_mn = f16 ? 64 : 32;
@@ -1048,8 +1151,9 @@ int tc_gemm_tn(const void* a_planes, const void* b_planes, float* C, int M, int 
     CUtensorMap ma, mb;
     if (int rc = make_map(&ma, a_planes, f16, N1, M, p1, box_mn, bk, sw)) return rc;
     if (int rc = make_map(&mb, b_planes, f16, N2, M, p2, box_mn, bk, sw, b_exact ? 1 : 2)) return rc;
-    if (f16) return launch_gemm<true, true>(ma, mb, C, N1, N2, M, N2, absmax_a, absmax_b, stream, b_exact ? 2 : 0);
-    return launch_gemm<true, false>(ma, mb, C, N1, N2, M, N2, nullptr, nullptr, stream, b_exact ? 2 : 0);
+    float* ts = static_cast<float*>(tail_scratch);
+    if (f16) return launch_gemm<true, true>(ma, mb, C, N1, N2, M, N2, absmax_a, absmax_b, stream, b_exact ? 2 : 0, ts, tail_scratch_bytes);
+    return launch_gemm<true, false>(ma, mb, C, N1, N2, M, N2, nullptr, nullptr, stream, b_exact ? 2 : 0, ts, tail_scratch_bytes);
 }
 
 }  // namespace mpv

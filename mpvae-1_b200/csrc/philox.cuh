@@ -19,13 +19,19 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     return ctr;
 }
 
+// Box-Muller on the special-function unit (MUFU lg2 / sqrt / sin / cos).  The outputs are rounded to the fp16 grid
+// right after (philox_normal4), a 2.4e-4 relative step, so the ~1e-6 error of the approximate units is invisible
+// there; what it buys is a third of the instructions of logf / sqrtf / sincospif.
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
     // 23 random bits + 0.5 is exact in fp32, so u is never 0 or 1 and has no rounding step
     const float u1 = ((float)(a >> 9) + 0.5f) * (1.0f / 8388608.0f);   // (0, 1)
     const float u2 = ((float)(b >> 9) + 0.5f) * (1.0f / 8388608.0f);
-    const float r = sqrtf(-2.0f * logf(u1));
+    // r^2 = -2 ln u1 = -2 ln2 * log2 u1; clamped at 0 because lg2.approx may return +1 ulp for u1 -> 1
+    const float r2 = fmaxf(-1.3862943611198906f * __log2f(u1), 0.0f);
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(r2));
     float sn, cs;
-    sincospif(2.0f * u2, &sn, &cs);
+    __sincosf(6.283185307179586f * u2, &sn, &cs);
     n0 = r * cs;
     n1 = r * sn;
 }

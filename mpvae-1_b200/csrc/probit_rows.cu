@@ -236,6 +236,61 @@ probit_row_fwd_kernel(const RowArgs a) {
     }
 }
 
+// Per-row coefficients of the backward (see cell_backward): effective weights of the loss terms = d objective / d term
+// (mpvae.py:207-208 + upstream cotangents), the ranking normaliser k_b and the log-likelihood factor -(a_nll / B).
+struct RowCoeffs { float kb[2], cnb[2], a_kl; };
+
+__device__ __forceinline__ RowCoeffs row_coeffs(const RowArgs& a, int b) {
+    const float gt = a.g_scalars[0] ? *a.g_scalars[0] : 0.0f, g1 = a.g_scalars[1] ? *a.g_scalars[1] : 0.0f,
+                g2 = a.g_scalars[2] ? *a.g_scalars[2] : 0.0f, g3 = a.g_scalars[3] ? *a.g_scalars[3] : 0.0f,
+                g4 = a.g_scalars[4] ? *a.g_scalars[4] : 0.0f, g5 = a.g_scalars[5] ? *a.g_scalars[5] : 0.0f;
+    const float a_nll[2] = {gt * a.nll_coeff + g1, gt * a.nll_coeff + g2};
+    const float a_c[2] = {gt * a.c_coeff + g3, gt * a.c_coeff + g4};
+    RowCoeffs rc;
+    rc.a_kl = gt * 1.1f + g5;
+    const float npos = a.rowaux[(size_t)b * 2], nneg = a.rowaux[(size_t)b * 2 + 1];
+    const float norm5 = 5.0f * (npos * nneg);
+    const float fS = (float)a.S, fB = (float)a.B;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        if (norm5 == 0.0f) {
+            // the reference back-propagates 0/0 through torch.div here (mpvae.py:118): NaN for the whole row
+            rc.kb[q] = a.sanitize ? 0.0f : __fdiv_rn(0.0f, norm5);
+        } else {
+            rc.kb[q] = (a_c[q] / (fS * fB)) / norm5;
+        }
+        rc.cnb[q] = -(a_nll[q] / fB);
+    }
+    return rc;
+}
+
+// Upper bound of |gxs| for one (row, sample), from cell_backward:
+//   |dL/dx| <= |cn| * max(phi/E, phi/(1-E)) + max(|cp| e^{-5E}, |cq| e^{5E}) * phi + |gp| * phi
+// with phi/E <= 4.3 (the clamp E >= eps/2 caps the inverse Mills ratio near x = -4.2; same by symmetry for 1-E),
+// e^{5E} phi <= 16.1 (x ~ 1) and phi <= 0.4.  Constants rounded up: 5, 17, 0.4.  The bound only has to be an upper
+// bound within a few binades: it sets the power-of-two scale of the fp16 planes (common.cuh).
+__global__ void __launch_bounds__(256)
+gxs_bound_kernel(const RowArgs a, const unsigned int* __restrict__ gp_absmax, unsigned int* __restrict__ out_bits) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int bits = 0u;
+    if (i < a.B * a.S) {
+        const int b = i / a.S;
+        const RowCoeffs rc = row_coeffs(a, b);
+        const float4 st = reinterpret_cast<const float4*>(a.stat)[i];
+        const float2 w = reinterpret_cast<const float2*>(a.wts)[i];
+        const float gp = gp_absmax ? (__uint_as_float(gp_absmax[0]) + __uint_as_float(gp_absmax[1])) / (float)a.S : 0.0f;
+        const float bl = 5.0f * fabsf(rc.cnb[0] * w.x) + 17.0f * 5.0f * fabsf(rc.kb[0]) * fmaxf(st.x, st.y);
+        const float bx = 5.0f * fabsf(rc.cnb[1] * w.y) + 17.0f * 5.0f * fabsf(rc.kb[1]) * fmaxf(st.z, st.w);
+        bits = __float_as_uint(bl + bx + 0.4f * gp) & 0x7FFFFFFFu;   // NaN (degenerate row) sorts highest
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned int t = __shfl_xor_sync(0xffffffffu, bits, o);
+        bits = t > bits ? t : bits;
+    }
+    if ((threadIdx.x & 31) == 0 && bits != 0u) atomicMax(out_bits, bits);
+}
+
 __global__ void __launch_bounds__(kThreads, 4)
 probit_row_bwd_kernel(const RowArgs a) {
     extern __shared__ float s_gacc[];   // [nws][2][L] logit-gradient partial sums
@@ -251,29 +306,13 @@ probit_row_bwd_kernel(const RowArgs a) {
 
     for (int i = tid; i < nws * 2 * L; i += kThreads) s_gacc[i] = 0.0f;
 
-    // effective weights of the five loss terms: d objective / d term (mpvae.py:207-208 + upstream)
-    const float gt = a.g_scalars[0] ? *a.g_scalars[0] : 0.0f, g1 = a.g_scalars[1] ? *a.g_scalars[1] : 0.0f,
-                g2 = a.g_scalars[2] ? *a.g_scalars[2] : 0.0f, g3 = a.g_scalars[3] ? *a.g_scalars[3] : 0.0f,
-                g4 = a.g_scalars[4] ? *a.g_scalars[4] : 0.0f, g5 = a.g_scalars[5] ? *a.g_scalars[5] : 0.0f;
-    const float a_nll[2] = {gt * a.nll_coeff + g1, gt * a.nll_coeff + g2};
-    const float a_c[2] = {gt * a.c_coeff + g3, gt * a.c_coeff + g4};
-    const float a_kl = gt * 1.1f + g5;
-
-    const float npos = a.rowaux[(size_t)b * 2], nneg = a.rowaux[(size_t)b * 2 + 1];
-    const float norm5 = 5.0f * (npos * nneg);
+    const RowCoeffs rc = row_coeffs(a, b);
     const float fS = (float)S, fB = (float)B;
-    float kb[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        if (norm5 == 0.0f) {
-            // the reference back-propagates 0/0 through torch.div here (mpvae.py:118): NaN for the whole row
-            kb[q] = a.sanitize ? 0.0f : __fdiv_rn(0.0f, norm5);
-        } else {
-            kb[q] = (a_c[q] / (fS * fB)) / norm5;
-        }
-    }
-    const float cnb[2] = {-(a_nll[0] / fB), -(a_nll[1] / fB)};
+    const float a_kl = rc.a_kl;
+    const float* kb = rc.kb;
+    const float* cnb = rc.cnb;
     const bool has_gp = a.g_indiv_prob != nullptr, has_gpl = a.g_indiv_prob_label != nullptr;
+    const float gscale = a.gxs_planes ? scale_from_absmax_bits(*a.gxs_scale) : 1.0f;
     __syncthreads();
 
     unsigned int gmax = 0u;
@@ -309,7 +348,14 @@ probit_row_bwd_kernel(const RowArgs a) {
                         const float dl = cell_backward(cur.nr[i] + cur.fe, cur.y, cn[i][0], cp[i][0], cq[i][0], gpl);
                         const float dx = cell_backward(cur.nr[i] + cur.fx, cur.y, cn[i][1], cp[i][1], cq[i][1], gpx);
                         gl += dl; gx += dx;
-                        if (a.gxs) {
+                        if (a.gxs_planes) {
+                            // operand planes of gxs^T . noise: hi = fp16(g s), lo = fp16(g s - hi)
+                            const float g = (dl + dx) * gscale;
+                            const __half hi = __float2half_rn(g);
+                            __half* __restrict__ dst = a.gxs_planes + ((size_t)(s0 + i) * B + b) * a.gxs_pitch + l;
+                            dst[0] = hi;
+                            dst[a.gxs_plane_elems] = __float2half_rn(g - __half2float(hi));
+                        } else if (a.gxs) {
                             const float g = dl + dx;
                             a.gxs[((size_t)(s0 + i) * B + b) * a.ldn + l] = g;
                             const unsigned int gb = __float_as_uint(g) & 0x7FFFFFFFu;   // |g| as ordered bits, NaN highest
@@ -323,7 +369,15 @@ probit_row_bwd_kernel(const RowArgs a) {
             cur = nxt;
         }
     }
-    if (a.gxs_absmax) {   // one atomic per warp: scale of the fp16 operand split of gxs (contract_tc.cu)
+    if (a.gxs_planes) {   // pad columns [L, pitch) of this row's S plane rows
+        const int pad = a.gxs_pitch - L;
+        for (int i = tid; i < S * pad; i += kThreads) {
+            __half* __restrict__ dst = a.gxs_planes + ((size_t)(i / pad) * B + b) * a.gxs_pitch + L + (i % pad);
+            dst[0] = __float2half_rn(0.0f);
+            dst[a.gxs_plane_elems] = __float2half_rn(0.0f);
+        }
+    }
+    if (a.gxs_absmax && !a.gxs_planes) {   // one atomic per warp: scale of the fp16 operand split of gxs (contract_tc.cu)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const unsigned int t = __shfl_xor_sync(0xffffffffu, gmax, o);
@@ -376,6 +430,11 @@ int launch_row_forward(RowArgs a, cudaStream_t stream) {
     }
     probit_row_fwd_kernel<<<a.B, kThreads, smem, stream>>>(a);
     return check_launch("probit_row_fwd_kernel");
+}
+
+int launch_gxs_bound(RowArgs a, const unsigned int* gp_absmax, unsigned int* out_bits, cudaStream_t stream) {
+    gxs_bound_kernel<<<ceil_div(a.B * a.S, 256), 256, 0, stream>>>(a, gp_absmax, out_bits);
+    return check_launch("gxs_bound_kernel");
 }
 
 int launch_row_backward(RowArgs a, cudaStream_t stream) {

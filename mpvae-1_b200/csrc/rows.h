@@ -1,5 +1,6 @@
 // Internal launch interfaces shared by the .cu translation units of libmpvae_b200.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -31,11 +32,21 @@ struct RowArgs {
     float *g_fe_out, *g_fx_out, *g_fe_mu, *g_fe_logvar, *g_fx_mu, *g_fx_logvar;
     float* gxs;        // (S,B,L) gx_l + gx_x, or nullptr when R needs no gradient
     unsigned int* gxs_absmax;   // max |gxs| as fp32 bits (atomicMax), or nullptr; feeds the fp16 operand scale
+    // tensor engine, fp16 kind: gxs is written straight as the hi|lo operand planes of the g_R product
+    // ([2][S*B][gxs_pitch] halves, scale from the bound launch_gxs_bound left in *gxs_scale) instead of as fp32
+    __half* gxs_planes;
+    size_t gxs_plane_elems;     // distance between the hi and the lo plane
+    int gxs_pitch;
+    const unsigned int* gxs_scale;
 };
 
 size_t row_smem_bytes(int L);
 int launch_row_forward(RowArgs a, cudaStream_t stream);
 int launch_row_backward(RowArgs a, cudaStream_t stream);
+// *out_bits = fp32 bits of an upper bound of max |gxs| over the whole batch (NaN for non-sanitised degenerate rows),
+// from the saved per-(row, sample) statistics and the upstream cotangents; gp_absmax: two slots holding max |g_indiv_prob|
+// and max |g_indiv_prob_label| as fp32 bits (zero when absent)
+int launch_gxs_bound(RowArgs a, const unsigned int* gp_absmax, unsigned int* out_bits, cudaStream_t stream);
 
 // CUDA-core contraction (contract_fma.cu)
 //   nt: C[M,N] = A[M,K] . B[N,K]^T

@@ -16,7 +16,7 @@ size_t tc_workspace_tn(int M, int N1, int N2);
 // reuse_planes != 0: skip the split pre-pass and use the operand planes a previous call left in `ws`
 // (lets a caller time the GEMM kernel alone)
 int tc_contract_nt(const float* A, const float* Bm, float* C, int M, int N, int K, void* ws, size_t ws_bytes,
-                   cudaStream_t stream, int reuse_planes = 0, int exact = 0);
+                   cudaStream_t stream, int reuse_planes = 0, int exact = 0, int ldc = 0);
 // C[N1,N2] = A[M,N1]^T . B[M,N2]
 int tc_contract_tn(const float* A, const float* Bm, float* C, int M, int N1, int N2, void* ws, size_t ws_bytes,
                    cudaStream_t stream, int reuse_planes = 0, int exact = 0);
@@ -37,8 +37,17 @@ int tc_philox_planes(void* planes, int S, int B, int Z, int B_global, int row0, 
 // Philox noise): two MMA passes instead of three.  Needs tc_exact_supported().
 bool tc_exact_supported();
 int tc_gemm_nt(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, const uint32_t* absmax_a,
-               const uint32_t* absmax_b, cudaStream_t stream, int ldc = 0, int a_exact = 0);   // ldc: pitch of C (0 = N)
+               const uint32_t* absmax_b, cudaStream_t stream, int ldc = 0, int a_exact = 0,   // ldc: pitch of C (0 = N)
+               void* tail_scratch = nullptr, size_t tail_scratch_bytes = 0);
+// tail_scratch (optional, tc_tail_scratch_bytes()): lets the kernel cut the tiles of the last, partial wave of its
+// persistent grid into K-slices so that the wave does not leave most SMs idle.
+size_t tc_tail_scratch_bytes();
+// fp16 operand kind (default): planes are halves with a per-tensor power-of-two scale (common.cuh); false = tf32 kind
+bool tc_f16_kind();
+int tc_pitch(int cols);                                      // plane row pitch (elements) for `cols` columns
+int tc_absmax(const float* src, size_t n, uint32_t* out_bits, cudaStream_t stream);   // atomicMax of |x| bits into *out
 int tc_gemm_tn(const void* a_planes, const void* b_planes, float* C, int M, int N1, int N2, const uint32_t* absmax_a,
-               const uint32_t* absmax_b, cudaStream_t stream, int b_exact = 0);
+               const uint32_t* absmax_b, cudaStream_t stream, int b_exact = 0, void* tail_scratch = nullptr,
+               size_t tail_scratch_bytes = 0);
 
 }  // namespace mpv

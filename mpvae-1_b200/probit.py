@@ -185,23 +185,25 @@ def philox_normal(S, B, Z, *, seed, offset=0, device="cuda", global_batch=None, 
     return out
 
 
-def contract_nt(a, b, engine=0, ws=None):
+def contract_nt(a, b, engine=0, ws=None, pitched=False):
     """C[M,N] = A[M,K] . B[N,K]^T through the library (the product of mpvae.py:168).  `ws` (a uint8 tensor from a
-    previous call, see `contract_workspace`) lets engine 3 reuse the operand planes engine 2 prepared."""
+    previous call, see `contract_workspace`) lets engine 3 reuse the operand planes engine 2 prepared.  `pitched`
+    stores C with rows padded to 16 bytes, as the loss kernels keep it, and returns the (M, N) view."""
     lib = _lib.lib()
     a, b = a.contiguous(), b.contiguous()
     M, K = a.shape
     N = b.shape[0]
     assert b.shape[1] == K and a.is_cuda and b.is_cuda and a.dtype == b.dtype == torch.float32
-    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    ldc = (N + 3) & ~3 if pitched else N
+    out = torch.empty((M, ldc), dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
         nbytes = int(lib.mpvae_contract_workspace_bytes(M, N, K, engine))
         if ws is None:
             ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
         stream = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
-        _lib.check(lib.mpvae_contract_nt(_ptr(a), _ptr(b), _ptr(out), M, N, K, engine, _ptr(ws), nbytes, stream),
-                   "mpvae_contract_nt")
-    return out
+        _lib.check(lib.mpvae_contract_nt_pitched(_ptr(a), _ptr(b), _ptr(out), M, N, K, ldc, engine, _ptr(ws), nbytes, stream),
+                   "mpvae_contract_nt_pitched")
+    return out[:, :N] if pitched else out
 
 
 def contract_workspace(M, N, K, device, engine=2):
