@@ -357,7 +357,8 @@ def run_b200(a):
         np.random.seed(4)
         torch.manual_seed(0)
         vae = M.VAE(margs).to(dev)
-        opt = torch.optim.Adam(vae.parameters(), lr=torch.tensor(1e-3, device=dev), weight_decay=1e-5, capturable=True)
+        from mpvae_b200.optim import FusedAdam
+        opt = FusedAdam(vae.parameters(), lr=torch.tensor(1e-3, device=dev), weight_decay=1e-5)
         sched = torch.optim.lr_scheduler.StepLR(opt, 1000, 0.5)
         stepper = DataParallelStep(vae, opt, sched, margs, clip_norm=100.0)
         rng = np.random.RandomState(5)
@@ -387,7 +388,8 @@ def run_b200(a):
                  "steps": k_train, "global_batch": Bg, "params": int(sum(p.numel() for p in vae.parameters())),
                  "loss": float(out_t.total_loss),
                  "what": "zero_grad, VAE fwd (torch/cuBLAS), probit ELBO fwd+bwd (this library), MLP bwd, "
-                         "grad all-reduce, clip_grad_norm_(100), Adam(wd=1e-5), StepLR; per-step host metrics excluded"}
+                         "grad all-reduce, clip_grad_norm_(100) + Adam(wd=1e-5) (this library: mpvae_b200.optim.FusedAdam), "
+                         "StepLR; per-step host metrics excluded"}
         try:   # the same step captured once as a CUDA graph and replayed (mpvae_b200.train.GraphedTrainStep)
             if world > 1:
                 raise NotImplementedError("graph capture is single-process only")

@@ -128,6 +128,22 @@ uint64_t mpvae_batch_metrics_workspace(int32_t B, int32_t L);
 int mpvae_batch_metrics(const float *indiv_prob, const float *input_label, int32_t B, int32_t L, float threshold,
                         double *out, void *workspace, uint64_t workspace_bytes, void *cuda_stream);
 
+/* The tail of the training step, train.py:126-128 (clip_grad_norm_(params, max_norm); optimizer.step() with
+ * torch.optim.Adam(lr, weight_decay)), over flat device buffers.
+ * mpvae_grad_norm: L2 norm of g[0..n) times grad_scale (1 / world size when g holds the all-reduced SUM), and the
+ *   per-step scalars the Adam kernel needs.  state (6 device doubles, persistent across steps):
+ *   [0] step count, incremented by this call  [1] the norm  [2] gradient multiplier = grad_scale * min(1, max_norm /
+ *   (norm + 1e-6)) (max_norm <= 0: no clipping)  [3] 1 - beta1^t  [4] sqrt(1 - beta2^t)  [5] learning rate
+ *   (*lr_dev when lr_dev != NULL, else lr).  workspace >= mpvae_grad_norm_workspace() bytes.
+ * mpvae_adam_step: one pass of torch.optim.Adam's update (L2 weight decay) over n elements; p, m, v are fp32 or fp64
+ *   (p_is_f64: the reference's r_sqrt_sigma is an fp64 Parameter), g is always fp32; shadow_f32 (optional) receives
+ *   the updated parameter as fp32. */
+uint64_t mpvae_grad_norm_workspace(void);
+int mpvae_grad_norm(const float *g, uint64_t n, double max_norm, double grad_scale, const float *lr_dev, double lr,
+                    double beta1, double beta2, double *state, void *workspace, uint64_t workspace_bytes, void *cuda_stream);
+int mpvae_adam_step(void *p, int32_t p_is_f64, const float *g, void *m, void *v, float *shadow_f32, uint64_t n,
+                    const double *state, double beta1, double beta2, double eps, double weight_decay, void *cuda_stream);
+
 const char *mpvae_last_error(void);
 int mpvae_abi_version(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches claim) */

@@ -20,7 +20,8 @@ FLAG_CONTRACT_FMA = 0x4
 # every symbol include/mpvae_b200.h declares
 EXPORTS = (
     "mpvae_workspace_bytes", "mpvae_probit_forward", "mpvae_probit_backward", "mpvae_philox_normal",
-    "mpvae_contract_nt", "mpvae_contract_nt_pitched", "mpvae_contract_tn", "mpvae_contract_workspace_bytes", "mpvae_last_error",
+    "mpvae_contract_nt", "mpvae_contract_nt_pitched", "mpvae_contract_tn", "mpvae_grad_norm_workspace",
+    "mpvae_grad_norm", "mpvae_adam_step", "mpvae_contract_workspace_bytes", "mpvae_last_error",
     "mpvae_abi_version", "mpvae_launch_count", "mpvae_batch_metrics", "mpvae_batch_metrics_workspace",
 )
 
@@ -82,6 +83,14 @@ def _load():
     for fn in (lib.mpvae_contract_nt, lib.mpvae_contract_tn):
         fn.restype = C.c_int
         fn.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.mpvae_grad_norm_workspace.restype = C.c_uint64
+    lib.mpvae_grad_norm_workspace.argtypes = []
+    lib.mpvae_grad_norm.restype = C.c_int
+    lib.mpvae_grad_norm.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_void_p, C.c_double, C.c_double,
+                                    C.c_double, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.mpvae_adam_step.restype = C.c_int
+    lib.mpvae_adam_step.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                    C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
     lib.mpvae_contract_nt_pitched.restype = C.c_int
     lib.mpvae_contract_nt_pitched.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 5 + [C.c_void_p, C.c_uint64, C.c_void_p]
     return lib

@@ -331,4 +331,20 @@ int mpvae_contract_tn(const float* A, const float* Bm, float* C, int32_t M, int3
     return launch_contract_tn_fma(A, Bm, C, M, N1, N2, workspace, workspace_bytes, stream);
 }
 
+uint64_t mpvae_grad_norm_workspace(void) { return grad_norm_workspace(); }
+
+int mpvae_grad_norm(const float* g, uint64_t n, double max_norm, double grad_scale, const float* lr_dev, double lr, double beta1,
+                    double beta2, double* state, void* workspace, uint64_t workspace_bytes, void* cuda_stream) {
+    if (!g || !state || !workspace || workspace_bytes < grad_norm_workspace()) { set_error("grad_norm: bad arguments"); return 1; }
+    return launch_grad_norm(g, (size_t)n, workspace, max_norm, grad_scale, lr_dev, lr, beta1, beta2, state,
+                            static_cast<cudaStream_t>(cuda_stream));
+}
+
+int mpvae_adam_step(void* p, int32_t p_is_f64, const float* g, void* m, void* v, float* shadow_f32, uint64_t n,
+                    const double* state, double beta1, double beta2, double eps, double weight_decay, void* cuda_stream) {
+    if (!p || !g || !m || !v || !state) { set_error("adam_step: NULL pointer"); return 1; }
+    return launch_adam(p, p_is_f64, g, m, v, shadow_f32, (size_t)n, state, beta1, beta2, eps, weight_decay,
+                       static_cast<cudaStream_t>(cuda_stream));
+}
+
 }  // extern "C"

@@ -61,6 +61,13 @@ int launch_contract_tn_fma(const float* A, const float* Bm, float* C, int M, int
 size_t batch_metrics_workspace(int B, int L);
 int launch_batch_metrics(const float* prob, const float* y, int B, int L, float thr, double* out, void* ws, cudaStream_t stream);
 
+// clip_grad_norm_ + Adam over flat buffers (optim.cu)
+size_t grad_norm_workspace();
+int launch_grad_norm(const float* g, size_t n, void* ws, double max_norm, double grad_scale, const float* lr_dev, double lr_host,
+                     double beta1, double beta2, double* state, cudaStream_t stream);
+int launch_adam(void* p, int p_is_f64, const float* g, void* m, void* v, float* shadow, size_t n, const double* state,
+                double beta1, double beta2, double eps, double weight_decay, cudaStream_t stream);
+
 // Philox noise (philox.cu)
 int launch_philox_normal(float* noise, int S, int B, int Z, int B_global, int row0, uint64_t seed, uint64_t offset,
                          const uint64_t* offset_dev, cudaStream_t stream);

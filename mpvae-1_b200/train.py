@@ -100,6 +100,7 @@ class DataParallelStep:
         others = [p for n, p in model.named_parameters() if p is not self.r_param]
         self.bucket = GradBucket(self.r_shadow, others)
         self._pending = []
+        self._shadow_fresh = False      # the fused optimizer wrote the fp32 shadow of R during the last step
         if self.world > 1 and self.r_shadow is not None:
             self.r_shadow.register_post_accumulate_grad_hook(self._reduce_r_early)
 
@@ -109,7 +110,7 @@ class DataParallelStep:
         seg = self.bucket.flat[:self.bucket.r_numel]
         self._pending.append(dist.all_reduce(seg, group=self.group, async_op=True))
 
-    def _finish_reduce(self):
+    def _finish_reduce(self, divide: bool = True):
         if self.world == 1:
             return
         start = self.bucket.r_numel if self._pending else 0
@@ -119,7 +120,8 @@ class DataParallelStep:
         for w in self._pending:
             w.wait()
         self._pending = []
-        self.bucket.flat.div_(self.world)
+        if divide:
+            self.bucket.flat.div_(self.world)
 
     # -- the step -------------------------------------------------------------------------------------------
     def step(self, input_label: torch.Tensor, input_feat: torch.Tensor, noise: Optional[torch.Tensor] = None,
@@ -134,7 +136,7 @@ class DataParallelStep:
         args.dp_global_batch, args.dp_row0 = n_rows, lo
         if getattr(args, "noise_offset_auto", True):
             args.noise_offset = self.step_no         # same Philox offset on every rank
-        if self.r_shadow is not None:
+        if self.r_shadow is not None and not self._shadow_fresh:
             with torch.no_grad():
                 self.r_shadow.copy_(self.r_param)
         self.bucket.attach(self.r_shadow)             # optimizer.zero_grad() of train.py:103 (in place, one memset)
@@ -152,18 +154,33 @@ class DataParallelStep:
         # every term is a mean over this rank's rows; weight by the shard size so unequal shards still average right
         weight = (hi - lo) * self.world / max(n_rows, 1)
         (total * weight if weight != 1.0 else total).backward()
-        self._finish_reduce()
-        if self.r_param is not None:
-            self.r_param.grad = self.bucket.r_view.double()
-        params = [p for p in self.model.parameters() if p.grad is not None]
-        grad_norm = nn.utils.clip_grad_norm_(params, self.clip_norm)
+        from .optim import FusedAdam
+        fused = isinstance(self.optimizer, FusedAdam) and not self.skip_nonfinite and total.is_cuda
+        self._finish_reduce(divide=not fused)
         stepped = True
-        if self.skip_nonfinite and not bool(torch.isfinite(grad_norm)):
-            stepped = False
-        if stepped:
-            self.optimizer.step()
+        self._shadow_fresh = False
+        if fused:
+            # clip + Adam as three launches over the flat bucket (optim.py); the 1/world of the gradient average is
+            # folded into the gradient multiplier, g_R is consumed as fp32, the fp32 shadow of R is refreshed in place
+            f32 = {self.r_param: self.bucket.r_view} if self.r_param is not None else None
+            shadows = {self.r_param: self.r_shadow} if self.r_param is not None else None
+            self.optimizer.step(max_norm=self.clip_norm, grad_scale=1.0 / self.world, flat_grad=self.bucket.flat,
+                                f32_grads=f32, f32_shadows=shadows)
+            grad_norm = self.optimizer.grad_norm
+            self._shadow_fresh = self.r_param is not None and self.r_param in self.optimizer.shadowed
             if self.scheduler is not None:
                 self.scheduler.step()
+        else:
+            if self.r_param is not None:
+                self.r_param.grad = self.bucket.r_view.double()
+            params = [p for p in self.model.parameters() if p.grad is not None]
+            grad_norm = nn.utils.clip_grad_norm_(params, self.clip_norm)
+            if self.skip_nonfinite and not bool(torch.isfinite(grad_norm)):
+                stepped = False
+            if stepped:
+                self.optimizer.step()
+                if self.scheduler is not None:
+                    self.scheduler.step()
         self.step_no += 1
         scal = [t.detach() for t in out[:6]]
         if self.world > 1:

@@ -158,3 +158,74 @@ def test_graphed_step_equals_eager_step():
     for (n, p), (_, q) in zip(vae_g.named_parameters(), vae_e.named_parameters()):
         assert torch.allclose(p.double(), q.double(), rtol=1e-3, atol=2e-5), n
     assert float(st_g.optimizer.param_groups[0]["lr"]) == pytest.approx(float(st_e.optimizer.param_groups[0]["lr"]))
+
+
+# ----------------------------------------------------------------------------- fused clip + Adam (optim.py)
+def test_fused_adam_matches_torch_adam():
+    """mpvae_grad_norm + mpvae_adam_step against clip_grad_norm_ + torch.optim.Adam (train.py:93,126-128) on a mixed
+    fp32 / fp64 parameter set, several steps, with and without the clip biting."""
+    from mpvae_b200.optim import FusedAdam
+    g = torch.Generator(device="cpu").manual_seed(5)
+    shapes = [(37, 11), (11,), (300, 129), (129,)]
+
+    def make():
+        ps = [torch.nn.Parameter(torch.randn(s, generator=g).to(DEV)) for s in shapes]
+        ps.append(torch.nn.Parameter((torch.randn(83, 83, generator=g).double() * 0.05).to(DEV)))   # r_sqrt_sigma-like
+        return ps
+
+    g.manual_seed(5); ref_p = make()
+    g.manual_seed(5); my_p = make()
+    ref = torch.optim.Adam(ref_p, lr=2e-3, weight_decay=1e-5)
+    mine = FusedAdam(my_p, lr=2e-3, weight_decay=1e-5)
+    for it, max_norm in enumerate((100.0, 0.5, 100.0, 0.05, 100.0)):
+        grads = [torch.randn(p.shape, generator=g).to(DEV) * (0.1 + it) for p in ref_p]
+        for p, q, gr in zip(ref_p, my_p, grads):
+            p.grad = gr.to(p.dtype).clone()
+            q.grad = gr.clone() if q.dtype == torch.float32 else None
+        norm_ref = torch.nn.utils.clip_grad_norm_(ref_p, max_norm)
+        ref.step()
+        mine.step(max_norm=max_norm, f32_grads={my_p[-1]: grads[-1]})
+        assert H.rel_err(mine.grad_norm.item(), norm_ref.item()) <= 1e-6
+        for p, q in zip(ref_p, my_p):
+            # fp64: torch carries the total norm in fp64 when an fp64 gradient takes part, the kernel reports it (and the
+            # clip coefficient) in fp32 -- a 6e-8 relative difference of the coefficient, 1e-10 of the parameter
+            tol = 2e-6 if p.dtype == torch.float32 else 1e-9
+            assert H.rel_err(q.detach().cpu().numpy(), p.detach().cpu().numpy()) <= tol, (it, p.shape)
+    sd = mine.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 5.0
+    for a, b in zip(ref.state_dict()["state"].values(), sd["state"].values()):
+        assert H.rel_err(b["exp_avg_sq"].cpu().numpy(), a["exp_avg_sq"].cpu().numpy()) <= 2e-6
+
+
+def test_fused_step_equals_torch_step():
+    """DataParallelStep with FusedAdam walks the same trajectory as with clip_grad_norm_ + torch.optim.Adam."""
+    from mpvae_b200.mpvae import VAE
+    from mpvae_b200.optim import FusedAdam
+    from mpvae_b200.train import DataParallelStep
+    x, y = yeast_data(512)
+
+    def build(fused):
+        args = yeast_args(keep_prob=0.0, noise_seed=77)
+        np.random.seed(4); torch.manual_seed(0)
+        vae = VAE(args).to(DEV)
+        with torch.no_grad():
+            for head in (vae.fe_logvar, vae.fx_logvar):
+                head.weight.zero_(); head.bias.fill_(-30.0)
+        cls = FusedAdam if fused else torch.optim.Adam
+        opt = cls(vae.parameters(), lr=1e-3, weight_decay=1e-5)
+        sched = torch.optim.lr_scheduler.StepLR(opt, 2, 0.5)
+        return vae, DataParallelStep(vae, opt, sched, args, clip_norm=1.0)     # a clip that bites
+
+    batches = [(y[i * 128:(i + 1) * 128], x[i * 128:(i + 1) * 128]) for i in range(4)]
+    vae_f, st_f = build(True)
+    vae_t, st_t = build(False)
+    for b in batches:
+        of, ot = st_f.step(*b), st_t.step(*b)
+        assert H.rel_err(float(of.total_loss), float(ot.total_loss)) <= 1e-5
+        assert H.rel_err(float(of.grad_norm), float(ot.grad_norm)) <= 1e-5
+    for (n, p), (_, q) in zip(vae_f.named_parameters(), vae_t.named_parameters()):
+        assert p.dtype == q.dtype
+        assert torch.allclose(p.double(), q.double(), rtol=1e-4, atol=2e-6), n
+    assert float(st_f.optimizer.param_groups[0]["lr"]) == pytest.approx(float(st_t.optimizer.param_groups[0]["lr"]))
+    # checkpoints keep the reference's layout: state_dict keys and dtypes unchanged by the flattening
+    assert {k: v.dtype for k, v in vae_f.state_dict().items()} == {k: v.dtype for k, v in vae_t.state_dict().items()}
