@@ -107,13 +107,34 @@ int mpvae_philox_normal(float *noise, int32_t S, int32_t B, int32_t Z, int32_t B
  * 3 = tcgen05 reusing the operand planes an engine-2 call left in the same workspace (GEMM kernel alone),
  * 4 = tcgen05 with the NOISE operand (A here, B of mpvae_contract_tn) promised to lie on the fp16 grid, as the
  * library's own Philox noise does: that operand is one piece and the product takes two MMA passes instead of three;
- * 5 = engine 4 reusing the planes of a previous engine-2/4 call. */
+ * 5 = engine 4 reusing the planes of a previous engine-2/4 call.
+ * MPVAE_ENGINE_KSPLIT or-ed into a tcgen05 engine code lets mpvae_contract_nt cut the tiles of a partial wave of its
+ * persistent grid into K slices (few output tiles, long K: the MLP layers).  The loss path never sets it: there the
+ * summation order of an output element must not depend on how many rows the call holds. */
+#define MPVAE_ENGINE_KSPLIT 0x100
 int mpvae_contract_nt(const float *A, const float *Bm, float *C, int32_t M, int32_t N, int32_t K, int32_t engine,
                       void *workspace, uint64_t workspace_bytes, void *cuda_stream);
 /* Same with a row pitch of ldc >= N floats for C.  The loss kernels keep noise.R^T in rows padded to 16 bytes
  * (ldc = N rounded up to 4) so that the GEMM epilogue can use 16-byte stores; this entry times exactly that variant. */
 int mpvae_contract_nt_pitched(const float *A, const float *Bm, float *C, int32_t M, int32_t N, int32_t K, int32_t ldc,
                               int32_t engine, void *workspace, uint64_t workspace_bytes, void *cuda_stream);
+
+/* The tcgen05 engine in stages, for callers that use an operand more than once (mpvae_b200/dense.py: a layer's input
+ * planes serve its forward and its weight gradient, the output-gradient planes both backward products):
+ *   mpvae_tc_split      fp32 [rows][cols] -> operand planes [hi|lo][rows][pitch] (mpvae_tc_planes_bytes) + the max |x|
+ *                       slot (4 bytes, device) that fixes the power-of-two scale of the fp16 pieces
+ *   mpvae_tc_gemm_nt    C[M,N] (pitch ldc) = A[M,K] . B[N,K]^T from planes;  ksplit != 0 allows K-sliced partial waves
+ *   mpvae_tc_gemm_tn    C[N1,N2] = A[M,N1]^T . B[M,N2] from planes
+ * tail_scratch: mpvae_tc_tail_scratch_bytes() of device memory (may be NULL: no K-slicing). */
+uint64_t mpvae_tc_planes_bytes(int32_t rows, int32_t cols);
+uint64_t mpvae_tc_tail_scratch_bytes(void);
+int mpvae_tc_split(const float *src, int32_t rows, int32_t cols, void *planes, uint32_t *absmax_slot, void *cuda_stream);
+int mpvae_tc_gemm_nt(const void *a_planes, const void *b_planes, float *C, int32_t M, int32_t N, int32_t K, int32_t ldc,
+                     const uint32_t *absmax_a, const uint32_t *absmax_b, int32_t ksplit, void *tail_scratch,
+                     uint64_t tail_scratch_bytes, void *cuda_stream);
+int mpvae_tc_gemm_tn(const void *a_planes, const void *b_planes, float *C, int32_t M, int32_t N1, int32_t N2,
+                     const uint32_t *absmax_a, const uint32_t *absmax_b, void *tail_scratch, uint64_t tail_scratch_bytes,
+                     void *cuda_stream);
 
 /* C[N1,N2] = A[M,N1]^T . B[M,N2] (fp32): g_R = gx^T . noise of SURVEY 8(a-12). Same engine codes. */
 int mpvae_contract_tn(const float *A, const float *Bm, float *C, int32_t M, int32_t N1, int32_t N2, int32_t engine,

@@ -21,7 +21,8 @@ FLAG_CONTRACT_FMA = 0x4
 EXPORTS = (
     "mpvae_workspace_bytes", "mpvae_probit_forward", "mpvae_probit_backward", "mpvae_philox_normal",
     "mpvae_contract_nt", "mpvae_contract_nt_pitched", "mpvae_contract_tn", "mpvae_grad_norm_workspace",
-    "mpvae_grad_norm", "mpvae_adam_step", "mpvae_contract_workspace_bytes", "mpvae_last_error",
+    "mpvae_grad_norm", "mpvae_adam_step", "mpvae_tc_planes_bytes", "mpvae_tc_tail_scratch_bytes", "mpvae_tc_split",
+    "mpvae_tc_gemm_nt", "mpvae_tc_gemm_tn", "mpvae_contract_workspace_bytes", "mpvae_last_error",
     "mpvae_abi_version", "mpvae_launch_count", "mpvae_batch_metrics", "mpvae_batch_metrics_workspace",
 )
 
@@ -83,6 +84,18 @@ def _load():
     for fn in (lib.mpvae_contract_nt, lib.mpvae_contract_tn):
         fn.restype = C.c_int
         fn.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.mpvae_tc_planes_bytes.restype = C.c_uint64
+    lib.mpvae_tc_planes_bytes.argtypes = [C.c_int32, C.c_int32]
+    lib.mpvae_tc_tail_scratch_bytes.restype = C.c_uint64
+    lib.mpvae_tc_tail_scratch_bytes.argtypes = []
+    lib.mpvae_tc_split.restype = C.c_int
+    lib.mpvae_tc_split.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mpvae_tc_gemm_nt.restype = C.c_int
+    lib.mpvae_tc_gemm_nt.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                                                         C.c_uint64, C.c_void_p]
+    lib.mpvae_tc_gemm_tn.restype = C.c_int
+    lib.mpvae_tc_gemm_tn.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                                                         C.c_void_p]
     lib.mpvae_grad_norm_workspace.restype = C.c_uint64
     lib.mpvae_grad_norm_workspace.argtypes = []
     lib.mpvae_grad_norm.restype = C.c_int

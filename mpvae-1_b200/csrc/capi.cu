@@ -292,6 +292,7 @@ int mpvae_batch_metrics(const float* indiv_prob, const float* input_label, int32
 uint64_t mpvae_contract_workspace_bytes(int32_t M, int32_t N, int32_t K, int32_t engine) {
     // covers both orientations: nt (M,N,K) and tn (M = reduction, N1 = N, N2 = K)
     size_t a = contract_tn_fma_workspace(M, N, K);
+    engine &= ~MPVAE_ENGINE_KSPLIT;
     if (engine != 1 && tc_available()) {
         size_t t1 = tc_workspace_nt(M, N, K), t2 = tc_workspace_tn(M, N, K);
         if (t1 > a) a = t1;
@@ -308,12 +309,15 @@ int mpvae_contract_nt(const float* A, const float* Bm, float* C, int32_t M, int3
 int mpvae_contract_nt_pitched(const float* A, const float* Bm, float* C, int32_t M, int32_t N, int32_t K, int32_t ldc,
                               int32_t engine, void* workspace, uint64_t workspace_bytes, void* cuda_stream) {
     if (!A || !Bm || !C || M <= 0 || N <= 0 || K <= 0 || ldc < N) { set_error("contract_nt: bad arguments"); return 1; }
+    const int ksplit = (engine & MPVAE_ENGINE_KSPLIT) ? 1 : 0;
+    engine &= ~MPVAE_ENGINE_KSPLIT;
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     if (engine == 0) engine = use_tensor(0, 1, M, N, K) ? 2 : 1;
     if (engine >= 2 && engine <= 5) {
         if (!tc_available()) { set_error("contract_nt: tensor engine not built"); return 7; }
         if (engine >= 4 && !tc_exact_supported()) { set_error("contract_nt: engines 4/5 need the CTA-pair kernel"); return 7; }
-        return tc_contract_nt(A, Bm, C, M, N, K, workspace, workspace_bytes, stream, engine == 3 || engine == 5, engine >= 4, ldc);
+        return tc_contract_nt(A, Bm, C, M, N, K, workspace, workspace_bytes, stream, engine == 3 || engine == 5, engine >= 4, ldc,
+                              ksplit);
     }
     return launch_contract_nt_fma(A, Bm, C, M, N, K, stream, ldc);
 }
@@ -329,6 +333,32 @@ int mpvae_contract_tn(const float* A, const float* Bm, float* C, int32_t M, int3
         return tc_contract_tn(A, Bm, C, M, N1, N2, workspace, workspace_bytes, stream, engine == 3 || engine == 5, engine >= 4);
     }
     return launch_contract_tn_fma(A, Bm, C, M, N1, N2, workspace, workspace_bytes, stream);
+}
+
+uint64_t mpvae_tc_planes_bytes(int32_t rows, int32_t cols) { return (rows > 0 && cols > 0) ? tc_planes_bytes(rows, cols) : 0; }
+uint64_t mpvae_tc_tail_scratch_bytes(void) { return tc_tail_scratch_bytes(); }
+
+int mpvae_tc_split(const float* src, int32_t rows, int32_t cols, void* planes, uint32_t* absmax_slot, void* cuda_stream) {
+    if (!src || !planes || !absmax_slot || rows <= 0 || cols < 8) { set_error("tc_split: bad arguments"); return 1; }
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    if (cudaMemsetAsync(absmax_slot, 0, sizeof(uint32_t), stream) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return 2; }
+    return tc_split(src, rows, cols, planes, absmax_slot, 1, stream);
+}
+
+int mpvae_tc_gemm_nt(const void* a_planes, const void* b_planes, float* C, int32_t M, int32_t N, int32_t K, int32_t ldc,
+                     const uint32_t* absmax_a, const uint32_t* absmax_b, int32_t ksplit, void* tail_scratch,
+                     uint64_t tail_scratch_bytes, void* cuda_stream) {
+    if (!a_planes || !b_planes || !C || M <= 0 || N <= 0 || K <= 0 || (ldc != 0 && ldc < N)) { set_error("tc_gemm_nt: bad arguments"); return 1; }
+    return tc_gemm_nt(a_planes, b_planes, C, M, N, K, absmax_a, absmax_b, static_cast<cudaStream_t>(cuda_stream), ldc, 0,
+                      ksplit ? tail_scratch : nullptr, ksplit ? (size_t)tail_scratch_bytes : 0);
+}
+
+int mpvae_tc_gemm_tn(const void* a_planes, const void* b_planes, float* C, int32_t M, int32_t N1, int32_t N2,
+                     const uint32_t* absmax_a, const uint32_t* absmax_b, void* tail_scratch, uint64_t tail_scratch_bytes,
+                     void* cuda_stream) {
+    if (!a_planes || !b_planes || !C || M <= 0 || N1 <= 0 || N2 <= 0) { set_error("tc_gemm_tn: bad arguments"); return 1; }
+    return tc_gemm_tn(a_planes, b_planes, C, M, N1, N2, absmax_a, absmax_b, static_cast<cudaStream_t>(cuda_stream), 0,
+                      tail_scratch, (size_t)tail_scratch_bytes);
 }
 
 uint64_t mpvae_grad_norm_workspace(void) { return grad_norm_workspace(); }

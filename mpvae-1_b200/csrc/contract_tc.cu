@@ -673,25 +673,27 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
 }
 
-// C += the K-slices 1 .. ksplit-1 of the tail tiles (see Item above), slice order fixed.  32 CTAs per tail tile,
-// each 8 rows of 256 columns.
+// C += the K-slices 1 .. ksplit-1 of the tail tiles (see Item above), slice order fixed.  64 CTAs per tail tile,
+// each 4 rows of 256 columns; the loads of a thread's four rows are independent of each other.
 __global__ void __launch_bounds__(256)
 tail_fixup_kernel(float* __restrict__ C, int Mc, int Nc, int ldc, int tiles_n, int full_tiles, int ksplit,
                   const float* __restrict__ partials) {
-    const int t = blockIdx.x >> 5, rows0 = (blockIdx.x & 31) * 8;
+    const int t = blockIdx.x >> 6, rows0 = (blockIdx.x & 63) * 4;
     const int st = full_tiles + t;
     const int m0 = (st / tiles_n) * 256, n0 = (st % tiles_n) * BN;
     const float* __restrict__ p = partials + (size_t)t * (ksplit - 1) * (256 * BN);
     const int c = threadIdx.x;                      // BN == 256 columns, one per thread
     if (n0 + c >= Nc) return;
+    float v[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = rows0 + i;
-        if (m0 + r >= Mc) break;
-        float v = C[(size_t)(m0 + r) * ldc + n0 + c];
-        for (int j = 0; j < ksplit - 1; ++j) v += p[(size_t)j * (256 * BN) + r * BN + c];
-        C[(size_t)(m0 + r) * ldc + n0 + c] = v;
+    for (int i = 0; i < 4; ++i) v[i] = (m0 + rows0 + i < Mc) ? C[(size_t)(m0 + rows0 + i) * ldc + n0 + c] : 0.0f;
+    for (int j = 0; j < ksplit - 1; ++j) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] += p[(size_t)j * (256 * BN) + (rows0 + i) * BN + c];
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (m0 + rows0 + i < Mc) C[(size_t)(m0 + rows0 + i) * ldc + n0 + c] = v[i];
 }
 
 // ------------------------------------------------------------------------------------------------ pre-passes
@@ -920,7 +922,7 @@ int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc
     if (int rc = check_launch("gemm_split_2sm_kernel")) return rc;
     if (ksplit > 1 && dbg == 0) {
         static_assert(BN == 256, "tail_fixup_kernel maps one thread to one tile column");
-        tail_fixup_kernel<<<(supers - full_tiles) * 32, 256, 0, stream>>>(C, Mc, Nc, ldc, tiles_n, full_tiles, ksplit, partials);
+        tail_fixup_kernel<<<(supers - full_tiles) * 64, 256, 0, stream>>>(C, Mc, Nc, ldc, tiles_n, full_tiles, ksplit, partials);
         return check_launch("tail_fixup_kernel");
     }
     return 0;
@@ -967,10 +969,10 @@ int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc, in
 
 bool tc_available() { return true; }
 
-// [absmax slots] [A planes] [B planes] [tail-wave scratch (tn only)]
+// [absmax slots] [A planes] [B planes] [tail-wave scratch]
 size_t tc_workspace_nt(int M, int N, int K) {
     const size_t kp = pitch_of(K);
-    return 256 + planes_bytes(M, kp) + planes_bytes(N, kp);
+    return 256 + planes_bytes(M, kp) + planes_bytes(N, kp) + tc_tail_scratch_bytes();
 }
 
 size_t tc_workspace_tn(int M, int N1, int N2) {
@@ -978,7 +980,7 @@ size_t tc_workspace_tn(int M, int N1, int N2) {
 }
 
 int tc_contract_nt(const float* A, const float* Bm, float* C, int M, int N, int K, void* ws, size_t ws_bytes,
-                   cudaStream_t stream, int reuse_planes, int exact, int ldc) {
+                   cudaStream_t stream, int reuse_planes, int exact, int ldc, int allow_ksplit) {
     if (!ws || ws_bytes < tc_workspace_nt(M, N, K)) { set_error("tc_contract_nt: workspace too small"); return 5; }
     if (ldc <= 0) ldc = N;
     const int ex = exact ? 1 : 0;
@@ -994,9 +996,12 @@ int tc_contract_nt(const float* A, const float* Bm, float* C, int M, int N, int 
     const int bk = f16 ? 64 : 32;
     if (int rc = make_map(&ma, s.a, f16, K, M, kp, bk, BM, CU_TENSOR_MAP_SWIZZLE_128B, ex ? 1 : 2)) return rc;
     if (int rc = make_map(&mb, s.b, f16, K, N, kp, bk, nt_b_box_rows(), CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    // no K-sliced tail wave for nt: each element's summation order stays a function of K alone (shard invariance)
-    if (f16) return launch_gemm<false, true>(ma, mb, C, M, N, K, ldc, s.absmax, s.absmax + 1, stream, ex);
-    return launch_gemm<false, false>(ma, mb, C, M, N, K, ldc, nullptr, nullptr, stream, ex);
+    // K-sliced partial waves only on request: without them each element's summation order is a function of K alone,
+    // which the loss path needs (a row's predictions must not depend on how many rows the call holds)
+    float* tail = allow_ksplit ? reinterpret_cast<float*>(s.b + planes_bytes(N, kp)) : nullptr;
+    const size_t tail_bytes = allow_ksplit ? tc_tail_scratch_bytes() : 0;
+    if (f16) return launch_gemm<false, true>(ma, mb, C, M, N, K, ldc, s.absmax, s.absmax + 1, stream, ex, tail, tail_bytes);
+    return launch_gemm<false, false>(ma, mb, C, M, N, K, ldc, nullptr, nullptr, stream, ex, tail, tail_bytes);
 }
 
 int tc_contract_tn(const float* A, const float* Bm, float* C, int M, int N1, int N2, void* ws, size_t ws_bytes,

@@ -47,9 +47,15 @@ grad_norm_kernel(const float* __restrict__ g, size_t n, double* __restrict__ par
 __global__ void grad_norm_finalize(const double* __restrict__ partials, int nparts, double max_norm, double grad_scale,
                                    const float* __restrict__ lr_dev, double lr_host, double beta1, double beta2,
                                    double* __restrict__ state) {
-    if (threadIdx.x != 0) return;
+    // one warp: lane l sums partials l, l+32, ... ; the 32 lane sums are then added in lane order (fixed order)
     double t = 0.0;
-    for (int i = 0; i < nparts; ++i) t += partials[i];
+    for (int i = threadIdx.x; i < nparts; i += 32) t += partials[i];
+    __shared__ double lanes[32];
+    lanes[threadIdx.x] = t;
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    t = 0.0;
+    for (int i = 0; i < 32; ++i) t += lanes[i];
     // the bucket holds the SUM over ranks; grad_scale = 1 / world turns it into the mean the reference clips
     const float norm = (float)(sqrt(t) * grad_scale);   // torch reports the norm in the gradients' dtype
     float coef = 1.0f;

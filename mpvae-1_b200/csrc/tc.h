@@ -16,7 +16,7 @@ size_t tc_workspace_tn(int M, int N1, int N2);
 // reuse_planes != 0: skip the split pre-pass and use the operand planes a previous call left in `ws`
 // (lets a caller time the GEMM kernel alone)
 int tc_contract_nt(const float* A, const float* Bm, float* C, int M, int N, int K, void* ws, size_t ws_bytes,
-                   cudaStream_t stream, int reuse_planes = 0, int exact = 0, int ldc = 0);
+                   cudaStream_t stream, int reuse_planes = 0, int exact = 0, int ldc = 0, int allow_ksplit = 0);
 // C[N1,N2] = A[M,N1]^T . B[M,N2]
 int tc_contract_tn(const float* A, const float* Bm, float* C, int M, int N1, int N2, void* ws, size_t ws_bytes,
                    cudaStream_t stream, int reuse_planes = 0, int exact = 0);

@@ -24,6 +24,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
+from .dense import linear
 from .probit import ProbitELBO, philox_normal
 
 _state = {"seed": 0x5EED_B200, "offset": 0}
@@ -70,13 +71,13 @@ class VAE(nn.Module):
     def label_encode(self, x):
         h = x
         for layer in (self.fe1, self.fe2):
-            h = self.dropout(F.relu(layer(h)))
+            h = self.dropout(F.relu(linear(layer, h)))
         return self._heads(h, self.fe_mu, self.fe_logvar)
 
     def feat_encode(self, x):
         h = x
         for layer in (self.fx1, self.fx2, self.fx3):
-            h = self.dropout(F.relu(layer(h)))
+            h = self.dropout(F.relu(linear(layer, h)))
         return self._heads(h, self.fx_mu, self.fx_logvar)
 
     # -- reparameterisation (mpvae.py:66-74) --
@@ -90,7 +91,7 @@ class VAE(nn.Module):
 
     # -- decoders (mpvae.py:76-84) --
     def _decode(self, z, head):
-        return head(F.relu(self.fd_x2(F.relu(self.fd_x1(z)))))
+        return linear(head, F.relu(linear(self.fd_x2, F.relu(linear(self.fd_x1, z)))))
 
     def label_decode(self, z):
         return self._decode(z, self.label_mp_mu)

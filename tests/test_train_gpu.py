@@ -229,3 +229,32 @@ def test_fused_step_equals_torch_step():
     assert float(st_f.optimizer.param_groups[0]["lr"]) == pytest.approx(float(st_t.optimizer.param_groups[0]["lr"]))
     # checkpoints keep the reference's layout: state_dict keys and dtypes unchanged by the flattening
     assert {k: v.dtype for k, v in vae_f.state_dict().items()} == {k: v.dtype for k, v in vae_t.state_dict().items()}
+
+
+# ----------------------------------------------------------------------------- MLP layers on the tensor engine (dense.py)
+@pytest.mark.parametrize("B,n_in,n_out,x_grad", [(1024, 5050, 256, True), (1024, 8993, 512, False), (1024, 512, 3993, True),
+                                                 (128, 1483, 983, True)])
+def test_tensor_linear_matches_fp64_linear(B, n_in, n_out, x_grad):
+    """The large nn.Linear layers of VAE.forward run on the split-precision tcgen05 product: forward, input gradient and
+    weight gradient must be as close to the exact (fp64) result as torch's fp32 SGEMM path is."""
+    from mpvae_b200.dense import linear, uses_tensor_engine
+    g = torch.Generator(device="cpu").manual_seed(B + n_in + n_out)
+    layer = torch.nn.Linear(n_in, n_out).to(DEV)
+    x = torch.randn(B, n_in, generator=g).to(DEV).requires_grad_(x_grad)
+    gy = (torch.randn(B, n_out, generator=g) * 1e-3).to(DEV)
+    assert uses_tensor_engine(layer, x)
+    y = linear(layer, x)
+    y.backward(gy)
+    got = {"y": y.detach(), "gw": layer.weight.grad.clone(), "gb": layer.bias.grad.clone(), "gx": x.grad.clone() if x_grad else None}
+    layer.zero_grad(); x.grad = None
+    y_t = layer(x)
+    y_t.backward(gy)
+    ref32 = {"y": y_t.detach(), "gw": layer.weight.grad.clone(), "gb": layer.bias.grad.clone(), "gx": x.grad.clone() if x_grad else None}
+    xd, wd, bd = x.detach().double(), layer.weight.detach().double(), layer.bias.detach().double()
+    truth = {"y": xd @ wd.T + bd, "gw": gy.double().T @ xd, "gb": gy.double().sum(0), "gx": gy.double() @ wd}
+    for k in ("y", "gw", "gb", "gx"):
+        if got[k] is None:
+            continue
+        err = H.rel_err(got[k].cpu().numpy(), truth[k].cpu().numpy())
+        err32 = H.rel_err(ref32[k].cpu().numpy(), truth[k].cpu().numpy())
+        assert err <= max(3e-6, 2 * err32), (k, err, err32)
