@@ -414,6 +414,23 @@ __device__ __forceinline__ void tc_mma_2sm(uint32_t d_tmem, uint64_t adesc, uint
 //   empty[s] then counts one tcgen05.commit per PAIR (multicast to all four CTAs): a stage is rewritten only
 //   after both pairs have consumed it, because either pair's producers write into both pairs' shared memory.
 // A cluster whose second tile falls outside the matrix runs it on zero-filled boxes and stores nothing.
+// One thread's 64 consecutive output columns.  Rows whose start is not 16-byte aligned (odd ldc: g_R, the 512 -> L
+// heads) get LEAD scalar stores up to the next 16-byte boundary, 15 vector stores, and the rest as scalars; every
+// register index is a compile-time constant.
+template <int LEAD>
+__device__ __forceinline__ void store_row64(float* __restrict__ dst, const float (&acc)[64], float k) {
+#pragma unroll
+    for (int j = 0; j < LEAD; ++j) dst[j] = acc[j] * k;
+    constexpr int NV = (LEAD == 0) ? 16 : 15;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const int j = LEAD + 4 * v;
+        *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j] * k, acc[j + 1] * k, acc[j + 2] * k, acc[j + 3] * k);
+    }
+#pragma unroll
+    for (int j = LEAD + 4 * NV; j < 64; ++j) dst[j] = acc[j] * k;
+}
+
 template <bool MN, bool F16, int EX, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -654,6 +671,15 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     for (int j = 0; j < 64; j += 4)
                         *reinterpret_cast<float4*>(crow + col0 + j) =
                             make_float4(acc[j] * inv_scale, acc[j + 1] * inv_scale, acc[j + 2] * inv_scale, acc[j + 3] * inv_scale);
+                } else if (col0 + 64 <= Nc) {
+                    // unaligned row: scalars up to the next 16-byte boundary, then vectors
+                    float* __restrict__ d = crow + col0;
+                    switch ((4 - (int)((reinterpret_cast<uintptr_t>(d) >> 2) & 3u)) & 3) {
+                        case 0: store_row64<0>(d, acc, inv_scale); break;
+                        case 1: store_row64<1>(d, acc, inv_scale); break;
+                        case 2: store_row64<2>(d, acc, inv_scale); break;
+                        default: store_row64<3>(d, acc, inv_scale); break;
+                    }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 64; ++j)
@@ -743,25 +769,39 @@ absmax_kernel(const float* __restrict__ src, size_t n, uint32_t* __restrict__ ou
         const uint32_t t = __shfl_xor_sync(0xffffffffu, m, o);
         m = t > m ? t : m;
     }
-    if ((threadIdx.x & 31) == 0 && m != 0) atomicMax(out, m);
+    // one atomic per CTA: thousands of atomics on one address serialise (10 us for a 5 MB tensor with one per warp)
+    __shared__ uint32_t s_m[8];
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = s_m[w] > m ? s_m[w] : m;
+        if (m != 0) atomicMax(out, m);
+    }
 }
 
-// hi = fp16(x * s), lo = fp16(x * s - hi) with s from the tensor's absmax; two elements per thread.
+// hi = fp16(x * s), lo = fp16(x * s - hi) with s from the tensor's absmax; four elements per thread.
 __global__ void __launch_bounds__(256)
 split_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int rows, int cols, int spitch, int dpitch,
                  size_t plane, const uint32_t* __restrict__ absmax) {
     const float s = absmax ? scale_from_absmax_bits(*absmax) : 1.0f;
-    const size_t n2 = (size_t)rows * dpitch / 2;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t e = 2 * i;
+    const size_t n4 = (size_t)rows * dpitch / 4;          // dpitch is a multiple of 64: groups of 4 never straddle rows
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = 4 * i;
         const int r = (int)(e / dpitch), c = (int)(e % dpitch);
-        float x0 = 0.0f, x1 = 0.0f;
-        if (c < cols) x0 = src[(size_t)r * spitch + c] * s;
-        if (c + 1 < cols) x1 = src[(size_t)r * spitch + c + 1] * s;
-        const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-        const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
-        reinterpret_cast<__half2*>(dst)[i] = __halves2half2(h0, h1);
-        reinterpret_cast<__half2*>(dst + plane)[i] = __halves2half2(l0, l1);
+        const float* __restrict__ sp = src + (size_t)r * spitch + c;
+        float x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = (c + j < cols) ? sp[j] * s : 0.0f;
+        __half h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { h[j] = __float2half_rn(x[j]); l[j] = __float2half_rn(x[j] - __half2float(h[j])); }
+        const __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
+        const __half2 l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+        lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(dst + e) = hv;
+        *reinterpret_cast<uint2*>(dst + plane + e) = lv;
     }
 }
 
@@ -843,7 +883,7 @@ int split_operand(const float* src, void* dst, int rows, int cols, int pitch, bo
         absmax_kernel<<<grid_for((size_t)rows * cols), 256, 0, stream>>>(src, (size_t)rows * cols, absmax);
         if (int rc = check_launch("absmax_kernel")) return rc;
     }
-    split_f16_kernel<<<grid_for(n / 2), 256, 0, stream>>>(src, static_cast<__half*>(dst), rows, cols, cols, pitch, n, absmax);
+    split_f16_kernel<<<grid_for(n / 4), 256, 0, stream>>>(src, static_cast<__half*>(dst), rows, cols, cols, pitch, n, absmax);
     return check_launch("split_f16_kernel");
 }
 
@@ -1043,7 +1083,7 @@ int tc_split(const float* src, int rows, int cols, void* planes, uint32_t* absma
         absmax_kernel<<<grid_for((size_t)rows * cols), 256, 0, stream>>>(src, (size_t)rows * cols, absmax);
         if (int rc = check_launch("absmax_kernel")) return rc;
     }
-    split_f16_kernel<<<grid_for(n / 2), 256, 0, stream>>>(src, static_cast<__half*>(planes), rows, cols, src_pitch, pitch, n, absmax);
+    split_f16_kernel<<<grid_for(n / 4), 256, 0, stream>>>(src, static_cast<__half*>(planes), rows, cols, src_pitch, pitch, n, absmax);
     return check_launch("split_f16_kernel");
 }
 
