@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-step", action="store_true", help="skip the full-training-step (steps/s) leg")
     ap.add_argument("--engine", default="auto", choices=["auto", "fma", "tensor"])
+    ap.add_argument("--exchange", default="nccl", choices=["peer", "nccl"],
+                    help="N>1: how g_R is summed over ranks (nccl = all-reduce after the backward; peer = inside the "
+                         "backward over NVLink peer memory, mpvae_b200.peer.PeerRing)")
     return ap.parse_args()
 
 
@@ -208,6 +211,13 @@ def run_b200(a):
     flush = torch.empty(2 * L2_BYTES // 4, dtype=torch.float32, device=dev)
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     step_no = [0]
+    # the path's one exchange: g_R summed over ranks.  Default: an NCCL all-reduce after the backward;
+    # --exchange peer = inside the backward over NVLink peer memory (mpvae_b200.peer.PeerRing)
+    ring = None
+    if world > 1 and not infer and a.exchange == "peer":
+        from mpvae_b200.peer import PeerRing
+        ring = PeerRing(L, Z, dev)
+        args.peer_ring = ring
 
     def one_step(src, from_host):
         args.noise_offset = step_no[0]
@@ -226,8 +236,9 @@ def run_b200(a):
                              leaves["fx_mu"], leaves["fx_logvar"], r32, args)
         out[0].backward()
         if world > 1:
-            dist.all_reduce(r32.grad)            # the path's one exchange step: NCCL sum over NVLink
-            r32.grad.div_(world)
+            if ring is None:
+                dist.all_reduce(r32.grad)        # the path's one exchange step: NCCL sum over NVLink
+            r32.grad.div_(world)                 # (with the peer ring the backward already returned the sum)
         if from_host:
             loss_host.copy_(out[0].detach(), non_blocking=True)
         for k in row_keys:
@@ -416,7 +427,9 @@ def run_b200(a):
                    "S": S, "B_per_gpu": B, "B_global": Bg,
                    "L": L, "Z": Z, "D": 50, "noise": "philox (on device, inside the step)", "engine": a.engine,
                    "l2": "L2 flushed between timed iterations (252 MB written); per-step CUDA events summed",
-                   "exchange": "NCCL all-reduce of g_R (fp32) per step" if world > 1 else "none (1 GPU)"},
+                   "exchange": ("none (1 GPU)" if world == 1 else
+                                "g_R summed over NVLink peer memory inside the backward (chunk owners pull, add in rank "
+                                "order, store to every rank)" if ring is not None else "NCCL all-reduce of g_R (fp32) per step")},
         "clocks": clocks,
         "e2e": {"value": units / (total_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": bi, "d2h_bytes_per_step": 4,
                 "how": "mpvae_b200.compute_loss + backward from pinned host buffers; H2D double-buffered on a side stream",

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPVAE_ABI_VERSION 7
+#define MPVAE_ABI_VERSION 8
 
 /* flags */
 #define MPVAE_FLAG_SANITIZE_DEGENERATE 0x1u /* rows with n_pos*n_neg == 0 get zero ranking gradient instead of
@@ -84,7 +84,32 @@ typedef struct mpvae_probit_params {
     int32_t noise_b_global, noise_row0;
     const uint64_t *noise_offset_dev; /* optional DEVICE counter added to noise_offset inside the kernel, so that a
                                          captured CUDA graph draws fresh noise on every replay; NULL = unused */
+
+    /* ---- data-parallel g_R over NVLink peer memory (optional; peer_world <= 1: off).
+       One process per GPU on one node: each rank allocates a partial buffer and a g_R buffer (L*Z floats each) and a
+       flag block (mpvae_peer_flag_bytes) with mpvae_peer_alloc, exchanges the IPC handles and opens the others' with
+       mpvae_peer_open.  With the tables filled in, mpvae_probit_backward leaves in g_r (which must be
+       peer_g_r[peer_rank]) the SUM of g_R over all ranks, bit-identical on every rank: each rank's product goes to its
+       own partial buffer, g_R is cut into peer_world chunks, a chunk's owner pulls it from every rank over NVLink, adds
+       in rank order and stores the result to every rank (csrc/peer_reduce.cu).  peer_step must increase by one per
+       call, the same number on every rank, starting at 1. ---- */
+    int32_t peer_world, peer_rank;
+    uint32_t peer_step, peer_reserved;
+    void *peer_part[8];
+    void *peer_g_r[8];
+    void *peer_flags[8];
 } mpvae_probit_params;
+
+/* Peer-memory plumbing for the fields above (CUDA IPC; same node).  handle = 64 opaque bytes + the offset word. */
+uint64_t mpvae_peer_flag_bytes(void);
+/* The same exchange stand-alone: g_r[r][0..n) = sum over ranks s of part[s][0..n), on every rank r (tables of `world`
+ * device pointers, this process being `rank`; `step` as peer_step above, shared with the backward's counter). */
+int mpvae_peer_allreduce(void *const *part, void *const *g_r, void *const *flags, int32_t world, int32_t rank,
+                         uint32_t step, uint64_t n, void *cuda_stream);
+int mpvae_peer_alloc(uint64_t bytes, void **ptr, unsigned char handle[64]);
+int mpvae_peer_open(const unsigned char handle[64], void **ptr);
+int mpvae_peer_close(void *ptr);
+int mpvae_peer_free(void *ptr);
 
 /* Bytes of scratch for one forward(+backward) call.  want_backward=0 sizes the inference path. */
 uint64_t mpvae_workspace_bytes(int32_t S, int32_t B, int32_t L, int32_t Z, int32_t want_backward, uint32_t flags);

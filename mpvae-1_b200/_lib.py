@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmpvae_b200.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 FLAG_SANITIZE_DEGENERATE = 0x1
 FLAG_CONTRACT_TENSOR = 0x2
 FLAG_CONTRACT_FMA = 0x4
@@ -22,7 +22,8 @@ EXPORTS = (
     "mpvae_workspace_bytes", "mpvae_probit_forward", "mpvae_probit_backward", "mpvae_philox_normal",
     "mpvae_contract_nt", "mpvae_contract_nt_pitched", "mpvae_contract_tn", "mpvae_grad_norm_workspace",
     "mpvae_grad_norm", "mpvae_adam_step", "mpvae_tc_planes_bytes", "mpvae_tc_tail_scratch_bytes", "mpvae_tc_split",
-    "mpvae_tc_gemm_nt", "mpvae_tc_gemm_tn", "mpvae_contract_workspace_bytes", "mpvae_last_error",
+    "mpvae_tc_gemm_nt", "mpvae_tc_gemm_tn", "mpvae_peer_flag_bytes", "mpvae_peer_allreduce",
+    "mpvae_peer_alloc", "mpvae_peer_open", "mpvae_peer_close", "mpvae_peer_free", "mpvae_contract_workspace_bytes", "mpvae_last_error",
     "mpvae_abi_version", "mpvae_launch_count", "mpvae_batch_metrics", "mpvae_batch_metrics_workspace",
 )
 
@@ -45,6 +46,8 @@ class ProbitParams(C.Structure):
         ("noise_seed", C.c_uint64), ("noise_offset", C.c_uint64),
         ("noise_b_global", C.c_int32), ("noise_row0", C.c_int32),
         ("noise_offset_dev", _f),
+        ("peer_world", C.c_int32), ("peer_rank", C.c_int32), ("peer_step", C.c_uint32), ("peer_reserved", C.c_uint32),
+        ("peer_part", _f * 8), ("peer_g_r", _f * 8), ("peer_flags", _f * 8),
     ]
 
 
@@ -84,6 +87,19 @@ def _load():
     for fn in (lib.mpvae_contract_nt, lib.mpvae_contract_tn):
         fn.restype = C.c_int
         fn.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.mpvae_peer_allreduce.restype = C.c_int
+    lib.mpvae_peer_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint32, C.c_uint64,
+                                         C.c_void_p]
+    lib.mpvae_peer_flag_bytes.restype = C.c_uint64
+    lib.mpvae_peer_flag_bytes.argtypes = []
+    lib.mpvae_peer_alloc.restype = C.c_int
+    lib.mpvae_peer_alloc.argtypes = [C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p]
+    lib.mpvae_peer_open.restype = C.c_int
+    lib.mpvae_peer_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.mpvae_peer_close.restype = C.c_int
+    lib.mpvae_peer_close.argtypes = [C.c_void_p]
+    lib.mpvae_peer_free.restype = C.c_int
+    lib.mpvae_peer_free.argtypes = [C.c_void_p]
     lib.mpvae_tc_planes_bytes.restype = C.c_uint64
     lib.mpvae_tc_planes_bytes.argtypes = [C.c_int32, C.c_int32]
     lib.mpvae_tc_tail_scratch_bytes.restype = C.c_uint64

@@ -1,6 +1,7 @@
 // extern "C" surface of libmpvae_b200 (include/mpvae_b200.h): argument validation, workspace carving and the
 // launch sequence of one forward / backward of the probit ELBO.
 #include <atomic>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/mpvae_b200.h"
@@ -250,6 +251,26 @@ int mpvae_probit_backward(const mpvae_probit_params* p, void* cuda_stream) {
     }
     if (int rc = launch_row_backward(a, stream)) return rc;
     if (!p->g_r) return 0;
+    // data-parallel: the product writes this rank's partial into its own `part` buffer, peer_reduce.cu sums the world's
+    // partials over NVLink and leaves the result in every rank's g_r
+    const bool peer = p->peer_world > 1;
+    PeerCtx pctx{};
+    float* g_r_out = p->g_r;
+    if (peer) {
+        if (p->peer_world > 8 || p->peer_rank < 0 || p->peer_rank >= p->peer_world || p->peer_step == 0 ||
+            p->g_r != p->peer_g_r[p->peer_rank]) {
+            set_error("peer tables: world %d rank %d step %u (g_r must be peer_g_r[rank])", p->peer_world, p->peer_rank, p->peer_step);
+            return 1;
+        }
+        pctx.world = p->peer_world; pctx.rank = p->peer_rank; pctx.step = p->peer_step;
+        for (int i = 0; i < p->peer_world; ++i) {
+            pctx.part[i] = static_cast<float*>(p->peer_part[i]);
+            pctx.g_r[i] = static_cast<float*>(p->peer_g_r[i]);
+            pctx.flags[i] = static_cast<uint32_t*>(p->peer_flags[i]);
+            if (!pctx.part[i] || !pctx.g_r[i] || !pctx.flags[i]) { set_error("peer tables: NULL entry for rank %d", i); return 1; }
+        }
+        g_r_out = pctx.part[p->peer_rank];
+    }
     if (tensor) {
         void* gpl = base + w.gxs_planes;
         void* tail = direct ? static_cast<void*>(base + w.tn_tail) : static_cast<void*>(a.gxs);
@@ -259,12 +280,14 @@ int mpvae_probit_backward(const mpvae_probit_params* p, void* cuda_stream) {
         }
         // the noise planes the forward left in the workspace are the MN-major B operand as they are; the fp32 gxs
         // cube (when there is one) is dead once it has been split: scratch for the K-sliced tail wave
-        return tc_gemm_tn(gpl, base + w.noise_planes, p->g_r, M, p->L, p->Z, slots + SLOT_ABSMAX_GXS, nullptr, stream,
-                          (!p->noise && tc_exact_supported()) ? 1 : 0, tail, tail_bytes);
+        if (int rc = tc_gemm_tn(gpl, base + w.noise_planes, g_r_out, M, p->L, p->Z, slots + SLOT_ABSMAX_GXS, nullptr, stream,
+                                (!p->noise && tc_exact_supported()) ? 1 : 0, tail, tail_bytes)) return rc;
+        return peer ? launch_peer_reduce(pctx, (size_t)p->L * p->Z, stream) : 0;
     }
     const float* nz = p->noise ? p->noise : reinterpret_cast<const float*>(base + w.noise_f32);
-    return launch_contract_tn_fma(a.gxs, nz, p->g_r, M, p->L, p->Z, base + w.fma_partials, w.total - w.fma_partials, stream,
-                                  row_pitch(p->L));
+    if (int rc = launch_contract_tn_fma(a.gxs, nz, g_r_out, M, p->L, p->Z, base + w.fma_partials, w.total - w.fma_partials, stream,
+                                        row_pitch(p->L))) return rc;
+    return peer ? launch_peer_reduce(pctx, (size_t)p->L * p->Z, stream) : 0;
 }
 
 int mpvae_philox_normal(float* noise, int32_t S, int32_t B, int32_t Z, int32_t B_global, int32_t row0, uint64_t seed,
@@ -333,6 +356,57 @@ int mpvae_contract_tn(const float* A, const float* Bm, float* C, int32_t M, int3
         return tc_contract_tn(A, Bm, C, M, N1, N2, workspace, workspace_bytes, stream, engine == 3 || engine == 5, engine >= 4);
     }
     return launch_contract_tn_fma(A, Bm, C, M, N1, N2, workspace, workspace_bytes, stream);
+}
+
+// ---- peer memory (CUDA IPC).  The 64-byte handle is cudaIpcMemHandle_t; allocations are made with cudaMalloc so that
+// the handle addresses exactly the buffer (no sub-allocation offsets). ----
+uint64_t mpvae_peer_flag_bytes(void) { return peer_flag_bytes(); }
+
+int mpvae_peer_allreduce(void* const* part, void* const* g_r, void* const* flags, int32_t world, int32_t rank, uint32_t step,
+                         uint64_t n, void* cuda_stream) {
+    if (!part || !g_r || !flags || world < 2 || world > 8 || rank < 0 || rank >= world || step == 0 || n == 0) {
+        set_error("peer_allreduce: bad arguments");
+        return 1;
+    }
+    PeerCtx ctx{};
+    ctx.world = world; ctx.rank = rank; ctx.step = step;
+    for (int i = 0; i < world; ++i) {
+        ctx.part[i] = static_cast<float*>(part[i]);
+        ctx.g_r[i] = static_cast<float*>(g_r[i]);
+        ctx.flags[i] = static_cast<uint32_t*>(flags[i]);
+        if (!ctx.part[i] || !ctx.g_r[i] || !ctx.flags[i]) { set_error("peer_allreduce: NULL table entry %d", i); return 1; }
+    }
+    return launch_peer_reduce(ctx, (size_t)n, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int mpvae_peer_alloc(uint64_t bytes, void** ptr, unsigned char handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    if (!ptr || !handle || bytes == 0) { set_error("peer_alloc: bad arguments"); return 1; }
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e != cudaSuccess) { set_error("peer_alloc: cudaMalloc(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e)); return 2; }
+    e = cudaMemset(*ptr, 0, bytes);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle), *ptr);
+    if (e != cudaSuccess) { set_error("peer_alloc: %s", cudaGetErrorString(e)); cudaFree(*ptr); *ptr = nullptr; return 2; }
+    return 0;
+}
+
+int mpvae_peer_open(const unsigned char handle[64], void** ptr) {
+    if (!ptr || !handle) { set_error("peer_open: bad arguments"); return 1; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    const cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { set_error("peer_open: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); return 2; }
+    return 0;
+}
+
+int mpvae_peer_close(void* ptr) {
+    if (ptr && cudaIpcCloseMemHandle(ptr) != cudaSuccess) { set_error("peer_close failed"); return 2; }
+    return 0;
+}
+
+int mpvae_peer_free(void* ptr) {
+    if (ptr && cudaFree(ptr) != cudaSuccess) { set_error("peer_free failed"); return 2; }
+    return 0;
 }
 
 uint64_t mpvae_tc_planes_bytes(int32_t rows, int32_t cols) { return (rows > 0 && cols > 0) ? tc_planes_bytes(rows, cols) : 0; }

@@ -1,0 +1,153 @@
+// Data-parallel sum of g_R over NVLink peer memory, one process per GPU on one node.  Every rank maps the
+// others' buffers with CUDA IPC (mpvae_peer_alloc / mpvae_peer_open) and passes the tables in mpvae_probit_params.
+//
+//   product       each rank's gxs^T . noise writes its partial g_R into its OWN `part` buffer (ordinary local stores)
+//   signal(0)     "my partial is complete": release-store of the step number into every rank's flag row 0
+//   reduce+bcast  g_R is cut into `world` contiguous chunks; the owner of a chunk waits for the world's flags, PULLS the
+//                 chunk from every rank's `part` (coalesced 16-byte NVLink loads), adds the partials in rank order (fixed
+//                 order: every rank ends up with bit-identical sums, run to run) and stores the result into EVERY rank's
+//                 g_R (coalesced 16-byte NVLink stores); the last CTA release-stores the step number into row 1
+//   wait(1)       returns when all owners have delivered: g_R is complete on this rank
+//
+// Per rank and step (G ranks, n = L*Z floats): 4n(G-1)/G bytes in and the same out, at once (NVLink is full duplex),
+// against 2 x 4n(G-1)/G each way in sequence for a ring all-reduce.
+//
+// A first version pushed the tiles from the product's epilogue straight into their owners' memory to overlap the
+// transfer with the GEMM; measured on 2 x B200 that was slower than NCCL: a thread of the epilogue holds one ROW, so
+// its 16-byte stores are 1 KiB apart and every one became its own NVLink packet (+0.17 ms on the 0.47 ms product).
+//
+// Buffers are reused every step; the step number in the flags orders the reuse: a rank starts its next product (which
+// overwrites `part`) only after wait(1), i.e. after every owner has finished pulling.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "rows.h"
+
+namespace mpv {
+namespace {
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *p == want; a peer that never arrives must not hang the GPU for ever
+__device__ __forceinline__ void wait_flag(const uint32_t* p, uint32_t want) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(p) != want) {
+        __nanosleep(100);
+        if (clock64() - t0 > 20000000000LL) __trap();   // ~10 s
+    }
+}
+
+// flags of one rank: [2 phases][8 source ranks] + [16] = CTA counter of the reduce kernel
+constexpr int kFlagWords = 32;
+constexpr int kReduceCtas = kNumSMs * 4;
+
+__global__ void peer_signal_kernel(PeerCtx ctx, int phase) {
+    const int p = threadIdx.x;
+    __threadfence_system();
+    if (p < ctx.world) st_release_sys(ctx.flags[p] + phase * 8 + ctx.rank, ctx.step);
+}
+
+__global__ void peer_wait_kernel(PeerCtx ctx, int phase) {
+    const int p = threadIdx.x;
+    if (p < ctx.world) wait_flag(ctx.flags[ctx.rank] + phase * 8 + p, ctx.step);
+}
+
+template <int W, int U>   // world size; float4 groups per thread and iteration (all loads are issued before the adds)
+__global__ void __launch_bounds__(256)
+peer_reduce_bcast_kernel(PeerCtx ctx, size_t n) {
+    if (threadIdx.x < W) wait_flag(ctx.flags[ctx.rank] + threadIdx.x, ctx.step);
+    __syncthreads();
+    // this rank's chunk, in units of float4 (the buffers come from cudaMalloc: 256-byte aligned)
+    const size_t n4 = (n + 3) / 4, per = (n4 + W - 1) / W;
+    const size_t lo = (size_t)ctx.rank * per, hi = min(n4, lo + per);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < hi; i0 += stride * U) {
+        if (i0 + (U - 1) * stride < hi && 4 * (i0 + (U - 1) * stride) + 4 <= n) {
+            float4 v[U][W];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int s = 0; s < W; ++s) v[u][s] = reinterpret_cast<const float4*>(ctx.part[s])[i0 + u * stride];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float4 a = v[u][0];
+#pragma unroll
+                for (int s = 1; s < W; ++s) { a.x += v[u][s].x; a.y += v[u][s].y; a.z += v[u][s].z; a.w += v[u][s].w; }
+#pragma unroll
+                for (int p = 0; p < W; ++p) reinterpret_cast<float4*>(ctx.g_r[p])[i0 + u * stride] = a;
+            }
+            continue;
+        }
+        for (int u = 0; u < U; ++u) {
+            const size_t i = i0 + u * stride;
+            if (i >= hi) break;
+            if (4 * i + 4 <= n) {
+                float4 a = reinterpret_cast<const float4*>(ctx.part[0])[i];
+                for (int s = 1; s < W; ++s) {
+                    const float4 t = reinterpret_cast<const float4*>(ctx.part[s])[i];
+                    a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+                }
+                for (int p = 0; p < W; ++p) reinterpret_cast<float4*>(ctx.g_r[p])[i] = a;
+                continue;
+            }
+            for (size_t e = 4 * i; e < n; ++e) {       // the last, partial float4 of the array
+                float a = 0.0f;
+                for (int s = 0; s < W; ++s) a += ctx.part[s][e];
+                for (int p = 0; p < W; ++p) ctx.g_r[p][e] = a;
+            }
+        }
+    }
+    // the last CTA tells every rank that this owner's chunk is delivered
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        uint32_t* counter = ctx.flags[ctx.rank] + 16;
+        last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+        if (last) *counter = 0;
+    }
+    __syncthreads();
+    if (last && threadIdx.x < W) {
+        __threadfence_system();
+        st_release_sys(ctx.flags[threadIdx.x] + 8 + ctx.rank, ctx.step);
+    }
+}
+
+}  // namespace
+
+size_t peer_flag_bytes() { return kFlagWords * sizeof(uint32_t); }
+
+template <int W>
+void launch_reduce_w(const PeerCtx& ctx, size_t n, int ctas, int unroll, cudaStream_t stream) {
+    if (unroll >= 4 && W <= 4) peer_reduce_bcast_kernel<W, 4><<<ctas, 256, 0, stream>>>(ctx, n);
+    else if (unroll >= 2) peer_reduce_bcast_kernel<W, 2><<<ctas, 256, 0, stream>>>(ctx, n);
+    else peer_reduce_bcast_kernel<W, 1><<<ctas, 256, 0, stream>>>(ctx, n);
+}
+
+int launch_peer_reduce(const PeerCtx& ctx, size_t n, cudaStream_t stream) {
+    static const int ctas = getenv("MPVAE_PEER_CTAS") ? atoi(getenv("MPVAE_PEER_CTAS")) : kReduceCtas;
+    static const int unroll = getenv("MPVAE_PEER_UNROLL") ? atoi(getenv("MPVAE_PEER_UNROLL")) : 2;
+    peer_signal_kernel<<<1, 32, 0, stream>>>(ctx, 0);
+    if (int rc = check_launch("peer_signal_kernel")) return rc;
+    switch (ctx.world) {
+        case 2: launch_reduce_w<2>(ctx, n, ctas, unroll, stream); break;
+        case 3: launch_reduce_w<3>(ctx, n, ctas, unroll, stream); break;
+        case 4: launch_reduce_w<4>(ctx, n, ctas, unroll, stream); break;
+        case 5: launch_reduce_w<5>(ctx, n, ctas, unroll, stream); break;
+        case 6: launch_reduce_w<6>(ctx, n, ctas, unroll, stream); break;
+        case 7: launch_reduce_w<7>(ctx, n, ctas, unroll, stream); break;
+        case 8: launch_reduce_w<8>(ctx, n, ctas, unroll, stream); break;
+        default: set_error("peer reduce: world size %d not in [2, 8]", ctx.world); return 1;
+    }
+    if (int rc = check_launch("peer_reduce_bcast_kernel")) return rc;
+    peer_wait_kernel<<<1, 32, 0, stream>>>(ctx, 1);
+    return check_launch("peer_wait_kernel");
+}
+
+}  // namespace mpv

@@ -61,6 +61,17 @@ int launch_contract_tn_fma(const float* A, const float* Bm, float* C, int M, int
 size_t batch_metrics_workspace(int B, int L);
 int launch_batch_metrics(const float* prob, const float* y, int B, int L, float thr, double* out, void* ws, cudaStream_t stream);
 
+// g_R summed over ranks through peer memory (peer_reduce.cu)
+struct PeerCtx {
+    int world, rank;
+    uint32_t step;
+    float* part[8];     // every rank's partial g_R (the rank's own product output)
+    float* g_r[8];      // every rank's final g_R
+    uint32_t* flags[8];
+};
+size_t peer_flag_bytes();
+int launch_peer_reduce(const PeerCtx& ctx, size_t n, cudaStream_t stream);
+
 // clip_grad_norm_ + Adam over flat buffers (optim.cu)
 size_t grad_norm_workspace();
 int launch_grad_norm(const float* g, size_t n, void* ws, double max_norm, double grad_scale, const float* lr_dev, double lr_host,

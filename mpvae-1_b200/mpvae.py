@@ -165,8 +165,9 @@ def compute_loss(input_label, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar
     r32 = r_sqrt_sigma.to(device).float()                # mpvae.py:165 -- outside the Function: grad returns as fp64
     noise, spec = noise_plan(args, n_sample, n_batch, device, noise)
     flags = int(getattr(args, "mpvae_flags", 0))
+    # args.peer_ring (peer.PeerRing, data-parallel runs): g_R comes back already summed over the ranks
     return ProbitELBO.apply(input_label.float(), fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise,
-                            float(args.nll_coeff), float(args.c_coeff), flags, spec)
+                            float(args.nll_coeff), float(args.c_coeff), flags, spec, getattr(args, "peer_ring", None))
 
 
 probit_elbo = compute_loss

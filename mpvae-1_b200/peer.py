@@ -1,0 +1,106 @@
+"""Peer-memory plumbing of the data-parallel g_R sum (csrc/peer_reduce.cu): one process per GPU on one node; every rank
+allocates a partial buffer, a g_R buffer and a flag block through the library (cudaMalloc + CUDA IPC), exchanges the
+handles over the torch.distributed group and maps the others'.  `PeerRing.fill(params)` then puts the tables into
+`mpvae_probit_params`, and `mpvae_probit_backward` leaves the SUM of g_R over all ranks in `ring.g_r`: every rank owns
+a chunk of g_R, pulls it from all ranks over NVLink, adds in rank order and stores the result to all ranks -- one
+kernel inside the backward instead of an NCCL all-reduce after it.
+
+torch.distributed is used for exactly one thing here: `all_gather_object` of the 64-byte handles at construction.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+class _DevMem:
+    """A cudaMalloc'ed buffer of the library exposed to torch without a copy (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"data": (ptr, False), "shape": shape, "typestr": typestr, "version": 3,
+                                         "strides": None}
+
+
+class PeerRing:
+    MAX_WORLD = 8
+
+    def __init__(self, L: int, Z: int, device, group=None):
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerRing needs an initialised torch.distributed process group")
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if not 2 <= self.world <= self.MAX_WORLD:
+            raise ValueError(f"PeerRing: world size {self.world} not in [2, {self.MAX_WORLD}]")
+        lib = _lib.lib()
+        self.L, self.Z = int(L), int(Z)
+        self.device = torch.device(device)
+        sizes = {"part": self.L * self.Z * 4, "g_r": self.L * self.Z * 4, "flags": int(lib.mpvae_peer_flag_bytes())}
+        self._local, self._remote, handles = {}, {}, {}
+        with torch.cuda.device(self.device):
+            for name, nbytes in sizes.items():
+                ptr, h = C.c_void_p(), C.create_string_buffer(64)
+                _lib.check(lib.mpvae_peer_alloc(nbytes, C.byref(ptr), h), "mpvae_peer_alloc")
+                self._local[name] = ptr.value
+                handles[name] = h.raw
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, handles, group=group)
+            self.ptrs = {name: [0] * self.world for name in sizes}
+            for r, hs in enumerate(gathered):
+                for name in sizes:
+                    if r == self.rank:
+                        self.ptrs[name][r] = self._local[name]
+                        continue
+                    ptr = C.c_void_p()
+                    _lib.check(lib.mpvae_peer_open(hs[name], C.byref(ptr)), "mpvae_peer_open")
+                    self.ptrs[name][r] = ptr.value
+                    self._remote.setdefault(name, []).append(ptr.value)
+            self.g_r = torch.as_tensor(_DevMem(self._local["g_r"], (self.L, self.Z), "<f4"), device=self.device)
+            self.part = torch.as_tensor(_DevMem(self._local["part"], (self.L, self.Z), "<f4"), device=self.device)
+        self.step = 0
+        dist.barrier(group=group)          # everybody has mapped everybody before the first kernel touches a peer
+
+    def applies(self, S: int, B: int, L: int, Z: int, flags: int) -> bool:
+        return (L, Z) == (self.L, self.Z) and B > 0
+
+    def fill(self, p) -> torch.Tensor:
+        """Put the peer tables of the next step into `p` (a _lib.ProbitParams); returns the tensor g_R lands in."""
+        self.step += 1
+        p.peer_world, p.peer_rank, p.peer_step = self.world, self.rank, self.step
+        for r in range(self.world):
+            p.peer_part[r] = self.ptrs["part"][r]
+            p.peer_g_r[r] = self.ptrs["g_r"][r]
+            p.peer_flags[r] = self.ptrs["flags"][r]
+        return self.g_r
+
+    def allreduce(self, n: int = None):
+        """Stand-alone exchange: `self.g_r` (flat, first n floats) = sum over ranks of `self.part`."""
+        lib = _lib.lib()
+        n = self.L * self.Z if n is None else int(n)
+        self.step += 1
+        tables = []
+        for name in ("part", "g_r", "flags"):
+            arr = (C.c_void_p * self.world)(*self.ptrs[name])
+            tables.append(arr)
+        with torch.cuda.device(self.device):
+            stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(lib.mpvae_peer_allreduce(tables[0], tables[1], tables[2], self.world, self.rank, self.step, n, stream),
+                       "mpvae_peer_allreduce")
+        return self.g_r
+
+    def close(self):
+        lib = _lib.lib()
+        torch.cuda.synchronize(self.device)
+        if dist.is_initialized():
+            dist.barrier(group=self.group)
+        for ptrs in self._remote.values():
+            for ptr in ptrs:
+                lib.mpvae_peer_close(C.c_void_p(ptr))
+        self._remote = {}
+        self.g_r = self.part = None
+        for ptr in self._local.values():
+            lib.mpvae_peer_free(C.c_void_p(ptr))
+        self._local = {}

@@ -77,7 +77,7 @@ class ProbitELBO(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, noise, nll_coeff, c_coeff, flags,
-                noise_spec=None):
+                noise_spec=None, peer=None):
         lib = _lib.lib()
         y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32 = (
             t.contiguous() for t in (y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32))
@@ -112,6 +112,8 @@ class ProbitELBO(torch.autograd.Function):
         if want_bwd:
             ctx.has_noise = noise is not None
             ctx.noise_spec = noise_spec
+            # data-parallel g_R over peer memory (peer.py): the backward then returns the SUM over all ranks
+            ctx.peer = peer if (peer is not None and peer.applies(S, B, L, Z, flags)) else None
             ctx.save_for_backward(y, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar, r32, ws,
                                   *([noise] if noise is not None else []))
             ctx.dims = (S, B, L, Z, D)
@@ -144,7 +146,8 @@ class ProbitELBO(torch.autograd.Function):
             g_fe_out = torch.empty_like(fe_out)
             g_fx_out = torch.empty_like(fx_out)
             g_mulv = [torch.empty_like(fe_mu) for _ in range(4)]
-            g_r = torch.empty_like(r32) if need_r else None
+            peer = ctx.peer if need_r else None
+            g_r = (torch.empty_like(r32) if peer is None else None) if need_r else None
             p = _lib.ProbitParams()
             p.struct_bytes = C.sizeof(_lib.ProbitParams)
             p.flags = flags
@@ -159,12 +162,15 @@ class ProbitELBO(torch.autograd.Function):
             p.g_indiv_prob, p.g_indiv_prob_label = _ptr(g_prob), _ptr(g_prob_label)
             p.g_fe_out, p.g_fx_out = _ptr(g_fe_out), _ptr(g_fx_out)
             p.g_fe_mu, p.g_fe_logvar, p.g_fx_mu, p.g_fx_logvar = (_ptr(t) for t in g_mulv)
+            if peer is not None:
+                g_r = peer.fill(p)               # the ring's own buffer; every rank writes its slab of the sum into it
             p.g_r = _ptr(g_r)
             p.workspace, p.workspace_bytes = _ptr(ws), ws.numel()
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             _lib.check(lib.mpvae_probit_backward(C.byref(p), stream), "mpvae_probit_backward")
         #       y     fe_out    fe_mu      fe_logvar  fx_out    fx_mu      fx_logvar  r32  noise nll_c c_c flags spec
-        return (None, g_fe_out, g_mulv[0], g_mulv[1], g_fx_out, g_mulv[2], g_mulv[3], g_r, None, None, None, None, None)
+        return (None, g_fe_out, g_mulv[0], g_mulv[1], g_fx_out, g_mulv[2], g_mulv[3], g_r, None, None, None, None, None,
+                None)
 
 
 def philox_normal(S, B, Z, *, seed, offset=0, device="cuda", global_batch=None, row0=0):
