@@ -136,6 +136,34 @@ int validate(const mpvae_probit_params* p, bool backward) {
     return 0;
 }
 
+// second stream + events of the overlapped g_R exchange (one process per GPU: created once)
+struct PeerStreams { cudaStream_t side; cudaEvent_t slab[8]; cudaEvent_t joined; };
+PeerStreams* peer_streams() {
+    static PeerStreams ps;
+    static int state = 0;       // 0 = not created, 1 = ok, -1 = failed
+    if (state == 0) {
+        state = -1;
+        if (cudaStreamCreateWithFlags(&ps.side, cudaStreamNonBlocking) != cudaSuccess) { set_error("peer: cudaStreamCreate failed"); return nullptr; }
+        for (int i = 0; i < 8; ++i)
+            if (cudaEventCreateWithFlags(&ps.slab[i], cudaEventDisableTiming) != cudaSuccess) { set_error("peer: cudaEventCreate failed"); return nullptr; }
+        if (cudaEventCreateWithFlags(&ps.joined, cudaEventDisableTiming) != cudaSuccess) { set_error("peer: cudaEventCreate failed"); return nullptr; }
+        state = 1;
+    }
+    if (state != 1) { set_error("peer: streams unavailable"); return nullptr; }
+    return &ps;
+}
+// row slabs of g_R exchanged one behind the other (MPVAE_PEER_SLABS, 1..8; must be the same on every rank)
+int peer_slabs() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("MPVAE_PEER_SLABS");
+        v = e ? atoi(e) : 1;
+        if (v < 1) v = 1;
+        if (v > 8) v = 8;
+    }
+    return v;
+}
+
 RowArgs row_args(const mpvae_probit_params* p, const Workspace& w) {
     char* base = static_cast<char*>(p->workspace);
     RowArgs a{};
@@ -280,13 +308,50 @@ int mpvae_probit_backward(const mpvae_probit_params* p, void* cuda_stream) {
         }
         // the noise planes the forward left in the workspace are the MN-major B operand as they are; the fp32 gxs
         // cube (when there is one) is dead once it has been split: scratch for the K-sliced tail wave
-        if (int rc = tc_gemm_tn(gpl, base + w.noise_planes, g_r_out, M, p->L, p->Z, slots + SLOT_ABSMAX_GXS, nullptr, stream,
-                                (!p->noise && tc_exact_supported()) ? 1 : 0, tail, tail_bytes)) return rc;
-        return peer ? launch_peer_reduce(pctx, (size_t)p->L * p->Z, stream) : 0;
+        const int b_exact = (!p->noise && tc_exact_supported()) ? 1 : 0;
+        if (!peer)
+            return tc_gemm_tn(gpl, base + w.noise_planes, g_r_out, M, p->L, p->Z, slots + SLOT_ABSMAX_GXS, nullptr, stream, b_exact,
+                              tail, tail_bytes);
+        const int slabs = peer_slabs();
+        if (slabs == 1) {
+            if (int rc = tc_gemm_tn(gpl, base + w.noise_planes, g_r_out, M, p->L, p->Z, slots + SLOT_ABSMAX_GXS, nullptr, stream,
+                                    b_exact, tail, tail_bytes)) return rc;
+            pctx.step = (pctx.step - 1) * 8u + 1u;
+            return launch_peer_reduce(pctx, (size_t)p->L * p->Z, stream);
+        }
+        // MPVAE_PEER_SLABS > 1 (experiment): g_R is produced in row slabs; while the product computes slab s+1 the
+        // exchange of slab s runs beside it on a second stream (its CTAs fit into the registers the GEMM CTAs leave
+        // free, peer_reduce.cu).  Measured on 2 x B200 it hides ~35 us of the 126 us exchange at 2 slabs and loses
+        // that again to the shorter GEMMs at 4: not the default.
+        PeerStreams* ps = peer_streams();
+        if (!ps) return 2;
+        const int rows_per_slab = ceil_div(ceil_div(p->L, 256), slabs) * 256;
+        const size_t es = tc_f16_kind() ? 2 : 4;
+        for (int sidx = 0; sidx < slabs; ++sidx) {
+            const int l0 = sidx * rows_per_slab, l1 = l0 + rows_per_slab < p->L ? l0 + rows_per_slab : p->L;
+            if (l0 >= p->L) break;
+            if (int rc = tc_gemm_tn(static_cast<char*>(gpl) + (size_t)l0 * es, base + w.noise_planes, g_r_out + (size_t)l0 * p->Z, M,
+                                    l1 - l0, p->Z, slots + SLOT_ABSMAX_GXS, nullptr, stream, b_exact, tail, tail_bytes,
+                                    tc_pitch(p->L))) return rc;
+            if (cudaEventRecord(ps->slab[sidx], stream) != cudaSuccess || cudaStreamWaitEvent(ps->side, ps->slab[sidx], 0) != cudaSuccess) {
+                set_error("peer: event record / wait failed");
+                return 2;
+            }
+            PeerCtx c = pctx;
+            c.step = (pctx.step - 1) * 8u + (uint32_t)sidx + 1u;
+            for (int i = 0; i < c.world; ++i) { c.part[i] += (size_t)l0 * p->Z; c.g_r[i] += (size_t)l0 * p->Z; }
+            if (int rc = launch_peer_reduce_small(c, (size_t)(l1 - l0) * p->Z, ps->side)) return rc;
+        }
+        if (cudaEventRecord(ps->joined, ps->side) != cudaSuccess || cudaStreamWaitEvent(stream, ps->joined, 0) != cudaSuccess) {
+            set_error("peer: join failed");
+            return 2;
+        }
+        return 0;
     }
     const float* nz = p->noise ? p->noise : reinterpret_cast<const float*>(base + w.noise_f32);
     if (int rc = launch_contract_tn_fma(a.gxs, nz, g_r_out, M, p->L, p->Z, base + w.fma_partials, w.total - w.fma_partials, stream,
                                         row_pitch(p->L))) return rc;
+    if (peer) pctx.step = (pctx.step - 1) * 8u + 1u;      // same step numbering as the slabbed tensor path
     return peer ? launch_peer_reduce(pctx, (size_t)p->L * p->Z, stream) : 0;
 }
 

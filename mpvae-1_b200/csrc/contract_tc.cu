@@ -1188,9 +1188,11 @@ int tc_gemm_nt(const void* a_planes, const void* b_planes, float* C, int M, int 
 }
 
 int tc_gemm_tn(const void* a_planes, const void* b_planes, float* C, int M, int N1, int N2, const uint32_t* absmax_a,
-               const uint32_t* absmax_b, cudaStream_t stream, int b_exact, void* tail_scratch, size_t tail_scratch_bytes) {
+               const uint32_t* absmax_b, cudaStream_t stream, int b_exact, void* tail_scratch, size_t tail_scratch_bytes,
+               int a_pitch) {
     const bool f16 = use_f16();
-    const int p1 = pitch_of(N1), p2 = pitch_of(N2);
+    // a_pitch > 0: A is a column range of wider planes (row slab of C): a_planes points at its first column
+    const int p1 = a_pitch > 0 ? a_pitch : pitch_of(N1), p2 = pitch_of(N2);
     const int bk = f16 ? 64 : 32, box_mn = f16 ? 64 : 32;
     const CUtensorMapSwizzle sw = f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     CUtensorMap ma, mb;

@@ -123,6 +123,58 @@ peer_reduce_bcast_kernel(PeerCtx ctx, size_t n) {
 
 size_t peer_flag_bytes() { return kFlagWords * sizeof(uint32_t); }
 
+// The same reduction for a slab of g_R that is exchanged WHILE the product computes the next slab: 128 threads and at
+// most 32 registers per thread, so that one such CTA fits into the 4096 registers the GEMM CTA (640 x 96) leaves free on
+// its SM and the two kernels run side by side.
+template <int W>
+__global__ void __launch_bounds__(128, 16)
+peer_reduce_small_kernel(PeerCtx ctx, size_t n) {
+    if (threadIdx.x < W) wait_flag(ctx.flags[ctx.rank] + threadIdx.x, ctx.step);
+    __syncthreads();
+    const size_t n4 = (n + 3) / 4, per = (n4 + W - 1) / W, nfull = n / 4;    // nfull complete float4 groups
+    const size_t lo = (size_t)ctx.rank * per, hi = min(n4, lo + per), vhi = min(hi, nfull);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < vhi; i += 2 * stride) {
+        const size_t j = i + stride;
+        const bool two = j < vhi;
+        // two groups in flight per thread, sources added in rank order
+        float4 a = reinterpret_cast<const float4*>(ctx.part[0])[i];
+        float4 b = two ? reinterpret_cast<const float4*>(ctx.part[0])[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int s = 1; s < W; ++s) {
+            const float4 t = reinterpret_cast<const float4*>(ctx.part[s])[i];
+            const float4 u = two ? reinterpret_cast<const float4*>(ctx.part[s])[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+            b.x += u.x; b.y += u.y; b.z += u.z; b.w += u.w;
+        }
+#pragma unroll
+        for (int p = 0; p < W; ++p) {
+            reinterpret_cast<float4*>(ctx.g_r[p])[i] = a;
+            if (two) reinterpret_cast<float4*>(ctx.g_r[p])[j] = b;
+        }
+    }
+    if (nfull < n4 && nfull >= lo && nfull < hi && blockIdx.x == 0 && threadIdx.x == 0) {
+        for (size_t e = 4 * nfull; e < n; ++e) {       // the last, partial float4 of the array
+            float acc = 0.0f;
+            for (int s = 0; s < W; ++s) acc += ctx.part[s][e];
+            for (int p = 0; p < W; ++p) ctx.g_r[p][e] = acc;
+        }
+    }
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        uint32_t* counter = ctx.flags[ctx.rank] + 16;
+        last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+        if (last) *counter = 0;
+    }
+    __syncthreads();
+    if (last && threadIdx.x < W) {
+        __threadfence_system();
+        st_release_sys(ctx.flags[threadIdx.x] + 8 + ctx.rank, ctx.step);
+    }
+}
+
 template <int W>
 void launch_reduce_w(const PeerCtx& ctx, size_t n, int ctas, int unroll, cudaStream_t stream) {
     if (unroll >= 4 && W <= 4) peer_reduce_bcast_kernel<W, 4><<<ctas, 256, 0, stream>>>(ctx, n);
@@ -146,6 +198,26 @@ int launch_peer_reduce(const PeerCtx& ctx, size_t n, cudaStream_t stream) {
         default: set_error("peer reduce: world size %d not in [2, 8]", ctx.world); return 1;
     }
     if (int rc = check_launch("peer_reduce_bcast_kernel")) return rc;
+    peer_wait_kernel<<<1, 32, 0, stream>>>(ctx, 1);
+    return check_launch("peer_wait_kernel");
+}
+
+// Exchange of one slab on `stream`, with the small-footprint kernel (see above).  ctx pointers already address the slab.
+int launch_peer_reduce_small(const PeerCtx& ctx, size_t n, cudaStream_t stream) {
+    const int ctas = kNumSMs * 4;
+    peer_signal_kernel<<<1, 32, 0, stream>>>(ctx, 0);
+    if (int rc = check_launch("peer_signal_kernel")) return rc;
+    switch (ctx.world) {
+        case 2: peer_reduce_small_kernel<2><<<ctas, 128, 0, stream>>>(ctx, n); break;
+        case 3: peer_reduce_small_kernel<3><<<ctas, 128, 0, stream>>>(ctx, n); break;
+        case 4: peer_reduce_small_kernel<4><<<ctas, 128, 0, stream>>>(ctx, n); break;
+        case 5: peer_reduce_small_kernel<5><<<ctas, 128, 0, stream>>>(ctx, n); break;
+        case 6: peer_reduce_small_kernel<6><<<ctas, 128, 0, stream>>>(ctx, n); break;
+        case 7: peer_reduce_small_kernel<7><<<ctas, 128, 0, stream>>>(ctx, n); break;
+        case 8: peer_reduce_small_kernel<8><<<ctas, 128, 0, stream>>>(ctx, n); break;
+        default: set_error("peer reduce: world size %d not in [2, 8]", ctx.world); return 1;
+    }
+    if (int rc = check_launch("peer_reduce_small_kernel")) return rc;
     peer_wait_kernel<<<1, 32, 0, stream>>>(ctx, 1);
     return check_launch("peer_wait_kernel");
 }

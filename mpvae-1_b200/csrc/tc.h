@@ -48,6 +48,6 @@ int tc_pitch(int cols);                                      // plane row pitch 
 int tc_absmax(const float* src, size_t n, uint32_t* out_bits, cudaStream_t stream);   // atomicMax of |x| bits into *out
 int tc_gemm_tn(const void* a_planes, const void* b_planes, float* C, int M, int N1, int N2, const uint32_t* absmax_a,
                const uint32_t* absmax_b, cudaStream_t stream, int b_exact = 0, void* tail_scratch = nullptr,
-               size_t tail_scratch_bytes = 0);
+               size_t tail_scratch_bytes = 0, int a_pitch = 0);
 
 }  // namespace mpv

@@ -87,7 +87,9 @@ class PeerRing:
             tables.append(arr)
         with torch.cuda.device(self.device):
             stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-            _lib.check(lib.mpvae_peer_allreduce(tables[0], tables[1], tables[2], self.world, self.rank, self.step, n, stream),
+            # flag values: eight per step (the backward exchanges g_R in up to eight slabs, each with its own number)
+            _lib.check(lib.mpvae_peer_allreduce(tables[0], tables[1], tables[2], self.world, self.rank,
+                                                (self.step - 1) * 8 + 1, n, stream),
                        "mpvae_peer_allreduce")
         return self.g_r
 
