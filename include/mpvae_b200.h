@@ -190,6 +190,14 @@ int mpvae_grad_norm(const float *g, uint64_t n, double max_norm, double grad_sca
 int mpvae_adam_step(void *p, int32_t p_is_f64, const float *g, void *m, void *v, float *shadow_f32, uint64_t n,
                     const double *state, double beta1, double beta2, double eps, double weight_decay, void *cuda_stream);
 
+/* Per-label ranking curves of evals.compute_metrics(..., all_metrics=True) (evals.py:129-175; the reference calls
+ * scikit-learn's roc_auc_score / precision_recall_curve + auc per label, 27 times per evaluation, train.py:277-289).
+ * sorted_scores / sorted_targets: (N, L) row-major, every COLUMN sorted by decreasing score (targets carried along).
+ * out[3][L] (device, fp64): ROC AUC (NaN when a class is absent), area under the PR curve, recall at the lowest
+ * threshold whose 1 - precision <= fdr_cutoff. */
+int mpvae_label_curves(const float *sorted_scores, const float *sorted_targets, int32_t N, int32_t L, double fdr_cutoff,
+                       double *out, void *cuda_stream);
+
 const char *mpvae_last_error(void);
 int mpvae_abi_version(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches claim) */

@@ -22,7 +22,7 @@ EXPORTS = (
     "mpvae_workspace_bytes", "mpvae_probit_forward", "mpvae_probit_backward", "mpvae_philox_normal",
     "mpvae_contract_nt", "mpvae_contract_nt_pitched", "mpvae_contract_tn", "mpvae_grad_norm_workspace",
     "mpvae_grad_norm", "mpvae_adam_step", "mpvae_tc_planes_bytes", "mpvae_tc_tail_scratch_bytes", "mpvae_tc_split",
-    "mpvae_tc_gemm_nt", "mpvae_tc_gemm_tn", "mpvae_peer_flag_bytes", "mpvae_peer_allreduce",
+    "mpvae_tc_gemm_nt", "mpvae_tc_gemm_tn", "mpvae_peer_flag_bytes", "mpvae_peer_allreduce", "mpvae_label_curves",
     "mpvae_peer_alloc", "mpvae_peer_open", "mpvae_peer_close", "mpvae_peer_free", "mpvae_contract_workspace_bytes", "mpvae_last_error",
     "mpvae_abi_version", "mpvae_launch_count", "mpvae_batch_metrics", "mpvae_batch_metrics_workspace",
 )
@@ -87,6 +87,8 @@ def _load():
     for fn in (lib.mpvae_contract_nt, lib.mpvae_contract_tn):
         fn.restype = C.c_int
         fn.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.mpvae_label_curves.restype = C.c_int
+    lib.mpvae_label_curves.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]
     lib.mpvae_peer_allreduce.restype = C.c_int
     lib.mpvae_peer_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint32, C.c_uint64,
                                          C.c_void_p]

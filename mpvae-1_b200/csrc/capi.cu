@@ -500,6 +500,12 @@ int mpvae_tc_gemm_tn(const void* a_planes, const void* b_planes, float* C, int32
                       tail_scratch, (size_t)tail_scratch_bytes);
 }
 
+int mpvae_label_curves(const float* sorted_scores, const float* sorted_targets, int32_t N, int32_t L, double fdr_cutoff,
+                       double* out, void* cuda_stream) {
+    if (!sorted_scores || !sorted_targets || !out || N <= 0 || L <= 0) { set_error("label_curves: bad arguments"); return 1; }
+    return launch_label_curves(sorted_scores, sorted_targets, N, L, fdr_cutoff, out, static_cast<cudaStream_t>(cuda_stream));
+}
+
 uint64_t mpvae_grad_norm_workspace(void) { return grad_norm_workspace(); }
 
 int mpvae_grad_norm(const float* g, uint64_t n, double max_norm, double grad_scale, const float* lr_dev, double lr, double beta1,

@@ -114,7 +114,57 @@ metrics_finalize_kernel(const int* __restrict__ counts, const int* __restrict__ 
     (void)s_red;
 }
 
+// the per-label curves of compute_metrics(..., all_metrics=True) (evals.py:129-175, which calls
+// scikit-learn 1.9: roc_auc_score, precision_recall_curve + auc, and the "FDR" recall).  Input: every label's scores
+// sorted in DECREASING order with the targets carried along ((N, L) row-major, column l = label l).  One thread per
+// label walks its column (coalesced across labels) and emits one curve point per DISTINCT score:
+//   ROC  (fps / n_neg, tps / n_pos) from (0, 0), trapezoid area; NaN when a class is absent
+//   PR   (recall, precision) = (tps / n_pos, tps / (tps + fps)) from the closing point (0, 1), trapezoid area;
+//        recall = 1 throughout for a label without positives (-> 0.5)
+//   FDR  recall of the lowest-threshold point with 1 - precision <= cutoff (the closing point always qualifies)
+// Counts are integers, the arithmetic fp64: the results equal the numpy restatement to rounding (1e-15).
+__global__ void __launch_bounds__(128)
+label_curves_kernel(const float* __restrict__ s, const float* __restrict__ y, int N, int L, double cutoff,
+                    double* __restrict__ out /* [3][L] */) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    int n_pos = 0;
+    for (int i = 0; i < N; ++i) n_pos += (y[(size_t)i * L + l] != 0.0f);
+    const int n_neg = N - n_pos;
+    const double inv_pos = n_pos > 0 ? 1.0 / (double)n_pos : 0.0, inv_neg = n_neg > 0 ? 1.0 / (double)n_neg : 0.0;
+    int tps = 0, fps = 0;
+    double fpr_prev = 0.0, tpr_prev = 0.0, rec_prev = 0.0, prec_prev = 1.0;
+    double auc = 0.0, aupr = 0.0, fdr_rec = 0.0;
+    float cur = N > 0 ? s[l] : 0.0f;
+    for (int i = 0; i < N; ++i) {
+        const bool pos = y[(size_t)i * L + l] != 0.0f;
+        tps += pos; fps += !pos;
+        const float nxt = (i + 1 < N) ? s[(size_t)(i + 1) * L + l] : 0.0f;
+        if (i + 1 == N || nxt != cur) {       // last element of a group of equal scores: one curve point
+            const double fpr = (double)fps / (double)(n_neg > 0 ? n_neg : 1), tpr = (double)tps / (double)(n_pos > 0 ? n_pos : 1);
+            auc += (fpr - fpr_prev) * (tpr + tpr_prev) * 0.5;
+            fpr_prev = fpr; tpr_prev = tpr;
+            const double prec = (double)tps / (double)(tps + fps);
+            const double rec = n_pos > 0 ? (double)tps / (double)n_pos : 1.0;
+            aupr += (rec - rec_prev) * (prec + prec_prev) * 0.5;
+            rec_prev = rec; prec_prev = prec;
+            if (1.0 - prec <= cutoff) fdr_rec = rec;
+        }
+        cur = nxt;
+    }
+    (void)inv_pos; (void)inv_neg;
+    out[l] = (n_pos == 0 || n_neg == 0) ? NAN : auc;
+    out[L + l] = aupr;
+    out[2 * L + l] = fdr_rec;
+}
+
 }  // namespace
+
+int launch_label_curves(const float* sorted_scores, const float* sorted_targets, int N, int L, double cutoff, double* out,
+                        cudaStream_t stream) {
+    label_curves_kernel<<<ceil_div(L, 128), 128, 0, stream>>>(sorted_scores, sorted_targets, N, L, cutoff, out);
+    return check_launch("label_curves_kernel");
+}
 
 size_t batch_metrics_workspace(int B, int L) { return align_up((size_t)3 * L * sizeof(int), 256) + (size_t)B * 8 * sizeof(int); }
 

@@ -60,6 +60,8 @@ int launch_contract_tn_fma(const float* A, const float* Bm, float* C, int M, int
 // per-step metrics (metrics.cu)
 size_t batch_metrics_workspace(int B, int L);
 int launch_batch_metrics(const float* prob, const float* y, int B, int L, float thr, double* out, void* ws, cudaStream_t stream);
+int launch_label_curves(const float* sorted_scores, const float* sorted_targets, int N, int L, double cutoff, double* out,
+                        cudaStream_t stream);
 
 // g_R summed over ranks through peer memory (peer_reduce.cu)
 struct PeerCtx {

@@ -38,3 +38,57 @@ def batch_metrics(indiv_prob: torch.Tensor, input_label: torch.Tensor, threshold
                                            C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), nbytes, stream),
                    "mpvae_batch_metrics")
     return dict(zip(NAMES, out.unbind(0)))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the test-time threshold sweep (test.py:90-101, train.py:277-289): for each of 27 thresholds the
+# reference calls compute_metrics(pred, label, t, all_metrics=True), which recomputes the threshold-INDEPENDENT
+# per-label scikit-learn curves (AUC, AUPR, FDR-recall: 3 x L sklearn calls) every time.  Here the curves are computed
+# once on the device (one sort + one kernel), the thresholded counts once per threshold (three small kernels each).
+CURVE_NAMES = ("AUC", "AUPR", "FDR")
+
+
+def label_curves(indiv_prob: torch.Tensor, input_label: torch.Tensor, fdr_cutoff: float = 0.5):
+    """(allAUC, allAUPR, allFDR): three (L,) float64 CUDA tensors (evals.py:129-175 with scikit-learn 1.9 semantics)."""
+    if not (indiv_prob.is_cuda and input_label.is_cuda):
+        raise RuntimeError("mpvae_b200.label_curves runs on CUDA tensors only")
+    p = indiv_prob.detach().float().contiguous()
+    y = input_label.detach().float().contiguous()
+    if p.shape != y.shape or p.dim() != 2 or p.shape[0] == 0:
+        raise ValueError(f"bad shapes: {tuple(p.shape)} vs {tuple(y.shape)}")
+    N, L = p.shape
+    lib = _lib.lib()
+    with torch.cuda.device(p.device):
+        scores, order = torch.sort(p, dim=0, descending=True)        # plumbing: the library kernel walks sorted columns
+        targets = torch.gather(y, 0, order)
+        out = torch.empty((3, L), dtype=torch.float64, device=p.device)
+        stream = C.c_void_p(torch.cuda.current_stream(p.device).cuda_stream)
+        _lib.check(lib.mpvae_label_curves(C.c_void_p(scores.data_ptr()), C.c_void_p(targets.data_ptr()), N, L,
+                                          float(fdr_cutoff), C.c_void_p(out.data_ptr()), stream), "mpvae_label_curves")
+    return out[0], out[1], out[2]
+
+
+def _np_median(t: torch.Tensor) -> torch.Tensor:
+    """numpy.median semantics on a 1-D device tensor: mean of the two middle values, NaN if any NaN."""
+    s, _ = torch.sort(t)
+    n = s.numel()
+    mid = (s[(n - 1) // 2] + s[n // 2]) * 0.5
+    return torch.where(torch.isnan(t).any(), torch.full_like(mid, float("nan")), mid)
+
+
+def sweep_metrics(indiv_prob: torch.Tensor, input_label: torch.Tensor, thresholds, fdr_cutoff: float = 0.5) -> list:
+    """One metrics dict per threshold with the keys of the reference's compute_metrics(..., all_metrics=True)
+    (evals.py:218-239); values are device tensors (0-dim float64, the `all*` entries (L,) float64)."""
+    auc, aupr, fdr = label_curves(indiv_prob, input_label, fdr_cutoff)
+    shared = {}
+    for name, arr in zip(CURVE_NAMES, (auc, aupr, fdr)):
+        shared["mean" + name] = arr.mean()
+        shared["median" + name] = _np_median(arr)
+        shared["var" + name] = arr.var(unbiased=False)
+        shared["all" + name] = arr
+    out = []
+    for t in thresholds:
+        m = batch_metrics(indiv_prob, input_label, float(t))
+        m.update(shared)
+        out.append(m)
+    return out

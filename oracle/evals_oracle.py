@@ -68,3 +68,55 @@ def batch_metrics(scores: np.ndarray, targets: np.ndarray, threshold: float = 0.
     out["maF1"] = macro_f1(tp, fp, fn)
     out["tp"], out["fp"], out["fn"] = tp, fp, fn
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the threshold-independent per-label curves of `compute_metrics(..., all_metrics=True)`
+# (evals.py:129-175).  The reference delegates them to scikit-learn (NOT vendored; this container has 1.9.0):
+#   compute_auc   -> metrics.roc_auc_score(y, s)                      = trapezoid area under the ROC points
+#   compute_aupr  -> metrics.precision_recall_curve + metrics.auc     = trapezoid area under the PR points
+#   compute_fdr   -> recall at the first PR point (increasing threshold) whose 1 - precision <= cutoff
+# Restated from the published algorithm (sklearn/metrics/_ranking.py 1.9.0: one curve point per DISTINCT score, in
+# decreasing score order, tps / fps cumulative; PR curve closed with the point (recall 0, precision 1); no truncation at
+# full recall; a label without positives gets recall 1 everywhere; a label with a single class gets AUC = NaN) and
+# pinned against the reference run with that sklearn (tests/golden/metrics_curves.npz).
+def label_curve_metrics(scores: np.ndarray, targets: np.ndarray, fdr_cutoff: float = 0.5):
+    """Per-label (AUC, AUPR, FDR-recall) arrays of length L, fp64."""
+    n, L = scores.shape
+    auc, aupr, fdr = np.empty(L), np.empty(L), np.empty(L)
+    for l in range(L):
+        order = np.argsort(-scores[:, l].astype(np.float64), kind="stable")
+        s, y = scores[order, l], targets[order, l] != 0
+        last_of_group = np.r_[s[1:] != s[:-1], True]            # one point per distinct score
+        tps = np.cumsum(y)[last_of_group].astype(np.float64)
+        fps = np.cumsum(~y)[last_of_group].astype(np.float64)
+        n_pos, n_neg = tps[-1], fps[-1]
+        # ROC: (0,0) then (fps/n_neg, tps/n_pos)
+        if n_pos == 0 or n_neg == 0:
+            auc[l] = np.nan
+        else:
+            fpr, tpr = np.r_[0.0, fps / n_neg], np.r_[0.0, tps / n_pos]
+            auc[l] = np.sum(np.diff(fpr) * (tpr[1:] + tpr[:-1]) * 0.5)
+        # PR in decreasing-threshold order, preceded by the closing point (recall 0, precision 1)
+        prec = np.r_[1.0, tps / (tps + fps)]
+        rec = np.r_[0.0, (tps / n_pos) if n_pos > 0 else np.ones_like(tps)]
+        aupr[l] = np.sum(np.diff(rec) * (prec[1:] + prec[:-1]) * 0.5)
+        # sklearn's arrays run the other way (increasing threshold): the FIRST point with fdr <= cutoff there is the LAST
+        # one here; the closing point (fdr 0) always qualifies
+        ok = np.nonzero(1.0 - prec <= fdr_cutoff)[0]
+        fdr[l] = rec[ok[-1]]
+    return auc, aupr, fdr
+
+
+def _summary(a):
+    return float(np.mean(a)), float(np.median(a)), float(np.var(a))
+
+
+def full_metrics(scores: np.ndarray, targets: np.ndarray, threshold: float) -> dict:
+    """evals.py:178-239 with all_metrics=True."""
+    out = batch_metrics(scores, targets, threshold)
+    auc, aupr, fdr = label_curve_metrics(scores, targets)
+    for name, arr in (("AUC", auc), ("AUPR", aupr), ("FDR", fdr)):
+        out["mean" + name], out["median" + name], out["var" + name] = _summary(arr)
+        out["all" + name] = arr
+    return out
