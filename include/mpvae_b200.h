@@ -31,7 +31,7 @@ extern "C" {
 /* flags */
 #define MPVAE_FLAG_SANITIZE_DEGENERATE 0x1u /* rows with n_pos*n_neg == 0 get zero ranking gradient instead of
                                                the reference's NaN (mpvae.py:118-121); default off = faithful */
-#define MPVAE_FLAG_CONTRACT_TENSOR     0x2u /* noise.R^T and g_R on tcgen05 (3xTF32); default: chosen by shape */
+#define MPVAE_FLAG_CONTRACT_TENSOR     0x2u /* noise.R^T and g_R on tcgen05 (split-precision fp16 pieces); default: chosen by shape */
 #define MPVAE_FLAG_CONTRACT_FMA        0x4u /* force the CUDA-core FMA contraction */
 
 /* order of the six scalar outputs (first six entries of the 8-tuple at mpvae.py:210) */

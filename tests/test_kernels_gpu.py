@@ -175,7 +175,7 @@ def test_full_size_properties(name, L, Z, B):
     assert all(torch.isfinite(g).all() for g in g_full.values())
 
 
-# ----------------------------------------------------------------------------- tcgen05 3xTF32 engine
+# ----------------------------------------------------------------------------- tcgen05 split-precision engine
 def _tc_report(**kw):
     import json, os
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "tc_report.jsonl")
@@ -190,7 +190,7 @@ def _tc_report(**kw):
 @pytest.mark.parametrize("M,N,K", [(128, 256, 32), (128, 256, 64), (256, 512, 256), (300, 500, 200), (1280, 983, 983),
                                    (10240, 983, 983), (640, 3993, 3993)])
 def test_contract_nt_tensor(M, N, K):
-    """3xTF32 on tcgen05 must agree with the exact product to fp32-SGEMM accuracy (parity needs ~1e-6)."""
+    """The split-precision product on tcgen05 must agree with the exact product to fp32-SGEMM accuracy (parity needs ~1e-6)."""
     from mpvae_b200.probit import contract_nt
     g = torch.Generator(device="cpu").manual_seed(M + 3 * N + 7 * K)
     a = torch.randn(M, K, generator=g)

@@ -217,7 +217,7 @@ def test_large_label_sets_against_exact_sum_oracle(name, L, Z, B):
 @pytest.mark.parametrize("name,L,Z,B", [("delicious", 983, 983, 16), ("delicious_b128", 983, 983, 128),
                                         ("eurlex_b16", 3993, 3993, 16)])
 def test_tensor_engine_is_as_accurate_as_the_reference(name, L, Z, B):
-    """Dense regime (Z >= 128): noise.R^T runs as 3xTF32 on tcgen05, whose rounding differs from an fp32 SGEMM's
+    """Dense regime (Z >= 128): noise.R^T runs as a split-precision product on tcgen05, whose rounding differs from an fp32 SGEMM's
     (it is ~2x closer to the exact product).  At these sizes a 1e-6 perturbation of x moves softmax_s(lp) -- and
     with it every gradient -- by ~sqrt(L) * 1e-6 * |dll/dx| ~ 1e-4, for ANY implementation including the
     reference's own cuBLAS path.  So the bar is: forward terms within 1e-5 of the reference path, decisions equal
