@@ -239,8 +239,9 @@ def run_b200(a):
         out[0].backward()
         if world > 1:
             if ring is None:
-                dist.all_reduce(r32.grad)        # the path's one exchange step: NCCL sum over NVLink
-            r32.grad.div_(world)                 # (with the peer ring the backward already returned the sum)
+                dist.all_reduce(r32.grad, op=dist.ReduceOp.AVG)   # the path's one exchange step: NCCL mean over NVLink
+            else:
+                r32.grad.div_(world)             # with the peer ring the backward already returned the sum
         if from_host:
             loss_host.copy_(out[0].detach(), non_blocking=True)
         for k in row_keys:

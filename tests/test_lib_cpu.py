@@ -121,3 +121,40 @@ def test_vae_state_dict_layout():
         torch.manual_seed(1); b = ours(y, x)
         for u, v in zip(a, b):
             assert torch.equal(u, v)
+
+
+def test_new_entry_points_validate_arguments(lib):
+    """The optimizer / staged-engine / metrics / peer entry points reject bad arguments before touching the device."""
+    assert lib.mpvae_grad_norm(None, 10, 1.0, 1.0, None, 1e-3, 0.9, 0.999, None, None, 0, None) == 1
+    assert b"grad_norm" in lib.mpvae_last_error()
+    assert lib.mpvae_adam_step(None, 0, None, None, None, None, 10, None, 0.9, 0.999, 1e-8, 0.0, None) == 1
+    assert b"adam_step" in lib.mpvae_last_error()
+    assert lib.mpvae_tc_split(None, 4, 64, None, None, None) == 1
+    assert lib.mpvae_tc_gemm_nt(None, None, None, 1, 1, 1, 0, None, None, 0, None, 0, None) == 1
+    assert lib.mpvae_tc_gemm_tn(None, None, None, 1, 1, 1, None, None, None, 0, None) == 1
+    assert lib.mpvae_label_curves(None, None, 4, 4, 0.5, None, None) == 1
+    assert b"label_curves" in lib.mpvae_last_error()
+    assert lib.mpvae_peer_allreduce(None, None, None, 2, 0, 1, 16, None) == 1
+    assert b"peer_allreduce" in lib.mpvae_last_error()
+    assert lib.mpvae_tc_planes_bytes(1024, 3993) >= 2 * 1024 * 3993 * 2
+    assert lib.mpvae_peer_flag_bytes() >= 17 * 4
+    assert lib.mpvae_grad_norm_workspace() > 0
+
+
+def test_host_wrappers_have_no_cpu_path():
+    """The device-side replacements refuse CPU tensors; only the small-layer fallback of dense.linear (plain torch.nn,
+    which the design keeps for the MLP) runs anywhere."""
+    from mpvae_b200 import metrics
+    from mpvae_b200.dense import linear, uses_tensor_engine
+    from mpvae_b200.optim import FusedAdam
+    p, y = torch.rand(4, 6), (torch.rand(4, 6) < 0.5).float()
+    for fn in (metrics.batch_metrics, metrics.label_curves):
+        with pytest.raises(RuntimeError, match="CUDA tensors only"):
+            fn(p, y)
+    w = torch.nn.Parameter(torch.randn(3, 3))
+    w.grad = torch.randn(3, 3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FusedAdam([w], lr=1e-3).step()
+    layer, x = torch.nn.Linear(2048, 1024), torch.randn(256, 2048)
+    assert not uses_tensor_engine(layer, x)
+    assert torch.equal(linear(layer, x), layer(x))
