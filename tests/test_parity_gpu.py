@@ -253,6 +253,46 @@ def test_tensor_engine_is_as_accurate_as_the_reference(name, L, Z, B):
         assert rec["gmax_" + k] <= 2e-3, (k, rec["gmax_" + k])
 
 
+@pytest.mark.parametrize("L,Z,B", [(256, 253, 64), (256, 254, 64), (255, 255, 64), (130, 256, 70), (983, 983, 128)])
+def test_library_noise_in_the_dense_regime(L, Z, B):
+    """With `noise=None` the library draws Philox normals on the fp16 grid straight into ONE operand plane and runs the
+    two-pass products (contract_tc.cu EX = 1 / 2).  The same numbers come out of `philox_normal`; fed back as an
+    external tensor they take the split + three-pass route.  Both routes -- and the reference's torch path on the
+    same noise -- must agree: this pins the plane writer (all four destination alignments: Z mod 4 = 1, 2, 3, 0), the
+    exact-operand kernels and the gxs planes the row backward writes with its a-priori scale."""
+    from mpvae_b200 import synth
+    from mpvae_b200.mpvae import compute_loss
+    from mpvae_b200.probit import philox_normal
+    S = 10
+    inp = synth.loss_inputs(L, Z, B, S, seed=77, sigma=1.0, label_rate=max(0.05, 20.0 / L), with_noise=False)
+    dev = torch.device("cuda:0")
+
+    def run(external):
+        args = orc.make_args(L, Z, n_train_sample=S, noise_seed=909, noise_offset=3)
+        t = {k: torch.from_numpy(v).to(dev).requires_grad_(k != "y") for k, v in inp.items()}
+        kw = {"noise": philox_normal(S, B, Z, seed=909, offset=3, device=dev)} if external else {}
+        out = compute_loss(t["y"], t["fe_out"], t["fe_mu"], t["fe_logvar"], t["fx_out"], t["fx_mu"], t["fx_logvar"],
+                           t["r_sqrt_sigma"], args, **kw)
+        out[0].backward()
+        return ([o.detach().cpu().numpy() for o in out], {k: t[k].grad.cpu().numpy() for k in H.GRAD_KEYS})
+
+    lib_o, lib_g = run(False)
+    ext_o, ext_g = run(True)
+    noise = philox_normal(S, B, Z, seed=909, offset=3, device=dev)
+    assert torch.equal(noise, noise.half().float())                       # on the fp16 grid
+    ref, ref_g = orc.probit_elbo_with_grads({k: torch.from_numpy(v).to(dev) for k, v in inp.items()}, noise, 0.5, 10.0,
+                                            ranking="factorised")
+    for i, k in enumerate(H.SCALAR_KEYS):
+        assert H.rel_err(lib_o[i], ext_o[i]) <= 2e-6, (k, "two-pass vs three-pass")
+        assert H.rel_err(lib_o[i], getattr(ref, k).item()) <= 1e-5, (k, "vs the torch path")
+    assert float(np.max(np.abs(lib_o[6] - ext_o[6]))) <= 2e-6
+    assert float(np.max(np.abs(lib_o[6] - ref.indiv_prob.detach().cpu().numpy()))) <= 5e-6
+    for k in H.GRAD_KEYS:
+        mine = H.rel_err_l2(lib_g[k], ext_g[k])
+        assert mine <= 2e-4, (k, mine, "two-pass vs three-pass")
+        assert H.rel_err_l2(lib_g[k], ref_g[k].cpu().numpy()) <= 5e-4, (k, "vs the torch path")
+
+
 def test_upstream_on_every_output():
     """Cotangents on all 8 outputs at once (autograd contract)."""
     from mpvae_b200 import synth
