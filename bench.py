@@ -346,8 +346,8 @@ def run_b200(a):
             div = float(passes) if kind != "tf32" else 2.0 * passes
             peak = peaks["bf16_tflops"] / div
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
-            # (profiles/r01_two_pass_ncu_full_summary.txt: 587.56 MB + 150.30 MB per launch) -- eurlex default only
-            traffic = 737.86e6 if (L, Z, M_rows, passes, kind) == (3993, 3993, 10240, 2, "f16") else None
+            # (profiles/r01_final_ncu_full_summary.txt: 620.58 MB + 148.60 MB per launch) -- eurlex default only
+            traffic = 769.18e6 if (L, Z, M_rows, passes, kind) == (3993, 3993, 10240, 2, "f16") else None
             roof = {"bound": "tensor", "achieved": flops / t_k / 1e12, "peak": peak, "unit": "TFLOP/s",
                     "frac": flops / t_k / 1e12 / peak, "traffic": traffic,
                     "kernel": "gemm_split_2sm_kernel<nt> (noise.R^T, mpvae.py:168), tcgen05 " + kind + f" hi/lo split, {passes} MMA passes",
