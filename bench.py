@@ -46,9 +46,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-step", action="store_true", help="skip the full-training-step (steps/s) leg")
     ap.add_argument("--engine", default="auto", choices=["auto", "fma", "tensor"])
-    ap.add_argument("--exchange", default="nccl", choices=["peer", "nccl"],
-                    help="N>1: how g_R is summed over ranks (nccl = all-reduce after the backward; peer = inside the "
-                         "backward over NVLink peer memory, mpvae_b200.peer.PeerRing)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: how g_R is summed over ranks (peer = inside the backward over NVLink peer memory, "
+                         "mpvae_b200.peer.PeerRing, falling back to nccl if the ring cannot be set up on every rank; "
+                         "nccl = all-reduce after the backward)")
     return ap.parse_args()
 
 
@@ -213,12 +214,22 @@ def run_b200(a):
     flush = torch.empty(2 * L2_BYTES // 4, dtype=torch.float32, device=dev)
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     step_no = [0]
-    # the path's one exchange: g_R summed over ranks.  Default: an NCCL all-reduce after the backward;
-    # --exchange peer = inside the backward over NVLink peer memory (mpvae_b200.peer.PeerRing)
+    # the path's one exchange: g_R summed over ranks.  Default: inside the backward over NVLink peer memory
+    # (mpvae_b200.peer.PeerRing; measured 34 / 203 us against NCCL's 54 / 270 us for 4 / 64 MB on 8 GPUs,
+    # profiles/r01_peer_allreduce.txt); --exchange nccl = an NCCL all-reduce after the backward.  If any rank fails
+    # to set the ring up (CUDA IPC unavailable), every rank falls back to NCCL.
     ring = None
     if world > 1 and not infer and a.exchange == "peer":
         from mpvae_b200.peer import PeerRing
-        ring = PeerRing(L, Z, dev)
+        try:
+            ring = PeerRing(L, Z, dev)
+        except Exception as e:          # noqa: BLE001 -- any failure means "use NCCL", decided collectively below
+            print(f"[bench] rank {rank}: peer ring unavailable ({e}); NCCL exchange", file=sys.stderr)
+            ring = None
+        ok = torch.tensor([1 if ring is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0 and ring is not None:
+            ring = None                 # (its buffers stay allocated; the process is short-lived)
         args.peer_ring = ring
 
     def one_step(src, from_host):

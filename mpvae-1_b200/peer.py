@@ -10,6 +10,7 @@ torch.distributed is used for exactly one thing here: `all_gather_object` of the
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -40,24 +41,44 @@ class PeerRing:
         self.device = torch.device(device)
         sizes = {"part": self.L * self.Z * 4, "g_r": self.L * self.Z * 4, "flags": int(lib.mpvae_peer_flag_bytes())}
         self._local, self._remote, handles = {}, {}, {}
+        # Every collective below is entered by EVERY rank whatever happened locally, and the outcome is agreed on
+        # collectively: either all ranks own a working ring or all of them raise (no rank is left waiting).
+        error = None
         with torch.cuda.device(self.device):
-            for name, nbytes in sizes.items():
-                ptr, h = C.c_void_p(), C.create_string_buffer(64)
-                _lib.check(lib.mpvae_peer_alloc(nbytes, C.byref(ptr), h), "mpvae_peer_alloc")
-                self._local[name] = ptr.value
-                handles[name] = h.raw
+            try:
+                if os.environ.get("MPVAE_PEER_TEST_FAIL") == str(self.rank):     # test hook: exercise the collective fallback
+                    raise RuntimeError("simulated set-up failure (MPVAE_PEER_TEST_FAIL)")
+                for name, nbytes in sizes.items():
+                    ptr, h = C.c_void_p(), C.create_string_buffer(64)
+                    _lib.check(lib.mpvae_peer_alloc(nbytes, C.byref(ptr), h), "mpvae_peer_alloc")
+                    self._local[name] = ptr.value
+                    handles[name] = h.raw
+            except Exception as e:      # noqa: BLE001
+                error, handles = e, None
             gathered = [None] * self.world
             dist.all_gather_object(gathered, handles, group=group)
             self.ptrs = {name: [0] * self.world for name in sizes}
-            for r, hs in enumerate(gathered):
-                for name in sizes:
-                    if r == self.rank:
-                        self.ptrs[name][r] = self._local[name]
-                        continue
-                    ptr = C.c_void_p()
-                    _lib.check(lib.mpvae_peer_open(hs[name], C.byref(ptr)), "mpvae_peer_open")
-                    self.ptrs[name][r] = ptr.value
-                    self._remote.setdefault(name, []).append(ptr.value)
+            if error is None and all(h is not None for h in gathered):
+                try:
+                    for r, hs in enumerate(gathered):
+                        for name in sizes:
+                            if r == self.rank:
+                                self.ptrs[name][r] = self._local[name]
+                                continue
+                            ptr = C.c_void_p()
+                            _lib.check(lib.mpvae_peer_open(hs[name], C.byref(ptr)), "mpvae_peer_open")
+                            self.ptrs[name][r] = ptr.value
+                            self._remote.setdefault(name, []).append(ptr.value)
+                except Exception as e:  # noqa: BLE001
+                    error = e
+            elif error is None:
+                error = RuntimeError("a peer rank could not allocate its buffers")
+            verdicts = [None] * self.world
+            dist.all_gather_object(verdicts, None if error is None else str(error), group=group)
+            if any(v is not None for v in verdicts):
+                self._release()
+                raise RuntimeError("PeerRing: set-up failed on rank(s) " +
+                                   ", ".join(f"{r}: {v}" for r, v in enumerate(verdicts) if v is not None))
             self.g_r = torch.as_tensor(_DevMem(self._local["g_r"], (self.L, self.Z), "<f4"), device=self.device)
             self.part = torch.as_tensor(_DevMem(self._local["part"], (self.L, self.Z), "<f4"), device=self.device)
         self.step = 0
@@ -93,11 +114,8 @@ class PeerRing:
                        "mpvae_peer_allreduce")
         return self.g_r
 
-    def close(self):
+    def _release(self):
         lib = _lib.lib()
-        torch.cuda.synchronize(self.device)
-        if dist.is_initialized():
-            dist.barrier(group=self.group)
         for ptrs in self._remote.values():
             for ptr in ptrs:
                 lib.mpvae_peer_close(C.c_void_p(ptr))
@@ -106,3 +124,9 @@ class PeerRing:
         for ptr in self._local.values():
             lib.mpvae_peer_free(C.c_void_p(ptr))
         self._local = {}
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        if dist.is_initialized():
+            dist.barrier(group=self.group)      # nobody unmaps while a peer may still be reading
+        self._release()
