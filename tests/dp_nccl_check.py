@@ -16,7 +16,7 @@ from mpvae_b200.mpvae import VAE
 from mpvae_b200.train import DataParallelStep, GraphedTrainStep
 
 
-def build(dev, L, Z, F):
+def build(dev, L, Z, F, fused=False):
     args = SimpleNamespace(feature_dim=F, label_dim=L, latent_dim=50, z_dim=Z, keep_prob=0.0, scale_coeff=1.0,
                            residue_sigma="", n_train_sample=10, n_test_sample=10, mode="train", nll_coeff=0.5,
                            c_coeff=10.0, noise_seed=5)
@@ -25,7 +25,11 @@ def build(dev, L, Z, F):
     with torch.no_grad():
         for head in (vae.fe_logvar, vae.fx_logvar):
             head.weight.zero_(); head.bias.fill_(-30.0)
-    opt = torch.optim.SGD(vae.parameters(), lr=0.05)
+    if fused:
+        from mpvae_b200.optim import FusedAdam
+        opt = FusedAdam(vae.parameters(), lr=1e-3, weight_decay=1e-5)
+    else:
+        opt = torch.optim.SGD(vae.parameters(), lr=0.05)
     return vae, opt, args
 
 
@@ -35,15 +39,19 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for (L, Z, F, B) in ((38, 38, 100, 128), (983, 983, 64, 256)):
+    # (peer_g_r, fused): NCCL bucket + SGD; g_R summed over NVLink peer memory inside the backward; the same with the
+    # fused clip + Adam (the 1 / world of the gradient mean folded into its gradient multiplier)
+    for (L, Z, F, B, peer, fused) in ((38, 38, 100, 128, False, False), (983, 983, 64, 256, False, False),
+                                      (983, 983, 64, 256, True, False), (983, 983, 64, 256, True, True),
+                                      (983, 983, 64, 256, False, True)):
         rng = np.random.RandomState(1)
         x = torch.from_numpy(synth.features(B, F, rng)).to(dev)
         y = torch.from_numpy(synth.labels(B, L, 0.1, rng)).to(dev)
-        vae, opt, args = build(dev, L, Z, F)
-        step = DataParallelStep(vae, opt, None, args, clip_norm=100.0)
+        vae, opt, args = build(dev, L, Z, F, fused)
+        step = DataParallelStep(vae, opt, None, args, clip_norm=100.0, peer_g_r=peer)
         outs = [step.step(y, x) for _ in range(3)]
         # reference trajectory: the same three steps on the full batch by a single (group-less) stepper
-        vae1, opt1, args1 = build(dev, L, Z, F)
+        vae1, opt1, args1 = build(dev, L, Z, F, fused)
         solo = DataParallelStep(vae1, opt1, None, args1, clip_norm=100.0, distributed=False)
         outs1 = [solo.step(y, x) for _ in range(3)]
         worst, who = 0.0, ""
@@ -54,7 +62,10 @@ def main():
                 worst, who = d, n
         dl = max(abs(float(a.total_loss) - float(b.total_loss)) / abs(float(b.total_loss)) for a, b in zip(outs, outs1))
         if rank == 0:
-            print(f"L={L} Z={Z} B={B}: worst param rel diff {worst:.2e} ({who}), worst loss rel diff {dl:.2e}", flush=True)
+            print(f"L={L} Z={Z} B={B} peer_g_r={peer} fused_adam={fused}: worst param rel diff {worst:.2e} ({who}), "
+                  f"worst loss rel diff {dl:.2e}", flush=True)
+        if step.ring is not None:
+            step.ring.close()
         ok &= worst < 2e-4 and dl < 1e-5
     t = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
