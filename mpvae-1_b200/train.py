@@ -265,9 +265,13 @@ class GraphedTrainStep:
         stepper.args.noise_offset_tensor = self.counter
         stepper.args.noise_offset_auto = False
         stepper.args.noise_offset = 0
+        from .optim import FusedAdam
         for group in stepper.optimizer.param_groups:
             if "capturable" in group and not group["capturable"]:
                 raise ValueError("construct the optimizer with capturable=True for graph capture")
+            if isinstance(stepper.optimizer, FusedAdam) and not (isinstance(group["lr"], torch.Tensor) and group["lr"].is_cuda):
+                # a Python float would be baked into the captured launch; StepLR writes into the tensor between replays
+                raise ValueError("FusedAdam under graph capture needs lr as a CUDA tensor: lr=torch.tensor(1e-3, device=...)")
 
     def _capture(self, y, x):
         st = self.stepper

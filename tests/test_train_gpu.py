@@ -258,3 +258,38 @@ def test_tensor_linear_matches_fp64_linear(B, n_in, n_out, x_grad):
         err = H.rel_err(got[k].cpu().numpy(), truth[k].cpu().numpy())
         err32 = H.rel_err(ref32[k].cpu().numpy(), truth[k].cpu().numpy())
         assert err <= max(3e-6, 2 * err32), (k, err, err32)
+
+
+def test_fused_adam_state_dict_round_trip():
+    """Checkpoint / resume: a FusedAdam restored from state_dict continues exactly where the original would have."""
+    from mpvae_b200.optim import FusedAdam
+    g = torch.Generator(device="cpu").manual_seed(9)
+
+    def make():
+        g.manual_seed(9)
+        return [torch.nn.Parameter(torch.randn(50, 7, generator=g).to(DEV)),
+                torch.nn.Parameter((torch.randn(31, 31, generator=g).double() * 0.1).to(DEV))]
+
+    def feed(ps, k):
+        gg = torch.Generator(device="cpu").manual_seed(100 + k)
+        for p in ps:
+            p.grad = torch.randn(p.shape, generator=gg).to(DEV).to(p.dtype)
+
+    a = make()
+    opt_a = FusedAdam(a, lr=3e-3, weight_decay=1e-5)
+    for k in range(3):
+        feed(a, k)
+        opt_a.step(max_norm=1.0)
+    b = make()
+    with torch.no_grad():
+        for p, q in zip(a, b):
+            q.copy_(p)
+    opt_b = FusedAdam(b, lr=3e-3, weight_decay=1e-5)
+    opt_b.load_state_dict(opt_a.state_dict())
+    assert float(opt_b.state_dict()["state"][0]["step"]) == 3.0
+    for k in range(3, 6):
+        feed(a, k); feed(b, k)
+        opt_a.step(max_norm=1.0)
+        opt_b.step(max_norm=1.0)
+    for p, q in zip(a, b):
+        assert torch.equal(p, q)
