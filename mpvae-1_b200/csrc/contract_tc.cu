@@ -984,7 +984,11 @@ int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc, in
     // k-blocks per TMEM chunk: the same number of truncating MMAs per chunk (48) whether a k-step is 3 or 2 MMAs
     const int kc = chunk_kblocks(ex == 0 ? Geo<MN, F16>::default_kc : (Geo<MN, F16>::default_kc * 3) / 2);
     static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("MPVAE_TC_DEBUG"); dbg = e ? atoi(e) : 0; }   // timing probes, results invalid
+    if (dbg < 0) {   // timing probes for kernel development: results are INVALID while one is active
+        const char* e = getenv("MPVAE_TC_DEBUG");
+        dbg = e ? atoi(e) : 0;
+        if (dbg != 0) fprintf(stderr, "[mpvae tc] MPVAE_TC_DEBUG=%d: timing probe active, tensor-engine results are INVALID\n", dbg);
+    }
     if (dbg == 3) return 0;                                                               // pre-passes only
     if (cta_group() == 2) {
         if (ex == 1) return launch_gemm_2sm<MN, F16, 1>(a, b, C, Mc, Nc, K, ldc, ma, mb, kc, dbg, stream, partials, partials_bytes);
