@@ -72,8 +72,15 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.lines = []
+        self.lines = []          # (arrival time, csv line); only those inside [t0, t1] are reported
         self.proc = None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.monotonic()
+
+    def mark_end(self):
+        self.t1 = time.monotonic()
 
     def start(self):
         try:
@@ -87,7 +94,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.monotonic(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -99,7 +106,11 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t0 = self.t0 if self.t0 is not None else float("-inf")
+        t1 = self.t1 if self.t1 is not None else float("inf")
+        for when, ln in self.lines:
+            if not (t0 <= when <= t1):
+                continue          # nvidia-smi was started before the warm-up so that it is already looping here
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -297,22 +308,23 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, a.warmup)):
-        one_step(devt, False)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()             # started ahead of the warm-up: its first sample takes a few hundred ms
+    for _ in range(max(3, a.warmup)):
+        one_step(devt, False)
+    timed_e2e(2)
+    barrier()
+    sampler.mark_begin()            # clocks are reported for the two timed regions below only
     launches0 = _lib.launch_count()
     ms = timed(a.steps, False)
     launches = _lib.launch_count() - launches0
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     total_ms = sum(ms)
-    timed_e2e(2)
-    barrier()
     total_e2e = timed_e2e(a.steps)
     barrier()
+    sampler.mark_end()
+    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([total_ms, total_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
