@@ -293,3 +293,48 @@ def test_fused_adam_state_dict_round_trip():
         opt_b.step(max_norm=1.0)
     for p, q in zip(a, b):
         assert torch.equal(p, q)
+
+
+def test_reference_training_script_flow_on_the_device():
+    """The whole of the reference's train.py flow with every replacement in place and no host round trip inside the
+    loop: FusedAdam (train.py:93), the step (train.py:103-129) as a CUDA graph, the per-step metrics
+    (train.py:131-136) as device scalars, and the final threshold sweep of the validation pass
+    (train.py:277-289 / test.py:90-101) -- checked against the numpy restatement of evals.compute_metrics."""
+    from oracle import evals_oracle as ev
+    from mpvae_b200.infer import predict_proba
+    from mpvae_b200.metrics import batch_metrics, sweep_metrics
+    from mpvae_b200.mpvae import VAE
+    from mpvae_b200.optim import FusedAdam
+    from mpvae_b200.train import DataParallelStep, GraphedTrainStep
+    args = yeast_args()
+    x, y = yeast_data(1408)
+    n_train = 1152                                           # nine full batches of 128: one captured graph
+    np.random.seed(4); torch.manual_seed(0)
+    vae = VAE(args).to(DEV)
+    opt = FusedAdam(vae.parameters(), lr=torch.tensor(1e-3, device=DEV), weight_decay=1e-5)
+    sched = torch.optim.lr_scheduler.StepLR(opt, 9 * 5, 0.5)
+    graphed = GraphedTrainStep(DataParallelStep(vae, opt, sched, args, clip_norm=100.0))
+    history = []
+    for epoch in range(10):
+        order = torch.randperm(n_train, device=DEV)
+        for i in range(9):
+            idx = order[i * 128:(i + 1) * 128]
+            out = graphed.step(y[idx], x[idx])
+            m = batch_metrics(out.indiv_prob, y[idx], 0.5)           # device scalars: nothing synchronises here
+            history.append(torch.stack([out.total_loss.double(), m["miF1"], m["HA"]]))
+    hist = torch.stack(history).cpu().numpy()                        # ONE transfer for the whole run
+    assert np.isfinite(hist).all()
+    assert hist[-9:, 0].mean() < 0.8 * hist[:9, 0].mean()            # the loss went down
+    assert hist[-9:, 1].mean() > hist[:9, 1].mean()                  # micro-F1 went up
+    assert float(opt.param_groups[0]["lr"]) == pytest.approx(0.25e-3)   # StepLR(45, 0.5) stepped 90 times
+    # validation pass + threshold sweep on the device, against the numpy restatement on the same predictions
+    args_t = yeast_args(n_test_sample=100)
+    probs, _ = predict_proba(vae, x[n_train:], y[n_train:], args_t, batch_size=128)
+    thresholds = [0.05, 0.25, 0.5, 0.75]
+    got = sweep_metrics(probs, y[n_train:], thresholds)
+    p_np, y_np = probs.cpu().numpy(), y[n_train:].cpu().numpy()
+    for t, m in zip(thresholds, got):
+        want = ev.full_metrics(p_np, y_np, t)
+        for k in ("ACC", "HA", "ebF1", "miF1", "maF1", "p_at_1", "meanAUC", "medianAUPR", "varFDR"):
+            a, b = m[k].item(), float(want[k])
+            assert (np.isnan(a) and np.isnan(b)) or abs(a - b) <= 3e-6 * max(abs(b), 1.0), (t, k, a, b)
