@@ -33,6 +33,9 @@ extern "C" {
                                                the reference's NaN (mpvae.py:118-121); default off = faithful */
 #define MPVAE_FLAG_CONTRACT_TENSOR     0x2u /* noise.R^T and g_R on tcgen05 (split-precision fp16 pieces); default: chosen by shape */
 #define MPVAE_FLAG_CONTRACT_FMA        0x4u /* force the CUDA-core FMA contraction */
+#define MPVAE_FLAG_STABLE_CDF          0x8u /* opt-in: Phi and 1 - Phi from erfc(|x| / sqrt 2) (no cancellation in the tails)
+                                               instead of the reference's 0.5 (1 + erf) and 1 - E.  More accurate than the
+                                               reference, hence NOT within 1e-5 of it in saturated cells. */
 
 /* order of the six scalar outputs (first six entries of the 8-tuple at mpvae.py:210) */
 enum { MPVAE_TOTAL = 0, MPVAE_NLL = 1, MPVAE_NLL_X = 2, MPVAE_C = 3, MPVAE_C_X = 4, MPVAE_KL = 5 };

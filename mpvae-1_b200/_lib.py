@@ -16,6 +16,7 @@ ABI_VERSION = 8
 FLAG_SANITIZE_DEGENERATE = 0x1
 FLAG_CONTRACT_TENSOR = 0x2
 FLAG_CONTRACT_FMA = 0x4
+FLAG_STABLE_CDF = 0x8
 
 # every symbol include/mpvae_b200.h declares
 EXPORTS = (

@@ -170,6 +170,7 @@ RowArgs row_args(const mpvae_probit_params* p, const Workspace& w) {
     a.S = p->S; a.B = p->B; a.L = p->L; a.D = p->D;
     a.ldn = row_pitch(p->L);
     a.sanitize = (p->flags & MPVAE_FLAG_SANITIZE_DEGENERATE) ? 1 : 0;
+    a.stable = (p->flags & MPVAE_FLAG_STABLE_CDF) ? 1 : 0;
     a.nll_coeff = p->nll_coeff; a.c_coeff = p->c_coeff;
     a.y = p->y; a.fe_out = p->fe_out; a.fx_out = p->fx_out;
     a.fe_mu = p->fe_mu; a.fe_logvar = p->fe_logvar; a.fx_mu = p->fx_mu; a.fx_logvar = p->fx_logvar;

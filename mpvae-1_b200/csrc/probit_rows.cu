@@ -59,6 +59,7 @@ __device__ __forceinline__ BlockCounts count_labels(const float* __restrict__ yr
     return c;
 }
 
+template <bool STABLE>
 __global__ void __launch_bounds__(kThreads, 4)
 probit_row_fwd_kernel(const RowArgs a) {
     extern __shared__ float s_pacc[];                 // [nws][2][L] prediction partial sums
@@ -107,8 +108,8 @@ probit_row_fwd_kernel(const RowArgs a) {
 #pragma unroll
                     for (int i = 0; i < kST; ++i) {
                         if (s0 + i < S) {
-                            const CellFwd cl = cell_forward(cur.nr[i] + cur.fe, cur.y);   // mpvae.py:168,177
-                            const CellFwd cx = cell_forward(cur.nr[i] + cur.fx, cur.y);   // mpvae.py:170,180
+                            const CellFwd cl = cell_forward<STABLE>(cur.nr[i] + cur.fe, cur.y);   // mpvae.py:168,177
+                            const CellFwd cx = cell_forward<STABLE>(cur.nr[i] + cur.fx, cur.y);   // mpvae.py:170,180
                             lp[i][0] += (double)cl.ll;
                             lp[i][1] += (double)cx.ll;
                             pn[i][0] += cl.epos; pn[i][1] += cl.eneg;
@@ -291,6 +292,7 @@ gxs_bound_kernel(const RowArgs a, const unsigned int* __restrict__ gp_absmax, un
     if ((threadIdx.x & 31) == 0 && bits != 0u) atomicMax(out_bits, bits);
 }
 
+template <bool STABLE>
 __global__ void __launch_bounds__(kThreads, 4)
 probit_row_bwd_kernel(const RowArgs a) {
     extern __shared__ float s_gacc[];   // [nws][2][L] logit-gradient partial sums
@@ -345,8 +347,8 @@ probit_row_bwd_kernel(const RowArgs a) {
 #pragma unroll
                 for (int i = 0; i < kST; ++i) {
                     if (s0 + i < S) {
-                        const float dl = cell_backward(cur.nr[i] + cur.fe, cur.y, cn[i][0], cp[i][0], cq[i][0], gpl);
-                        const float dx = cell_backward(cur.nr[i] + cur.fx, cur.y, cn[i][1], cp[i][1], cq[i][1], gpx);
+                        const float dl = cell_backward<STABLE>(cur.nr[i] + cur.fe, cur.y, cn[i][0], cp[i][0], cq[i][0], gpl);
+                        const float dx = cell_backward<STABLE>(cur.nr[i] + cur.fx, cur.y, cn[i][1], cp[i][1], cq[i][1], gpx);
                         gl += dl; gx += dx;
                         if (a.gxs_planes) {
                             // operand planes of gxs^T . noise: hi = fp16(g s), lo = fp16(g s - hi)
@@ -424,11 +426,13 @@ int launch_row_forward(RowArgs a, cudaStream_t stream) {
     if (smem > 200 * 1024) { set_error("label_dim %d needs %zu B of shared memory per row (limit 200 KiB)", a.L, smem); return 3; }
     static bool configured = false;   // once, to the cap: later launches (e.g. under CUDA-graph capture) make no driver calls
     if (smem > 48 * 1024 && !configured) {
-        cudaError_t e = cudaFuncSetAttribute(probit_row_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(probit_row_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(probit_row_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(fwd): %s", cudaGetErrorString(e)); return 4; }
         configured = true;
     }
-    probit_row_fwd_kernel<<<a.B, kThreads, smem, stream>>>(a);
+    if (a.stable) probit_row_fwd_kernel<true><<<a.B, kThreads, smem, stream>>>(a);
+    else probit_row_fwd_kernel<false><<<a.B, kThreads, smem, stream>>>(a);
     return check_launch("probit_row_fwd_kernel");
 }
 
@@ -443,11 +447,13 @@ int launch_row_backward(RowArgs a, cudaStream_t stream) {
     if (smem > 200 * 1024) { set_error("label_dim %d needs %zu B of shared memory per row (limit 200 KiB)", a.L, smem); return 3; }
     static bool configured = false;
     if (smem > 48 * 1024 && !configured) {
-        cudaError_t e = cudaFuncSetAttribute(probit_row_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(probit_row_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(probit_row_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(bwd): %s", cudaGetErrorString(e)); return 4; }
         configured = true;
     }
-    probit_row_bwd_kernel<<<a.B, kThreads, smem, stream>>>(a);
+    if (a.stable) probit_row_bwd_kernel<true><<<a.B, kThreads, smem, stream>>>(a);
+    else probit_row_bwd_kernel<false><<<a.B, kThreads, smem, stream>>>(a);
     return check_launch("probit_row_bwd_kernel");
 }
 

@@ -12,6 +12,7 @@ struct RowArgs {
     int S, B, L, D;
     int nwl;        // warps along the label axis (filled by the launcher)
     int sanitize;   // MPVAE_FLAG_SANITIZE_DEGENERATE
+    int stable;     // MPVAE_FLAG_STABLE_CDF
     float nll_coeff, c_coeff;
     const float *y, *fe_out, *fx_out, *fe_mu, *fe_logvar, *fx_mu, *fx_logvar;
     int ldn;           // row pitch (floats) of nr and gxs: L rounded up to a multiple of 4 (16-byte aligned rows)

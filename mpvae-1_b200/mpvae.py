@@ -172,5 +172,6 @@ def compute_loss(input_label, fe_out, fe_mu, fe_logvar, fx_out, fx_mu, fx_logvar
 
 probit_elbo = compute_loss
 FLAG_SANITIZE_DEGENERATE = _lib.FLAG_SANITIZE_DEGENERATE
+FLAG_STABLE_CDF = _lib.FLAG_STABLE_CDF
 FLAG_CONTRACT_TENSOR = _lib.FLAG_CONTRACT_TENSOR
 FLAG_CONTRACT_FMA = _lib.FLAG_CONTRACT_FMA

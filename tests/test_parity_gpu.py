@@ -293,6 +293,31 @@ def test_library_noise_in_the_dense_regime(L, Z, B):
         assert H.rel_err_l2(lib_g[k], ref_g[k].cpu().numpy()) <= 5e-4, (k, "vs the torch path")
 
 
+def test_stable_cdf_flag_is_closer_to_the_exact_formula():
+    """MPVAE_FLAG_STABLE_CDF (opt-in; north_star's "numerically stable erfc form"): Phi and 1 - Phi from erfc(|x|/sqrt 2).
+    The reference's own fp32 form 0.5 (1 + erf) cancels in the tails; evaluated in fp64 the same formula is the truth
+    both modes are measured against.  On a tail-heavy case (logit sigma 3) the stable mode must sit much closer to it
+    than the faithful mode does -- which is also why the flag is off by default: parity is with the reference."""
+    from mpvae_b200 import _lib, synth
+    L, Z, B, S = 38, 38, 64, 10
+    inp = synth.loss_inputs(L, Z, B, S, seed=8, sigma=3.0)
+    noise = inp.pop("noise")
+    faithful_o, faithful_g = run_cuda(inp, noise, 0.5, 10.0)
+    stable_o, stable_g = run_cuda(inp, noise, 0.5, 10.0, flags=_lib.FLAG_STABLE_CDF)
+    truth_o, truth_g = run_oracle(inp, noise, 0.5, 10.0, device="cuda:0", dtype=torch.float64)
+    rec = {}
+    for k in ("nll_loss", "nll_loss_x", "total_loss"):
+        rec["faithful_" + k], rec["stable_" + k] = H.rel_err(faithful_o[k], truth_o[k]), H.rel_err(stable_o[k], truth_o[k])
+        assert rec["stable_" + k] <= 2e-6, (k, rec)
+    for k in ("fe_out", "fx_out", "r_sqrt_sigma"):
+        rec["faithful_g_" + k] = H.rel_err_l2(faithful_g[k], truth_g[k])
+        rec["stable_g_" + k] = H.rel_err_l2(stable_g[k], truth_g[k])
+        assert rec["stable_g_" + k] <= 5e-6, (k, rec)
+        assert rec["stable_g_" + k] <= 0.2 * rec["faithful_g_" + k], (k, rec)
+    report(tag="stable_cdf_vs_fp64", **{k: float(v) for k, v in rec.items()})
+    assert float(np.max(np.abs(stable_o["indiv_prob"] - truth_o["indiv_prob"]))) <= 1e-6
+
+
 def test_upstream_on_every_output():
     """Cotangents on all 8 outputs at once (autograd contract)."""
     from mpvae_b200 import synth
