@@ -103,3 +103,20 @@ def test_soft_labels_follow_the_reference_formula(cell_binary):
     E, ll, epos, eneg, _ = truth(recs)
     assert rel(got[:, 1], ll) <= 2e-6
     assert np.all(got[:, 2] == 0.0) and np.all(got[:, 3] == 0.0)      # a soft label is in neither ranking set
+
+
+def test_gxs_bound_constants_are_upper_bounds():
+    """gxs_bound_kernel (probit_rows.cu) scales the fp16 planes of gxs with the a-priori bound
+        |dL/dx| <= 5 |cn| + 17 max(|cp|, |cq|) + 0.4 |gp|
+    i.e. phi/E <= 5, phi/(1-E) <= 5, e^{5E} phi <= 17, phi <= 0.4 over all x, for the clamped E of mpvae.py:177.
+    Checked on a dense grid in fp64 (the maxima are 4.27, 4.27, 16.4 and 0.399)."""
+    x = torch.linspace(-12.0, 12.0, 2_400_001, dtype=torch.float64)
+    eps = torch.tensor(1e-6, dtype=torch.float32).double()
+    cdf = 0.5 * torch.erfc(-x / np.sqrt(2.0))
+    E = cdf * (1.0 - eps) + eps * 0.5
+    om = (1.0 - cdf) * (1.0 - eps) + eps * 0.5
+    phi = torch.exp(-0.5 * x * x) / np.sqrt(2.0 * np.pi)
+    m1, m2 = float((phi / E).max()), float((phi / om).max())
+    m3, m4 = float((torch.exp(5.0 * E) * phi).max()), float(phi.max())
+    assert 4.0 < m1 < 4.5 and 4.0 < m2 < 4.5 and 16.0 < m3 < 16.8 and m4 < 0.4
+    assert max(m1, m2) <= 5.0 / 1.15 and m3 <= 17.0 / 1.03       # the margins the kernel's constants leave
