@@ -1,5 +1,7 @@
 """GPU tests of the individual kernels behind the C-ABI: Philox noise, the contraction engines, and
 size-independent properties of the full path at BASELINE.json's large shapes."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -209,6 +211,8 @@ def test_contract_with_fp16_grid_noise_operand(M, N, K):
     """Engines 4/5: the noise operand (A of nt, B of tn) lies on the fp16 grid like the library's Philox noise, so it
     is a single operand piece and the product takes two MMA passes.  Same accuracy bar as the three-pass product."""
     from mpvae_b200.probit import contract_nt, contract_tn
+    if os.environ.get("MPVAE_TC_CTA") == "1":
+        pytest.skip("the single-piece operand variant exists for CTA pairs only")
     g = torch.Generator(device="cpu").manual_seed(M + 5 * N + 11 * K)
     noise = torch.randn(M, K, generator=g).half().float().to(DEV)
     r = ((torch.rand(N, K, generator=g) - 0.5) * 0.06).to(DEV)
@@ -230,6 +234,8 @@ def test_contract_with_fp16_grid_noise_operand(M, N, K):
 def test_contract_nt_pitched_rows(engine):
     """The loss kernels keep noise.R^T in rows padded to 16 bytes; the padded and the dense store paths agree bit for bit."""
     from mpvae_b200.probit import contract_nt
+    if engine == 4 and os.environ.get("MPVAE_TC_CTA") == "1":
+        pytest.skip("the single-piece operand variant exists for CTA pairs only")
     g = torch.Generator(device="cpu").manual_seed(77)
     a = torch.randn(1280, 983, generator=g).half().float().to(DEV)
     b = ((torch.rand(983, 983, generator=g) - 0.5) * 0.06).to(DEV)
