@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-step", action="store_true", help="skip the full-training-step (steps/s) leg")
     ap.add_argument("--engine", default="auto", choices=["auto", "fma", "tensor"])
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nvls", "nccl"],
                     help="N>1: how g_R is summed over ranks (peer = inside the backward over NVLink peer memory, "
                          "mpvae_b200.peer.PeerRing, falling back to nccl if the ring cannot be set up on every rank; "
                          "nccl = all-reduce after the backward)")
@@ -230,10 +230,11 @@ def run_b200(a):
     # profiles/r01_peer_allreduce.txt); --exchange nccl = an NCCL all-reduce after the backward.  If any rank fails
     # to set the ring up (CUDA IPC unavailable), every rank falls back to NCCL.
     ring = None
-    if world > 1 and not infer and a.exchange == "peer":
-        from mpvae_b200.peer import PeerRing
+    if world > 1 and not infer and a.exchange in ("peer", "nvls"):
+        from mpvae_b200.peer import NvlsRing, PeerRing
         try:
-            ring = PeerRing(L, Z, dev)
+            # nvls: the chunk owners reduce inside the NVSwitch (multimem.ld_reduce / multimem.st)
+            ring = (NvlsRing if a.exchange == "nvls" else PeerRing)(L, Z, dev)
         except Exception as e:          # noqa: BLE001 -- any failure means "use NCCL", decided collectively below
             print(f"[bench] rank {rank}: peer ring unavailable ({e}); NCCL exchange", file=sys.stderr)
             ring = None
@@ -457,6 +458,8 @@ def run_b200(a):
                    "L": L, "Z": Z, "D": 50, "noise": "philox (on device, inside the step)", "engine": a.engine,
                    "l2": "L2 flushed between timed iterations (252 MB written); per-step CUDA events summed",
                    "exchange": ("none (1 GPU)" if world == 1 else
+                                ("g_R summed inside the NVSwitch (multimem.ld_reduce / multimem.st by the chunk owners), inside "
+                                 "the backward") if (ring is not None and a.exchange == "nvls") else
                                 "g_R summed over NVLink peer memory inside the backward (chunk owners pull, add in rank "
                                 "order, store to every rank)" if ring is not None else "NCCL all-reduce of g_R (fp32) per step")},
         "clocks": clocks,

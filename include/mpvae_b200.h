@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPVAE_ABI_VERSION 8
+#define MPVAE_ABI_VERSION 9
 
 /* flags */
 #define MPVAE_FLAG_SANITIZE_DEGENERATE 0x1u /* rows with n_pos*n_neg == 0 get zero ranking gradient instead of
@@ -101,6 +101,10 @@ typedef struct mpvae_probit_params {
     void *peer_part[8];
     void *peer_g_r[8];
     void *peer_flags[8];
+    /* optional MULTICAST addresses of the same part / g_R buffers (both or neither): the chunk owners then reduce inside
+       the NVSwitch (multimem.ld_reduce / multimem.st) instead of pulling from every peer */
+    void *peer_mc_part;
+    void *peer_mc_g_r;
 } mpvae_probit_params;
 
 /* Peer-memory plumbing for the fields above (CUDA IPC; same node).  handle = 64 opaque bytes + the offset word. */
@@ -109,6 +113,9 @@ uint64_t mpvae_peer_flag_bytes(void);
  * device pointers, this process being `rank`; `step` as peer_step above, shared with the backward's counter). */
 int mpvae_peer_allreduce(void *const *part, void *const *g_r, void *const *flags, int32_t world, int32_t rank,
                          uint32_t step, uint64_t n, void *cuda_stream);
+/* ... with the in-switch reduction when mc_part / mc_g_r (multicast addresses of the same buffers) are given. */
+int mpvae_peer_allreduce_nvls(void *const *part, void *const *g_r, void *const *flags, void *mc_part, void *mc_g_r,
+                              int32_t world, int32_t rank, uint32_t step, uint64_t n, void *cuda_stream);
 int mpvae_peer_alloc(uint64_t bytes, void **ptr, unsigned char handle[64]);
 int mpvae_peer_open(const unsigned char handle[64], void **ptr);
 int mpvae_peer_close(void *ptr);

@@ -314,10 +314,13 @@ int mpvae_probit_backward(const mpvae_probit_params* p, void* cuda_stream) {
             return tc_gemm_tn(gpl, base + w.noise_planes, g_r_out, M, p->L, p->Z, slots + SLOT_ABSMAX_GXS, nullptr, stream, b_exact,
                               tail, tail_bytes);
         const int slabs = peer_slabs();
-        if (slabs == 1) {
+        if (slabs == 1 || (p->peer_mc_part && p->peer_mc_g_r)) {
             if (int rc = tc_gemm_tn(gpl, base + w.noise_planes, g_r_out, M, p->L, p->Z, slots + SLOT_ABSMAX_GXS, nullptr, stream,
                                     b_exact, tail, tail_bytes)) return rc;
             pctx.step = (pctx.step - 1) * 8u + 1u;
+            if (p->peer_mc_part && p->peer_mc_g_r)
+                return launch_peer_reduce_nvls(pctx, static_cast<const float*>(p->peer_mc_part), static_cast<float*>(p->peer_mc_g_r),
+                                               (size_t)p->L * p->Z, stream);
             return launch_peer_reduce(pctx, (size_t)p->L * p->Z, stream);
         }
         // MPVAE_PEER_SLABS > 1 (experiment): g_R is produced in row slabs; while the product computes slab s+1 the
@@ -353,6 +356,9 @@ int mpvae_probit_backward(const mpvae_probit_params* p, void* cuda_stream) {
     if (int rc = launch_contract_tn_fma(a.gxs, nz, g_r_out, M, p->L, p->Z, base + w.fma_partials, w.total - w.fma_partials, stream,
                                         row_pitch(p->L))) return rc;
     if (peer) pctx.step = (pctx.step - 1) * 8u + 1u;      // same step numbering as the slabbed tensor path
+    if (peer && p->peer_mc_part && p->peer_mc_g_r)
+        return launch_peer_reduce_nvls(pctx, static_cast<const float*>(p->peer_mc_part), static_cast<float*>(p->peer_mc_g_r),
+                                       (size_t)p->L * p->Z, stream);
     return peer ? launch_peer_reduce(pctx, (size_t)p->L * p->Z, stream) : 0;
 }
 
@@ -443,6 +449,24 @@ int mpvae_peer_allreduce(void* const* part, void* const* g_r, void* const* flags
         if (!ctx.part[i] || !ctx.g_r[i] || !ctx.flags[i]) { set_error("peer_allreduce: NULL table entry %d", i); return 1; }
     }
     return launch_peer_reduce(ctx, (size_t)n, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int mpvae_peer_allreduce_nvls(void* const* part, void* const* g_r, void* const* flags, void* mc_part, void* mc_g_r, int32_t world,
+                              int32_t rank, uint32_t step, uint64_t n, void* cuda_stream) {
+    if (!part || !g_r || !flags || !mc_part || !mc_g_r || world < 2 || world > 8 || rank < 0 || rank >= world || step == 0 || n == 0) {
+        set_error("peer_allreduce_nvls: bad arguments");
+        return 1;
+    }
+    PeerCtx ctx{};
+    ctx.world = world; ctx.rank = rank; ctx.step = step;
+    for (int i = 0; i < world; ++i) {
+        ctx.part[i] = static_cast<float*>(part[i]);
+        ctx.g_r[i] = static_cast<float*>(g_r[i]);
+        ctx.flags[i] = static_cast<uint32_t*>(flags[i]);
+        if (!ctx.part[i] || !ctx.g_r[i] || !ctx.flags[i]) { set_error("peer_allreduce_nvls: NULL table entry %d", i); return 1; }
+    }
+    return launch_peer_reduce_nvls(ctx, static_cast<const float*>(mc_part), static_cast<float*>(mc_g_r), (size_t)n,
+                                   static_cast<cudaStream_t>(cuda_stream));
 }
 
 int mpvae_peer_alloc(uint64_t bytes, void** ptr, unsigned char handle[64]) {

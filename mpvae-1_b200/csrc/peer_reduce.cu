@@ -175,6 +175,63 @@ peer_reduce_small_kernel(PeerCtx ctx, size_t n) {
     }
 }
 
+// In-switch reduction (NVLS): `mc_part` / `mc_gr` are MULTICAST addresses of the ranks' part / g_R buffers.  One
+// multimem.ld_reduce returns the sum of all ranks' copies of 16 bytes (added inside the NVSwitch), one multimem.st writes
+// the result into every rank's g_R.  A rank receives n / G bytes instead of n (G - 1) / G and sends its broadcast once,
+// but still feeds its whole copy to the switch; measured (profiles/r01_peer_allreduce.txt) it is no faster than the
+// pull kernel at 2 or at 8 GPUs, so it is opt-in.  Same flag protocol.
+__global__ void __launch_bounds__(256)
+peer_reduce_nvls_kernel(PeerCtx ctx, const float* __restrict__ mc_part, float* __restrict__ mc_gr, size_t n) {
+    if (threadIdx.x < ctx.world) wait_flag(ctx.flags[ctx.rank] + threadIdx.x, ctx.step);
+    __syncthreads();
+    const int W = ctx.world;
+    const size_t n4 = (n + 3) / 4, per = (n4 + W - 1) / W, nfull = n / 4;
+    const size_t lo = (size_t)ctx.rank * per, hi = min(n4, lo + per), vhi = min(hi, nfull);
+    // four reductions in flight per thread: a multimem.ld_reduce travels to the switch and back
+    constexpr int U = 4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < vhi; i0 += stride * U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t i = i0 + u * stride;
+            if (i < vhi)
+                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
+                             : "l"(mc_part + 4 * i)
+                             : "memory");
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t i = i0 + u * stride;
+            if (i < vhi)
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_gr + 4 * i), "f"(v[u].x),
+                             "f"(v[u].y), "f"(v[u].z), "f"(v[u].w)
+                             : "memory");
+        }
+    }
+    if (nfull < n4 && nfull >= lo && nfull < hi && blockIdx.x == 0 && threadIdx.x == 0) {
+        for (size_t e = 4 * nfull; e < n; ++e) {       // the last, partial float4: plain peer loads / stores
+            float acc = 0.0f;
+            for (int s = 0; s < W; ++s) acc += ctx.part[s][e];
+            for (int p = 0; p < W; ++p) ctx.g_r[p][e] = acc;
+        }
+    }
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        uint32_t* counter = ctx.flags[ctx.rank] + 16;
+        last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+        if (last) *counter = 0;
+    }
+    __syncthreads();
+    if (last && threadIdx.x < ctx.world) {
+        __threadfence_system();
+        st_release_sys(ctx.flags[threadIdx.x] + 8 + ctx.rank, ctx.step);
+    }
+}
+
 template <int W>
 void launch_reduce_w(const PeerCtx& ctx, size_t n, int ctas, int unroll, cudaStream_t stream) {
     if (unroll >= 4 && W <= 4) peer_reduce_bcast_kernel<W, 4><<<ctas, 256, 0, stream>>>(ctx, n);
@@ -198,6 +255,16 @@ int launch_peer_reduce(const PeerCtx& ctx, size_t n, cudaStream_t stream) {
         default: set_error("peer reduce: world size %d not in [2, 8]", ctx.world); return 1;
     }
     if (int rc = check_launch("peer_reduce_bcast_kernel")) return rc;
+    peer_wait_kernel<<<1, 32, 0, stream>>>(ctx, 1);
+    return check_launch("peer_wait_kernel");
+}
+
+int launch_peer_reduce_nvls(const PeerCtx& ctx, const float* mc_part, float* mc_gr, size_t n, cudaStream_t stream) {
+    if (ctx.world < 2 || ctx.world > 8) { set_error("peer reduce: world size %d not in [2, 8]", ctx.world); return 1; }
+    peer_signal_kernel<<<1, 32, 0, stream>>>(ctx, 0);
+    if (int rc = check_launch("peer_signal_kernel")) return rc;
+    peer_reduce_nvls_kernel<<<kReduceCtas, 256, 0, stream>>>(ctx, mc_part, mc_gr, n);
+    if (int rc = check_launch("peer_reduce_nvls_kernel")) return rc;
     peer_wait_kernel<<<1, 32, 0, stream>>>(ctx, 1);
     return check_launch("peer_wait_kernel");
 }

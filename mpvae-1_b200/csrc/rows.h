@@ -75,6 +75,7 @@ struct PeerCtx {
 size_t peer_flag_bytes();
 int launch_peer_reduce(const PeerCtx& ctx, size_t n, cudaStream_t stream);
 int launch_peer_reduce_small(const PeerCtx& ctx, size_t n, cudaStream_t stream);   // fits beside a GEMM CTA on an SM
+int launch_peer_reduce_nvls(const PeerCtx& ctx, const float* mc_part, float* mc_gr, size_t n, cudaStream_t stream);
 
 // clip_grad_norm_ + Adam over flat buffers (optim.cu)
 size_t grad_norm_workspace();

@@ -13,7 +13,7 @@ import torch.distributed as dist
 
 from mpvae_b200 import synth
 from mpvae_b200.mpvae import compute_loss
-from mpvae_b200.peer import PeerRing
+from mpvae_b200.peer import NvlsRing, PeerRing
 from oracle.probit_elbo_oracle import make_args          # args factory only (no oracle arithmetic is used here)
 
 
@@ -27,7 +27,8 @@ def main():
         inp = synth.loss_inputs(L, Z, B * world, S, seed=11, with_noise=False, label_rate=20.0 / L)
         rows = slice(rank * B, (rank + 1) * B)
         t = {k: torch.from_numpy(v if k == "r_sqrt_sigma" else v[rows]).to(dev) for k, v in inp.items()}
-        ring = PeerRing(L, Z, dev)
+        # PEER_CHECK_RING=nvls: the in-switch reduction (multimem) instead of the pull kernel
+        ring = (NvlsRing if os.environ.get("PEER_CHECK_RING") == "nvls" else PeerRing)(L, Z, dev)
 
         def run(use_ring, step):
             args = make_args(L, Z, n_train_sample=S, noise_seed=5, noise_offset=step)
@@ -83,7 +84,10 @@ def main():
         buf = ring.part.clone()
         want = buf.clone(); dist.all_reduce(want)
         got = ring.allreduce()
-        x_ok = torch.equal(got, want) if world == 2 else bool(((got - want).abs().max() / want.abs().max()) < 1e-6)
+        x_ok = bool(((got - want).abs().max() / want.abs().max()) < 1e-6)
+        gathered = [torch.empty_like(got) for _ in range(world)]
+        dist.all_gather(gathered, got.contiguous())
+        x_ok = x_ok and all(torch.equal(gathered[0], t_) for t_ in gathered)
         t_x_ring, t_x_nccl = time_x(ring.allreduce), time_x(lambda: dist.all_reduce(buf))
         if rank == 0:
             print(f"L={L}: exchange alone ({4 * L * Z / 1e6:.0f} MB): peer {t_x_ring * 1e3:.0f} us, nccl {t_x_nccl * 1e3:.0f} us, equal: {x_ok}")
