@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPVAE_ABI_VERSION 9
+#define MPVAE_ABI_VERSION 10
 
 /* flags */
 #define MPVAE_FLAG_SANITIZE_DEGENERATE 0x1u /* rows with n_pos*n_neg == 0 get zero ranking gradient instead of
@@ -36,12 +36,15 @@ extern "C" {
 #define MPVAE_FLAG_STABLE_CDF          0x8u /* opt-in: Phi and 1 - Phi from erfc(|x| / sqrt 2) (no cancellation in the tails)
                                                instead of the reference's 0.5 (1 + erf) and 1 - E.  More accurate than the
                                                reference, hence NOT within 1e-5 of it in saturated cells. */
+#define MPVAE_FLAG_NO_FUSED_FORWARD    0x10u /* dense regime: run the row forward as its own kernel after the tcgen05 product
+                                               instead of inside it (A/B measurements and cross-checks; same results) */
 
 /* order of the six scalar outputs (first six entries of the 8-tuple at mpvae.py:210) */
 enum { MPVAE_TOTAL = 0, MPVAE_NLL = 1, MPVAE_NLL_X = 2, MPVAE_C = 3, MPVAE_C_X = 4, MPVAE_KL = 5 };
 
 typedef struct mpvae_probit_params {
-    uint32_t struct_bytes; /* = sizeof(mpvae_probit_params); ABI guard */
+    uint32_t struct_bytes; /* = sizeof(mpvae_probit_params), or MPVAE_PARAMS_BASE_BYTES for a caller that stops before
+                              the peer_* fields (single-GPU bindings: the rest then defaults to "off"); ABI guard */
     uint32_t flags;
     int32_t S, B, L, Z, D;
     float nll_coeff; /* args.nll_coeff, mpvae.py:207 */
@@ -105,7 +108,13 @@ typedef struct mpvae_probit_params {
        the NVSwitch (multimem.ld_reduce / multimem.st) instead of pulling from every peer */
     void *peer_mc_part;
     void *peer_mc_g_r;
+    /* optional DEVICE counter added to peer_step inside the exchange kernels and advanced by them after every exchange,
+       so that a captured CUDA graph (which replays the same peer_step) keeps the flag values increasing; NULL = unused */
+    uint32_t *peer_step_dev;
 } mpvae_probit_params;
+
+/* size of the struct up to (not including) peer_world: what a binding without the multi-GPU fields fills in */
+#define MPVAE_PARAMS_BASE_BYTES ((uint32_t)offsetof(mpvae_probit_params, peer_world))
 
 /* Peer-memory plumbing for the fields above (CUDA IPC; same node).  handle = 64 opaque bytes + the offset word. */
 uint64_t mpvae_peer_flag_bytes(void);
@@ -116,6 +125,11 @@ int mpvae_peer_allreduce(void *const *part, void *const *g_r, void *const *flags
 /* ... with the in-switch reduction when mc_part / mc_g_r (multicast addresses of the same buffers) are given. */
 int mpvae_peer_allreduce_nvls(void *const *part, void *const *g_r, void *const *flags, void *mc_part, void *mc_g_r,
                               int32_t world, int32_t rank, uint32_t step, uint64_t n, void *cuda_stream);
+/* 0 while no flag wait of this rank has timed out; otherwise the step number that was given up on (the sums of that
+ * step are invalid; fall back to an NCCL all-reduce).  Waits give up after MPVAE_PEER_TIMEOUT_S seconds (default 120)
+ * instead of trapping, so a slow peer (checkpoint, evaluation, data-loader stall) cannot poison the other contexts.
+ * flags = this rank's own flag block; synchronises the stream it reads on. */
+int mpvae_peer_error(const void *flags, uint32_t *out_step, void *cuda_stream);
 int mpvae_peer_alloc(uint64_t bytes, void **ptr, unsigned char handle[64]);
 int mpvae_peer_open(const unsigned char handle[64], void **ptr);
 int mpvae_peer_close(void *ptr);
@@ -207,6 +221,18 @@ int mpvae_adam_step(void *p, int32_t p_is_f64, const float *g, void *m, void *v,
  * threshold whose 1 - precision <= fdr_cutoff. */
 int mpvae_label_curves(const float *sorted_scores, const float *sorted_targets, int32_t N, int32_t L, double fdr_cutoff,
                        double *out, void *cuda_stream);
+
+/* Per-kernel device times of the loss path, measured with CUDA events recorded on the caller's stream around each
+ * launch group inside mpvae_probit_forward / _backward (bench.py's roofline: the dominant kernel timed INSIDE the step).
+ * mpvae_profile(1) switches it on and clears the records (not under CUDA-graph capture: it creates events);
+ * mpvae_profile_read waits for the recorded events and returns the summed milliseconds and the number of records of
+ * one slot; mpvae_profile_name(slot) names it (NULL past the last slot). */
+enum { MPVAE_PROF_NOISE = 0, MPVAE_PROF_SPLIT_R, MPVAE_PROF_PRODUCT_NT, MPVAE_PROF_ROW_FORWARD, MPVAE_PROF_GXS_BOUND,
+       MPVAE_PROF_ROW_BACKWARD, MPVAE_PROF_PRODUCT_TN, MPVAE_PROF_EXCHANGE, MPVAE_PROF_FUSED_SMALL_FWD,
+       MPVAE_PROF_FUSED_SMALL_BWD, MPVAE_PROF_SLOTS };
+int mpvae_profile(int32_t enable);
+int mpvae_profile_read(int32_t slot, double *total_ms, int32_t *count);
+const char *mpvae_profile_name(int32_t slot);
 
 const char *mpvae_last_error(void);
 int mpvae_abi_version(void);

@@ -12,11 +12,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmpvae_b200.so")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 FLAG_SANITIZE_DEGENERATE = 0x1
 FLAG_CONTRACT_TENSOR = 0x2
 FLAG_CONTRACT_FMA = 0x4
 FLAG_STABLE_CDF = 0x8
+FLAG_NO_FUSED_FORWARD = 0x10
 
 # every symbol include/mpvae_b200.h declares
 EXPORTS = (
@@ -26,6 +27,7 @@ EXPORTS = (
     "mpvae_tc_gemm_nt", "mpvae_tc_gemm_tn", "mpvae_peer_flag_bytes", "mpvae_peer_allreduce", "mpvae_peer_allreduce_nvls", "mpvae_label_curves",
     "mpvae_peer_alloc", "mpvae_peer_open", "mpvae_peer_close", "mpvae_peer_free", "mpvae_contract_workspace_bytes", "mpvae_last_error",
     "mpvae_abi_version", "mpvae_launch_count", "mpvae_batch_metrics", "mpvae_batch_metrics_workspace",
+    "mpvae_peer_error", "mpvae_profile", "mpvae_profile_read", "mpvae_profile_name",
 )
 
 _f = C.c_void_p  # device pointer
@@ -50,7 +52,12 @@ class ProbitParams(C.Structure):
         ("peer_world", C.c_int32), ("peer_rank", C.c_int32), ("peer_step", C.c_uint32), ("peer_reserved", C.c_uint32),
         ("peer_part", _f * 8), ("peer_g_r", _f * 8), ("peer_flags", _f * 8),
         ("peer_mc_part", _f), ("peer_mc_g_r", _f),
+        ("peer_step_dev", _f),
     ]
+
+
+# size of the struct up to (not including) peer_world: MPVAE_PARAMS_BASE_BYTES of the header
+PARAMS_BASE_BYTES = ProbitParams.peer_world.offset
 
 
 class LibraryMissing(RuntimeError):
@@ -129,6 +136,14 @@ def _load():
                                     C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
     lib.mpvae_contract_nt_pitched.restype = C.c_int
     lib.mpvae_contract_nt_pitched.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 5 + [C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.mpvae_peer_error.restype = C.c_int
+    lib.mpvae_peer_error.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p]
+    lib.mpvae_profile.restype = C.c_int
+    lib.mpvae_profile.argtypes = [C.c_int32]
+    lib.mpvae_profile_read.restype = C.c_int
+    lib.mpvae_profile_read.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+    lib.mpvae_profile_name.restype = C.c_char_p
+    lib.mpvae_profile_name.argtypes = [C.c_int32]
     return lib
 
 
@@ -150,3 +165,23 @@ def check(rc: int, what: str):
 
 def launch_count() -> int:
     return int(lib().mpvae_launch_count())
+
+
+def profile(enable: bool):
+    """Switch the library's per-kernel CUDA-event timing on (and clear it) or off (include/mpvae_b200.h)."""
+    check(lib().mpvae_profile(1 if enable else 0), "mpvae_profile")
+
+
+def profile_read() -> dict:
+    """{slot name: (total ms, launches recorded)} since the last `profile(True)`; waits for the recorded events."""
+    out = {}
+    slot = 0
+    while True:
+        name = lib().mpvae_profile_name(slot)
+        if name is None:
+            return out
+        ms, n = C.c_double(), C.c_int32()
+        check(lib().mpvae_profile_read(slot, C.byref(ms), C.byref(n)), "mpvae_profile_read")
+        if n.value:
+            out[name.decode()] = (ms.value, n.value)
+        slot += 1

@@ -1,11 +1,15 @@
 // extern "C" surface of libmpvae_b200 (include/mpvae_b200.h): argument validation, workspace carving and the
 // launch sequence of one forward / backward of the probit ELBO.
 #include <atomic>
+#include <mutex>
 #include <stdlib.h>
 #include <string.h>
+#include <utility>
+#include <vector>
 
 #include "../../include/mpvae_b200.h"
 #include "common.cuh"
+#include "fused_rows.cuh"
 #include "rows.h"
 #include "tc.h"
 
@@ -33,22 +37,50 @@ int check_launch(const char* what) {
 
 namespace {
 
+// ---- per-kernel CUDA-event timing (mpvae_profile*) ----
+struct ProfState {
+    bool on = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool[MPVAE_PROF_SLOTS];
+    int used[MPVAE_PROF_SLOTS] = {};
+};
+ProfState g_prof;
+std::mutex g_prof_mu;
+
+// records an event pair around the launches issued during its lifetime (no-op unless profiling is on)
+struct ProfScope {
+    cudaEvent_t stop = nullptr;
+    cudaStream_t stream;
+    ProfScope(int slot, cudaStream_t st) : stream(st) {
+        if (!g_prof.on) return;
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        auto& pool = g_prof.pool[slot];
+        if (g_prof.used[slot] == (int)pool.size()) {
+            cudaEvent_t e0, e1;
+            if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return;
+            pool.emplace_back(e0, e1);
+        }
+        auto& pr = pool[g_prof.used[slot]++];
+        cudaEventRecord(pr.first, stream);
+        stop = pr.second;
+    }
+    ~ProfScope() { if (stop) cudaEventRecord(stop, stream); }
+};
+
 // Workspace carve-up.  Everything is 256-byte aligned; the same function sizes and places.
 struct Workspace {
     size_t nr, lp, stat, wts, rowaux, rowout, slots, gxs;
+    size_t fuse_part;                             // tensor engine, fused forward: per-(sample-row, tile) partial sums
     size_t noise_f32;                             // FMA engine, library-side noise
     size_t noise_planes, r_planes, gxs_planes;    // tensor engine operand planes (noise planes persist fwd -> bwd)
     size_t fma_partials;                          // FMA engine split-K partials of g_R
     size_t tn_tail;                               // tensor engine: K-slices of the g_R product's last wave
+    size_t slots_bytes;                           // slots + the fused forward's per-tile completion counters
     size_t total;
 };
-// 32-bit slots of the 256-byte `slots` block
+// 32-bit slots of the first 256 bytes of the `slots` block; the per-tile counters of the fused forward follow
 enum { SLOT_COUNTER = 0, SLOT_ABSMAX_R = 1, SLOT_ABSMAX_GXS = 2, SLOT_ABSMAX_GP = 3 /* and 4 */ };
 
-// fp16 operand kind: the row backward writes gxs straight as operand planes (no fp32 cube, no split pass)
-bool direct_gxs_planes() { return tc_f16_kind(); }
-
-// row pitch (floats) of the (S,B,L) scratch cubes nr and gxs: 16-byte aligned rows for vector loads / stores
+// row pitch (floats) of the (S*B, L) scratch matrices nr and gxs: 16-byte aligned rows for vector loads / stores
 int row_pitch(int L) { return (L + 3) & ~3; }
 
 bool use_tensor(uint32_t flags, int S, int B, int L, int Z) {
@@ -60,23 +92,32 @@ bool use_tensor(uint32_t flags, int S, int B, int L, int Z) {
     return Z >= 128 && L >= 128 && (long long)S * B >= 128;
 }
 
+// the product kernel carries the row forward on its math warps (fused_rows.cuh); a group of S sample-rows may reach
+// back one tile at most
+bool use_fused_forward(uint32_t flags, int S, int B, int L, int Z) {
+    return use_tensor(flags, S, B, L, Z) && !(flags & MPVAE_FLAG_NO_FUSED_FORWARD) && S <= kFuseMaxS;
+}
+
 Workspace carve(int S, int B, int L, int Z, bool want_backward, uint32_t flags) {
     Workspace w{};
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t cube = (size_t)S * B * row_pitch(L);
+    const bool tensor = use_tensor(flags, S, B, L, Z);
+    const int M = S * B;
+    const size_t tiles = (size_t)ceil_div(M, 256) * ceil_div(L, 256);
     w.nr = take(cube * sizeof(float));
     w.lp = take((size_t)B * S * 2 * sizeof(double));
     w.stat = take((size_t)B * S * 4 * sizeof(float));
     w.wts = take((size_t)B * S * 2 * sizeof(float));
     w.rowaux = take((size_t)B * 2 * sizeof(float));
     w.rowout = take((size_t)B * 8 * sizeof(double));
-    w.slots = take(256);
+    w.slots_bytes = 256 + (tensor ? align_up(tiles * sizeof(uint32_t), 256) : 0);
+    w.slots = take(w.slots_bytes);
     // everything the forward writes and the backward reads sits before the backward-only buffers, so a forward
     // sized for inference and a forward sized for training place the shared buffers identically
-    const bool tensor = use_tensor(flags, S, B, L, Z);
-    const int M = S * B;
     if (tensor) {
+        w.fuse_part = take((size_t)M * ceil_div(L, 256) * sizeof(FusePart));
         w.noise_planes = take(tc_planes_bytes(M, Z));
         w.r_planes = take(tc_planes_bytes(L, Z));
     } else {
@@ -84,8 +125,8 @@ Workspace carve(int S, int B, int L, int Z, bool want_backward, uint32_t flags) 
     }
     if (want_backward) {
         if (tensor) {
-            if (direct_gxs_planes()) w.tn_tail = take(tc_tail_scratch_bytes());
-            else w.gxs = take(cube * sizeof(float));       // doubles as the tail scratch once it has been split
+            // the row backward writes gxs straight as operand planes (no fp32 cube, no split pass)
+            w.tn_tail = take(tc_tail_scratch_bytes());
             w.gxs_planes = take(tc_planes_bytes(M, L));
         } else {
             w.gxs = take(cube * sizeof(float));
@@ -96,13 +137,22 @@ Workspace carve(int S, int B, int L, int Z, bool want_backward, uint32_t flags) 
     return w;
 }
 
-int validate(const mpvae_probit_params* p, bool backward) {
-    if (p == nullptr) { set_error("params is NULL"); return 1; }
-    if (p->struct_bytes != sizeof(mpvae_probit_params)) {
-        set_error("params.struct_bytes=%u, library expects %zu (ABI %d)", p->struct_bytes, sizeof(mpvae_probit_params),
-                  MPVAE_ABI_VERSION);
-        return 1;
+// A binding that stops before the peer_* fields passes MPVAE_PARAMS_BASE_BYTES; the rest defaults to "off".
+const mpvae_probit_params* normalize(const mpvae_probit_params* p, mpvae_probit_params* tmp) {
+    if (p == nullptr) { set_error("params is NULL"); return nullptr; }
+    if (p->struct_bytes == sizeof(mpvae_probit_params)) return p;
+    if (p->struct_bytes == MPVAE_PARAMS_BASE_BYTES) {
+        memset(tmp, 0, sizeof(*tmp));
+        memcpy(tmp, p, MPVAE_PARAMS_BASE_BYTES);
+        tmp->struct_bytes = sizeof(mpvae_probit_params);
+        return tmp;
     }
+    set_error("params.struct_bytes=%u, library expects %zu (or the base prefix %u) (ABI %d)", p->struct_bytes,
+              sizeof(mpvae_probit_params), MPVAE_PARAMS_BASE_BYTES, MPVAE_ABI_VERSION);
+    return nullptr;
+}
+
+int validate(const mpvae_probit_params* p, bool backward) {
     if (p->S <= 0 || p->B <= 0 || p->L <= 0 || p->Z <= 0 || p->D < 0) {
         set_error("bad sizes S=%d B=%d L=%d Z=%d D=%d (empty batches are handled by the host wrapper)", p->S, p->B, p->L,
                   p->Z, p->D);
@@ -136,30 +186,13 @@ int validate(const mpvae_probit_params* p, bool backward) {
     return 0;
 }
 
-// second stream + events of the overlapped g_R exchange (one process per GPU: created once)
-struct PeerStreams { cudaStream_t side; cudaEvent_t slab[8]; cudaEvent_t joined; };
-PeerStreams* peer_streams() {
-    static PeerStreams ps;
-    static int state = 0;       // 0 = not created, 1 = ok, -1 = failed
-    if (state == 0) {
-        state = -1;
-        if (cudaStreamCreateWithFlags(&ps.side, cudaStreamNonBlocking) != cudaSuccess) { set_error("peer: cudaStreamCreate failed"); return nullptr; }
-        for (int i = 0; i < 8; ++i)
-            if (cudaEventCreateWithFlags(&ps.slab[i], cudaEventDisableTiming) != cudaSuccess) { set_error("peer: cudaEventCreate failed"); return nullptr; }
-        if (cudaEventCreateWithFlags(&ps.joined, cudaEventDisableTiming) != cudaSuccess) { set_error("peer: cudaEventCreate failed"); return nullptr; }
-        state = 1;
-    }
-    if (state != 1) { set_error("peer: streams unavailable"); return nullptr; }
-    return &ps;
-}
-// row slabs of g_R exchanged one behind the other (MPVAE_PEER_SLABS, 1..8; must be the same on every rank)
-int peer_slabs() {
-    static int v = 0;
+long long peer_timeout_cycles() {
+    static long long v = 0;
     if (v == 0) {
-        const char* e = getenv("MPVAE_PEER_SLABS");
-        v = e ? atoi(e) : 1;
-        if (v < 1) v = 1;
-        if (v > 8) v = 8;
+        const char* e = getenv("MPVAE_PEER_TIMEOUT_S");
+        double sec = e ? atof(e) : 120.0;
+        if (sec < 1.0) sec = 1.0;
+        v = (long long)(sec * 1.9e9);        // SM clock <= 1.965 GHz
     }
     return v;
 }
@@ -168,6 +201,9 @@ RowArgs row_args(const mpvae_probit_params* p, const Workspace& w) {
     char* base = static_cast<char*>(p->workspace);
     RowArgs a{};
     a.S = p->S; a.B = p->B; a.L = p->L; a.D = p->D;
+    const bool tensor = use_tensor(p->flags, p->S, p->B, p->L, p->Z);
+    a.row_sb = tensor ? p->S : 1;      // b-major behind the tensor engine, s-major behind the CUDA-core contraction
+    a.row_ss = tensor ? 1 : p->B;
     a.ldn = row_pitch(p->L);
     a.sanitize = (p->flags & MPVAE_FLAG_SANITIZE_DEGENERATE) ? 1 : 0;
     a.stable = (p->flags & MPVAE_FLAG_STABLE_CDF) ? 1 : 0;
@@ -186,12 +222,6 @@ RowArgs row_args(const mpvae_probit_params* p, const Workspace& w) {
     a.g_indiv_prob = p->g_indiv_prob; a.g_indiv_prob_label = p->g_indiv_prob_label;
     a.g_fe_out = p->g_fe_out; a.g_fx_out = p->g_fx_out;
     a.g_fe_mu = p->g_fe_mu; a.g_fe_logvar = p->g_fe_logvar; a.g_fx_mu = p->g_fx_mu; a.g_fx_logvar = p->g_fx_logvar;
-    a.gxs = nullptr;
-    a.gxs_absmax = nullptr;
-    a.gxs_planes = nullptr;
-    a.gxs_plane_elems = 0;
-    a.gxs_pitch = 0;
-    a.gxs_scale = nullptr;
     return a;
 }
 
@@ -206,12 +236,54 @@ int mpvae_abi_version(void) { return MPVAE_ABI_VERSION; }
 const char* mpvae_last_error(void) { return g_err; }
 uint64_t mpvae_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+int mpvae_profile(int32_t enable) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.on = enable != 0;
+    for (int i = 0; i < MPVAE_PROF_SLOTS; ++i) g_prof.used[i] = 0;
+    return 0;
+}
+
+int mpvae_profile_read(int32_t slot, double* total_ms, int32_t* count) {
+    if (slot < 0 || slot >= MPVAE_PROF_SLOTS || !total_ms || !count) { set_error("profile_read: bad arguments"); return 1; }
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    double sum = 0.0;
+    for (int i = 0; i < g_prof.used[slot]; ++i) {
+        auto& pr = g_prof.pool[slot][i];
+        float ms = 0.0f;
+        if (cudaEventSynchronize(pr.second) != cudaSuccess || cudaEventElapsedTime(&ms, pr.first, pr.second) != cudaSuccess) {
+            set_error("profile_read: event query failed");
+            return 2;
+        }
+        sum += ms;
+    }
+    *total_ms = sum;
+    *count = g_prof.used[slot];
+    return 0;
+}
+
+const char* mpvae_profile_name(int32_t slot) {
+    static const char* names[MPVAE_PROF_SLOTS] = {"noise (philox planes / philox normal / split of an external tensor)",
+                                                  "R absmax + split",
+                                                  "product nt (noise.R^T; with the fused row forward in the dense regime)",
+                                                  "row forward / finalize",
+                                                  "gxs bound",
+                                                  "row backward",
+                                                  "product tn (g_R)",
+                                                  "g_R exchange over peer memory",
+                                                  "fused small-regime forward",
+                                                  "fused small-regime backward"};
+    return (slot >= 0 && slot < MPVAE_PROF_SLOTS) ? names[slot] : nullptr;
+}
+
 uint64_t mpvae_workspace_bytes(int32_t S, int32_t B, int32_t L, int32_t Z, int32_t want_backward, uint32_t flags) {
     if (S <= 0 || B <= 0 || L <= 0 || Z <= 0) return 256;
     return carve(S, B, L, Z, want_backward != 0, flags).total;
 }
 
-int mpvae_probit_forward(const mpvae_probit_params* p, void* cuda_stream) {
+int mpvae_probit_forward(const mpvae_probit_params* p_in, void* cuda_stream) {
+    mpvae_probit_params tmp;
+    const mpvae_probit_params* p = normalize(p_in, &tmp);
+    if (!p) return 1;
     if (int rc = validate(p, false)) return rc;
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     // the scratch may be shorter than the backward layout on the inference path; the buffers the forward touches
@@ -221,36 +293,74 @@ int mpvae_probit_forward(const mpvae_probit_params* p, void* cuda_stream) {
     float* nr = reinterpret_cast<float*>(base + w.nr);
     uint32_t* slots = reinterpret_cast<uint32_t*>(base + w.slots);
     const int M = p->S * p->B;
-    cudaError_t e = cudaMemsetAsync(slots, 0, 256, stream);   // last-CTA counter + absmax slots
+    cudaError_t e = cudaMemsetAsync(slots, 0, w.slots_bytes, stream);   // last-CTA counter, absmax slots, tile counters
     if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return 2; }
     int rc;
+    RowArgs a = row_args(p, w);
     if (use_tensor(p->flags, p->S, p->B, p->L, p->Z)) {
         void* npl = base + w.noise_planes;
         void* rpl = base + w.r_planes;
-        if (p->noise) rc = tc_split(p->noise, M, p->Z, npl, nullptr, 0, stream);   // |N(0,1)| fits fp16 at scale 1
-        else rc = tc_philox_planes(npl, p->S, p->B, p->Z, p->noise_b_global, p->noise_row0, p->noise_seed, p->noise_offset, p->noise_offset_dev, stream);
-        if (rc) return rc;
-        if ((rc = tc_split(p->r, p->L, p->Z, rpl, slots + SLOT_ABSMAX_R, 1, stream))) return rc;
-        // library noise sits on the fp16 grid: one plane, two MMA passes
-        // no tail scratch here: K-slicing the last wave would make the summation order of x = noise.R^T depend on
-        // how many rows the call holds, and a row's predictions must not change with the shard it is computed in
-        rc = tc_gemm_nt(npl, rpl, nr, M, p->L, p->Z, nullptr, slots + SLOT_ABSMAX_R, stream, row_pitch(p->L),
-                        (!p->noise && tc_exact_supported()) ? 1 : 0);
-    } else {
-        const float* nz = p->noise;
-        if (!nz) {
-            float* gen = reinterpret_cast<float*>(base + w.noise_f32);
-            if ((rc = launch_philox_normal(gen, p->S, p->B, p->Z, p->noise_b_global, p->noise_row0, p->noise_seed,
-                                           p->noise_offset, p->noise_offset_dev, stream))) return rc;
-            nz = gen;
+        {
+            ProfScope ps(MPVAE_PROF_NOISE, stream);
+            // operand rows are b-major (b * S + s): the S sample-rows of a batch row are neighbours
+            if (p->noise) rc = tc_split(p->noise, M, p->Z, npl, nullptr, 0, stream, 0, p->S, p->B);   // |N(0,1)| fits fp16 at scale 1
+            else rc = tc_philox_planes(npl, p->S, p->B, p->Z, p->noise_b_global, p->noise_row0, p->noise_seed, p->noise_offset, p->noise_offset_dev, stream);
         }
+        if (rc) return rc;
+        {
+            ProfScope ps(MPVAE_PROF_SPLIT_R, stream);
+            rc = tc_split(p->r, p->L, p->Z, rpl, slots + SLOT_ABSMAX_R, 1, stream);
+        }
+        if (rc) return rc;
+        const bool fused = use_fused_forward(p->flags, p->S, p->B, p->L, p->Z);
+        FuseFwd fz{};
+        if (fused) {
+            fz.S = p->S; fz.B = p->B; fz.L = p->L; fz.ldn = row_pitch(p->L);
+            fz.stable = a.stable;
+            fz.y = p->y; fz.fe_out = p->fe_out; fz.fx_out = p->fx_out;
+            fz.nr = nr;
+            fz.indiv_prob = p->indiv_prob; fz.indiv_prob_label = p->indiv_prob_label;
+            fz.part = reinterpret_cast<FusePart*>(base + w.fuse_part);
+            fz.done = slots + 64;
+        }
+        {
+            ProfScope ps(MPVAE_PROF_PRODUCT_NT, stream);
+            // library noise sits on the fp16 grid: one plane, two MMA passes.
+            // No tail scratch here: K-slicing the last wave would make the summation order of x = noise.R^T depend on
+            // how many rows the call holds, and a row's predictions must not change with the shard it is computed in
+            rc = tc_gemm_nt(npl, rpl, nr, M, p->L, p->Z, nullptr, slots + SLOT_ABSMAX_R, stream, row_pitch(p->L), p->noise ? 0 : 1,
+                            nullptr, 0, fused ? &fz : nullptr);
+        }
+        if (rc) return rc;
+        ProfScope ps(MPVAE_PROF_ROW_FORWARD, stream);
+        if (fused) {
+            a.part = fz.part;
+            a.part_tiles = ceil_div(p->L, 256);
+            return launch_row_finalize(a, stream);
+        }
+        return launch_row_forward(a, stream);
+    }
+    const float* nz = p->noise;
+    if (!nz) {
+        ProfScope ps(MPVAE_PROF_NOISE, stream);
+        float* gen = reinterpret_cast<float*>(base + w.noise_f32);
+        if ((rc = launch_philox_normal(gen, p->S, p->B, p->Z, p->noise_b_global, p->noise_row0, p->noise_seed,
+                                       p->noise_offset, p->noise_offset_dev, stream))) return rc;
+        nz = gen;
+    }
+    {
+        ProfScope ps(MPVAE_PROF_PRODUCT_NT, stream);
         rc = launch_contract_nt_fma(nz, p->r, nr, M, p->L, p->Z, stream, row_pitch(p->L));
     }
     if (rc) return rc;
-    return launch_row_forward(row_args(p, w), stream);
+    ProfScope ps(MPVAE_PROF_ROW_FORWARD, stream);
+    return launch_row_forward(a, stream);
 }
 
-int mpvae_probit_backward(const mpvae_probit_params* p, void* cuda_stream) {
+int mpvae_probit_backward(const mpvae_probit_params* p_in, void* cuda_stream) {
+    mpvae_probit_params tmp;
+    const mpvae_probit_params* p = normalize(p_in, &tmp);
+    if (!p) return 1;
     if (int rc = validate(p, true)) return rc;
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     const Workspace w = carve(p->S, p->B, p->L, p->Z, true, p->flags);
@@ -259,14 +369,12 @@ int mpvae_probit_backward(const mpvae_probit_params* p, void* cuda_stream) {
     const bool tensor = use_tensor(p->flags, p->S, p->B, p->L, p->Z);
     RowArgs a = row_args(p, w);
     const int M = p->S * p->B;
-    const bool direct = tensor && p->g_r && direct_gxs_planes();
     if (p->g_r && tensor) {
         // slots 2..4: scale source of the gxs planes, max |g_indiv_prob|, max |g_indiv_prob_label|
         if (cudaMemsetAsync(slots + SLOT_ABSMAX_GXS, 0, 3 * sizeof(uint32_t), stream) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return 2; }
-    }
-    if (direct) {
         // the plane scale comes from an upper bound of |gxs| computed from the saved row statistics, so the row
         // kernel can write the operand planes itself
+        ProfScope ps(MPVAE_PROF_GXS_BOUND, stream);
         if (p->g_indiv_prob) { if (int rc = tc_absmax(p->g_indiv_prob, (size_t)p->B * p->L, slots + SLOT_ABSMAX_GP, stream)) return rc; }
         if (p->g_indiv_prob_label) { if (int rc = tc_absmax(p->g_indiv_prob_label, (size_t)p->B * p->L, slots + SLOT_ABSMAX_GP + 1, stream)) return rc; }
         if (int rc = launch_gxs_bound(a, slots + SLOT_ABSMAX_GP, slots + SLOT_ABSMAX_GXS, stream)) return rc;
@@ -276,9 +384,11 @@ int mpvae_probit_backward(const mpvae_probit_params* p, void* cuda_stream) {
         a.gxs_scale = slots + SLOT_ABSMAX_GXS;
     } else if (p->g_r) {
         a.gxs = reinterpret_cast<float*>(base + w.gxs);
-        if (tensor) a.gxs_absmax = slots + SLOT_ABSMAX_GXS;
     }
-    if (int rc = launch_row_backward(a, stream)) return rc;
+    {
+        ProfScope ps(MPVAE_PROF_ROW_BACKWARD, stream);
+        if (int rc = launch_row_backward(a, stream)) return rc;
+    }
     if (!p->g_r) return 0;
     // data-parallel: the product writes this rank's partial into its own `part` buffer, peer_reduce.cu sums the world's
     // partials over NVLink and leaves the result in every rank's g_r
@@ -292,6 +402,8 @@ int mpvae_probit_backward(const mpvae_probit_params* p, void* cuda_stream) {
             return 1;
         }
         pctx.world = p->peer_world; pctx.rank = p->peer_rank; pctx.step = p->peer_step;
+        pctx.step_dev = p->peer_step_dev; pctx.step_stride = 1;
+        pctx.timeout_cycles = peer_timeout_cycles();
         for (int i = 0; i < p->peer_world; ++i) {
             pctx.part[i] = static_cast<float*>(p->peer_part[i]);
             pctx.g_r[i] = static_cast<float*>(p->peer_g_r[i]);
@@ -300,66 +412,26 @@ int mpvae_probit_backward(const mpvae_probit_params* p, void* cuda_stream) {
         }
         g_r_out = pctx.part[p->peer_rank];
     }
-    if (tensor) {
-        void* gpl = base + w.gxs_planes;
-        void* tail = direct ? static_cast<void*>(base + w.tn_tail) : static_cast<void*>(a.gxs);
-        const size_t tail_bytes = direct ? tc_tail_scratch_bytes() : (size_t)M * row_pitch(p->L) * sizeof(float);
-        if (!direct) {
-            if (int rc = tc_split(a.gxs, M, p->L, gpl, slots + SLOT_ABSMAX_GXS, 0, stream, row_pitch(p->L))) return rc;   // absmax: row kernel
+    {
+        ProfScope ps(MPVAE_PROF_PRODUCT_TN, stream);
+        int rc;
+        if (tensor) {
+            // the noise planes the forward left in the workspace are the MN-major B operand as they are
+            rc = tc_gemm_tn(base + w.gxs_planes, base + w.noise_planes, g_r_out, M, p->L, p->Z, slots + SLOT_ABSMAX_GXS, nullptr, stream,
+                            p->noise ? 0 : 1, base + w.tn_tail, tc_tail_scratch_bytes());
+        } else {
+            const float* nz = p->noise ? p->noise : reinterpret_cast<const float*>(base + w.noise_f32);
+            rc = launch_contract_tn_fma(a.gxs, nz, g_r_out, M, p->L, p->Z, base + w.fma_partials, w.total - w.fma_partials, stream,
+                                        row_pitch(p->L));
         }
-        // the noise planes the forward left in the workspace are the MN-major B operand as they are; the fp32 gxs
-        // cube (when there is one) is dead once it has been split: scratch for the K-sliced tail wave
-        const int b_exact = (!p->noise && tc_exact_supported()) ? 1 : 0;
-        if (!peer)
-            return tc_gemm_tn(gpl, base + w.noise_planes, g_r_out, M, p->L, p->Z, slots + SLOT_ABSMAX_GXS, nullptr, stream, b_exact,
-                              tail, tail_bytes);
-        const int slabs = peer_slabs();
-        if (slabs == 1 || (p->peer_mc_part && p->peer_mc_g_r)) {
-            if (int rc = tc_gemm_tn(gpl, base + w.noise_planes, g_r_out, M, p->L, p->Z, slots + SLOT_ABSMAX_GXS, nullptr, stream,
-                                    b_exact, tail, tail_bytes)) return rc;
-            pctx.step = (pctx.step - 1) * 8u + 1u;
-            if (p->peer_mc_part && p->peer_mc_g_r)
-                return launch_peer_reduce_nvls(pctx, static_cast<const float*>(p->peer_mc_part), static_cast<float*>(p->peer_mc_g_r),
-                                               (size_t)p->L * p->Z, stream);
-            return launch_peer_reduce(pctx, (size_t)p->L * p->Z, stream);
-        }
-        // MPVAE_PEER_SLABS > 1 (experiment): g_R is produced in row slabs; while the product computes slab s+1 the
-        // exchange of slab s runs beside it on a second stream (its CTAs fit into the registers the GEMM CTAs leave
-        // free, peer_reduce.cu).  Measured on 2 x B200 it hides ~35 us of the 126 us exchange at 2 slabs and loses
-        // that again to the shorter GEMMs at 4: not the default.
-        PeerStreams* ps = peer_streams();
-        if (!ps) return 2;
-        const int rows_per_slab = ceil_div(ceil_div(p->L, 256), slabs) * 256;
-        const size_t es = tc_f16_kind() ? 2 : 4;
-        for (int sidx = 0; sidx < slabs; ++sidx) {
-            const int l0 = sidx * rows_per_slab, l1 = l0 + rows_per_slab < p->L ? l0 + rows_per_slab : p->L;
-            if (l0 >= p->L) break;
-            if (int rc = tc_gemm_tn(static_cast<char*>(gpl) + (size_t)l0 * es, base + w.noise_planes, g_r_out + (size_t)l0 * p->Z, M,
-                                    l1 - l0, p->Z, slots + SLOT_ABSMAX_GXS, nullptr, stream, b_exact, tail, tail_bytes,
-                                    tc_pitch(p->L))) return rc;
-            if (cudaEventRecord(ps->slab[sidx], stream) != cudaSuccess || cudaStreamWaitEvent(ps->side, ps->slab[sidx], 0) != cudaSuccess) {
-                set_error("peer: event record / wait failed");
-                return 2;
-            }
-            PeerCtx c = pctx;
-            c.step = (pctx.step - 1) * 8u + (uint32_t)sidx + 1u;
-            for (int i = 0; i < c.world; ++i) { c.part[i] += (size_t)l0 * p->Z; c.g_r[i] += (size_t)l0 * p->Z; }
-            if (int rc = launch_peer_reduce_small(c, (size_t)(l1 - l0) * p->Z, ps->side)) return rc;
-        }
-        if (cudaEventRecord(ps->joined, ps->side) != cudaSuccess || cudaStreamWaitEvent(stream, ps->joined, 0) != cudaSuccess) {
-            set_error("peer: join failed");
-            return 2;
-        }
-        return 0;
+        if (rc) return rc;
     }
-    const float* nz = p->noise ? p->noise : reinterpret_cast<const float*>(base + w.noise_f32);
-    if (int rc = launch_contract_tn_fma(a.gxs, nz, g_r_out, M, p->L, p->Z, base + w.fma_partials, w.total - w.fma_partials, stream,
-                                        row_pitch(p->L))) return rc;
-    if (peer) pctx.step = (pctx.step - 1) * 8u + 1u;      // same step numbering as the slabbed tensor path
-    if (peer && p->peer_mc_part && p->peer_mc_g_r)
+    if (!peer) return 0;
+    ProfScope ps(MPVAE_PROF_EXCHANGE, stream);
+    if (p->peer_mc_part && p->peer_mc_g_r)
         return launch_peer_reduce_nvls(pctx, static_cast<const float*>(p->peer_mc_part), static_cast<float*>(p->peer_mc_g_r),
                                        (size_t)p->L * p->Z, stream);
-    return peer ? launch_peer_reduce(pctx, (size_t)p->L * p->Z, stream) : 0;
+    return launch_peer_reduce(pctx, (size_t)p->L * p->Z, stream);
 }
 
 int mpvae_philox_normal(float* noise, int32_t S, int32_t B, int32_t Z, int32_t B_global, int32_t row0, uint64_t seed,
@@ -410,7 +482,6 @@ int mpvae_contract_nt_pitched(const float* A, const float* Bm, float* C, int32_t
     if (engine == 0) engine = use_tensor(0, 1, M, N, K) ? 2 : 1;
     if (engine >= 2 && engine <= 5) {
         if (!tc_available()) { set_error("contract_nt: tensor engine not built"); return 7; }
-        if (engine >= 4 && !tc_exact_supported()) { set_error("contract_nt: engines 4/5 need the CTA-pair kernel"); return 7; }
         return tc_contract_nt(A, Bm, C, M, N, K, workspace, workspace_bytes, stream, engine == 3 || engine == 5, engine >= 4, ldc,
                               ksplit);
     }
@@ -424,7 +495,6 @@ int mpvae_contract_tn(const float* A, const float* Bm, float* C, int32_t M, int3
     if (engine == 0) engine = use_tensor(0, 1, M, N1, N2) ? 2 : 1;
     if (engine >= 2 && engine <= 5) {
         if (!tc_available()) { set_error("contract_tn: tensor engine not built"); return 7; }
-        if (engine >= 4 && !tc_exact_supported()) { set_error("contract_tn: engines 4/5 need the CTA-pair kernel"); return 7; }
         return tc_contract_tn(A, Bm, C, M, N1, N2, workspace, workspace_bytes, stream, engine == 3 || engine == 5, engine >= 4);
     }
     return launch_contract_tn_fma(A, Bm, C, M, N1, N2, workspace, workspace_bytes, stream);
@@ -442,6 +512,7 @@ int mpvae_peer_allreduce(void* const* part, void* const* g_r, void* const* flags
     }
     PeerCtx ctx{};
     ctx.world = world; ctx.rank = rank; ctx.step = step;
+    ctx.timeout_cycles = peer_timeout_cycles();
     for (int i = 0; i < world; ++i) {
         ctx.part[i] = static_cast<float*>(part[i]);
         ctx.g_r[i] = static_cast<float*>(g_r[i]);
@@ -459,6 +530,7 @@ int mpvae_peer_allreduce_nvls(void* const* part, void* const* g_r, void* const* 
     }
     PeerCtx ctx{};
     ctx.world = world; ctx.rank = rank; ctx.step = step;
+    ctx.timeout_cycles = peer_timeout_cycles();
     for (int i = 0; i < world; ++i) {
         ctx.part[i] = static_cast<float*>(part[i]);
         ctx.g_r[i] = static_cast<float*>(g_r[i]);
@@ -467,6 +539,15 @@ int mpvae_peer_allreduce_nvls(void* const* part, void* const* g_r, void* const* 
     }
     return launch_peer_reduce_nvls(ctx, static_cast<const float*>(mc_part), static_cast<float*>(mc_g_r), (size_t)n,
                                    static_cast<cudaStream_t>(cuda_stream));
+}
+
+int mpvae_peer_error(const void* flags, uint32_t* out_step, void* cuda_stream) {
+    if (!flags || !out_step) { set_error("peer_error: bad arguments"); return 1; }
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    const cudaError_t e = cudaMemcpyAsync(out_step, static_cast<const uint32_t*>(flags) + peer_error_word(), sizeof(uint32_t),
+                                          cudaMemcpyDeviceToHost, stream);
+    if (e != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) { set_error("peer_error: copy failed"); return 2; }
+    return 0;
 }
 
 int mpvae_peer_alloc(uint64_t bytes, void** ptr, unsigned char handle[64]) {

@@ -1,0 +1,179 @@
+// Row math of the probit ELBO forward executed INSIDE the tcgen05 product kernel (contract_tc.cu, FUSE = true).
+//
+// The product noise.R^T keeps the tensor pipe busy but uses ~13 % of an SM's issue slots; the row forward
+// (Phi, log, exp per (sample, row, label) cell, mpvae.py:177-190 / :110-114 / :203-204) is bound by exactly those issue
+// slots and leaves the tensor pipe idle.  So the product kernel carries eight extra "math" warps per CTA that follow a
+// tile or two behind the tensor pipeline: as soon as a 256 x 256 tile of nr = noise.R^T has been stored (and is still
+// in L2), they read it back, add the decoder logits, and reduce
+//     over the labels of the tile  -> per-(sample-row, tile) partial log-likelihoods and ranking factors (FusePart)
+//     over the samples of a row    -> the predictions mean_s E (written once, final)
+// A small finalize kernel (probit_rows.cu) adds the per-tile partials in a fixed order and does the per-row tail.
+//
+// Rows of nr are ordered b-major (m = b * S + s): the S sample-rows of batch row b are neighbours, so the mean over
+// samples is a loop in registers / shared memory of one warp.  A work unit is a "group" = the S rows of one b over the
+// 256 columns of one tile; a group belongs to the tile that holds its LAST row and may reach back into the tile above
+// (S <= 256), whose completion it then also waits for.  Completion is a device-scope counter per tile that the
+// promotion warps of both CTAs of a pair bump after their stores.  Math warps never block the tensor pipeline.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "probit_math.cuh"
+
+namespace mpv {
+
+constexpr int kFuseMathWarps = 8;          // per CTA: two warpgroups
+constexpr int kFuseTileArrivals = 32;      // 16 promotion warps x 2 CTAs bump a tile's counter
+constexpr int kFuseMaxS = 256;             // a group reaches back at most one tile
+
+// partial sums of one sample-row over the labels of one 256-column tile, both branches
+struct __align__(16) FusePart {
+    double lp_l, lp_x;                      // sum_l ll            (label branch, feature branch)
+    float pos_l, neg_l, pos_x, neg_x;       // sum_l exp(-5E) [y = 1], sum_l exp(5E) [y = 0]
+};
+
+struct FuseFwd {
+    int S, B, L, ldn;                       // nr is (B*S, ldn) row-major, rows b-major
+    int stable;                             // MPVAE_FLAG_STABLE_CDF
+    const float *y, *fe_out, *fx_out;       // (B, L)
+    const float* nr;
+    float *indiv_prob, *indiv_prob_label;   // (B, L)
+    FusePart* part;                         // [B*S][tiles_n]
+    unsigned int* done;                     // [tiles_m * tiles_n], zeroed before the launch
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// whole warp: block until the tile's counter says every promotion warp has stored its part
+__device__ __forceinline__ void fuse_wait_tile(const unsigned int* cnt, int lane) {
+    if (lane == 0) {
+        const long long t0 = clock64();
+        while (ld_acquire_gpu(cnt) < (unsigned)kFuseTileArrivals) {
+            __nanosleep(200);
+            if (clock64() - t0 > 8000000000LL) __trap();   // ~4 s: a protocol bug must not hang the GPU
+        }
+    }
+    __syncwarp();
+}
+
+// promotion warp, after the stores of its part of tile `idx`
+__device__ __forceinline__ void fuse_signal_tile(unsigned int* done, int idx, int lane) {
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicAdd(done + idx, 1u);
+}
+
+struct FuseChunk { float y, fe, fx, n0, n1; };
+
+__device__ __forceinline__ void fuse_load(FuseChunk& c, const FuseFwd& f, size_t yoff, size_t r0, bool two, int l) {
+    if (l < f.L) {
+        c.y = __ldg(f.y + yoff + l);
+        c.fe = __ldg(f.fe_out + yoff + l);
+        c.fx = __ldg(f.fx_out + yoff + l);
+        c.n0 = __ldcg(f.nr + r0 + l);
+        c.n1 = two ? __ldcg(f.nr + r0 + f.ldn + l) : 0.0f;
+    }
+}
+
+// One group: batch row b over the columns [c0, c0 + 256) of tile column tn.  pacc: this warp's [2][256] floats.
+template <bool STABLE>
+__device__ __forceinline__ void fuse_group(const FuseFwd& f, int b, int tn, int tiles_n, float* __restrict__ pacc, int lane) {
+    const int c0 = tn * 256;
+    const int ncols = min(256, f.L - c0);
+    const int nch = (ncols + 31) >> 5;
+    const size_t yoff = (size_t)b * f.L;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { pacc[c * 32 + lane] = 0.0f; pacc[256 + c * 32 + lane] = 0.0f; }
+    for (int s0 = 0; s0 < f.S; s0 += 2) {
+        const bool two = s0 + 1 < f.S;
+        const size_t r0 = ((size_t)b * f.S + s0) * f.ldn;
+        double lp00 = 0.0, lp01 = 0.0, lp10 = 0.0, lp11 = 0.0;
+        float pn0[4] = {0.f, 0.f, 0.f, 0.f}, pn1[4] = {0.f, 0.f, 0.f, 0.f};
+        FuseChunk cur, nxt;
+        fuse_load(cur, f, yoff, r0, two, c0 + lane);
+        for (int c = 0; c < nch; ++c) {
+            if (c + 1 < nch) fuse_load(nxt, f, yoff, r0, two, c0 + ((c + 1) << 5) + lane);
+            if (c0 + (c << 5) + lane < f.L) {
+                // same accumulation order as probit_row_fwd_kernel (pairs of samples), so predictions are bit-equal
+                float pl = 0.0f, px = 0.0f;
+                {
+                    const CellFwd cl = cell_forward<STABLE>(cur.n0 + cur.fe, cur.y);   // mpvae.py:168,177
+                    const CellFwd cx = cell_forward<STABLE>(cur.n0 + cur.fx, cur.y);   // mpvae.py:170,180
+                    lp00 += (double)cl.ll; lp01 += (double)cx.ll;
+                    pn0[0] += cl.epos; pn0[1] += cl.eneg; pn0[2] += cx.epos; pn0[3] += cx.eneg;
+                    pl += cl.E; px += cx.E;
+                }
+                if (two) {
+                    const CellFwd cl = cell_forward<STABLE>(cur.n1 + cur.fe, cur.y);
+                    const CellFwd cx = cell_forward<STABLE>(cur.n1 + cur.fx, cur.y);
+                    lp10 += (double)cl.ll; lp11 += (double)cx.ll;
+                    pn1[0] += cl.epos; pn1[1] += cl.eneg; pn1[2] += cx.epos; pn1[3] += cx.eneg;
+                    pl += cl.E; px += cx.E;
+                }
+                pacc[(c << 5) + lane] += pl;              // a lane only ever touches its own entries
+                pacc[256 + (c << 5) + lane] += px;
+            }
+            cur = nxt;
+        }
+        lp00 = warp_sum(lp00); lp01 = warp_sum(lp01);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pn0[q] = warp_sum(pn0[q]);
+        if (two) {
+            lp10 = warp_sum(lp10); lp11 = warp_sum(lp11);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pn1[q] = warp_sum(pn1[q]);
+        }
+        if (lane == 0) {
+            FusePart p;
+            p.lp_l = lp00; p.lp_x = lp01; p.pos_l = pn0[0]; p.neg_l = pn0[1]; p.pos_x = pn0[2]; p.neg_x = pn0[3];
+            f.part[((size_t)b * f.S + s0) * tiles_n + tn] = p;
+            if (two) {
+                p.lp_l = lp10; p.lp_x = lp11; p.pos_l = pn1[0]; p.neg_l = pn1[1]; p.pos_x = pn1[2]; p.neg_x = pn1[3];
+                f.part[((size_t)b * f.S + s0 + 1) * tiles_n + tn] = p;
+            }
+        }
+    }
+    // predictions: mean over samples (mpvae.py:203-204)
+    const float fS = (float)f.S;
+    for (int c = 0; c < nch; ++c) {
+        const int l = c0 + (c << 5) + lane;
+        if (l < f.L) {
+            float sl = 0.0f, sx = 0.0f;
+            sl += pacc[(c << 5) + lane];
+            sx += pacc[256 + (c << 5) + lane];
+            f.indiv_prob_label[yoff + l] = sl / fS;
+            f.indiv_prob[yoff + l] = sx / fS;
+        }
+    }
+}
+
+// The loop of one math warp of a CTA pair over the pair's tiles (`first`, `first + stride`, ... < num_tiles; tiles are
+// numbered tile_m * tiles_n + tile_n).  widx = 0..15 over both CTAs of the pair; groups are dealt round-robin with a
+// running counter so that the 25.6 groups of a tile average out over its 16 warps.
+template <bool STABLE>
+__device__ __forceinline__ void fuse_math_loop(const FuseFwd& f, int first, int stride, int num_tiles, int tiles_n, int widx,
+                                               float* __restrict__ pacc, int lane) {
+    long long J = 0;
+    for (int w = first; w < num_tiles; w += stride) {
+        const int tm = w / tiles_n, tn = w % tiles_n;
+        const int g_lo = (256 * tm) / f.S;                                   // groups whose last row lies in this tile
+        const int g_hi = min(f.B, (256 * (tm + 1)) / f.S);
+        const int ng = g_hi - g_lo;
+        if (ng > 0) {
+            int j = (int)((widx - (J & 15) + 16) & 15);
+            if (j < ng) {
+                fuse_wait_tile(f.done + w, lane);
+                if (g_lo * f.S < 256 * tm) fuse_wait_tile(f.done + w - tiles_n, lane);   // first group starts in the tile above
+                for (; j < ng; j += 16) fuse_group<STABLE>(f, g_lo + j, tn, tiles_n, pacc, lane);
+            }
+            J += ng;
+        }
+    }
+}
+
+}  // namespace mpv

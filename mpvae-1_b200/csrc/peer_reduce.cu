@@ -34,34 +34,46 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// spin until *p == want; a peer that never arrives must not hang the GPU for ever
-__device__ __forceinline__ void wait_flag(const uint32_t* p, uint32_t want) {
+// flags of one rank: [2 phases][8 source ranks] + [16] = CTA counter of the reduce kernel + [17] = error word
+constexpr int kFlagWords = 32;
+constexpr int kErrWord = 17;
+constexpr int kReduceCtas = kNumSMs * 4;
+
+// Spin until *p == want.  A peer that never arrives must not hang the GPU for ever, and a slow one (checkpointing,
+// evaluation, a data-loader stall) must not poison every other rank's context either: after ctx.timeout_cycles the
+// wait gives up WITHOUT trapping and records the failed flag in this rank's error word, which the host reads with
+// mpvae_peer_error() and answers by falling back to NCCL (the sums of that step are then invalid).
+__device__ __forceinline__ void wait_flag(const PeerCtx& ctx, const uint32_t* p, uint32_t want) {
     const long long t0 = clock64();
     while (ld_acquire_sys(p) != want) {
         __nanosleep(100);
-        if (clock64() - t0 > 20000000000LL) __trap();   // ~10 s
+        if (clock64() - t0 > ctx.timeout_cycles) {
+            atomicMax(ctx.flags[ctx.rank] + kErrWord, want);
+            return;
+        }
     }
 }
-
-// flags of one rank: [2 phases][8 source ranks] + [16] = CTA counter of the reduce kernel
-constexpr int kFlagWords = 32;
-constexpr int kReduceCtas = kNumSMs * 4;
+// the step number of this launch: host value plus the optional device counter (CUDA-graph replays)
+__device__ __forceinline__ uint32_t step_of(const PeerCtx& ctx) { return ctx.step + (ctx.step_dev ? *ctx.step_dev : 0u); }
 
 __global__ void peer_signal_kernel(PeerCtx ctx, int phase) {
     const int p = threadIdx.x;
     __threadfence_system();
-    if (p < ctx.world) st_release_sys(ctx.flags[p] + phase * 8 + ctx.rank, ctx.step);
+    if (p < ctx.world) st_release_sys(ctx.flags[p] + phase * 8 + ctx.rank, step_of(ctx));
 }
 
+// the last kernel of an exchange: also advances the device-side step counter for the next replay
 __global__ void peer_wait_kernel(PeerCtx ctx, int phase) {
     const int p = threadIdx.x;
-    if (p < ctx.world) wait_flag(ctx.flags[ctx.rank] + phase * 8 + p, ctx.step);
+    if (p < ctx.world) wait_flag(ctx, ctx.flags[ctx.rank] + phase * 8 + p, step_of(ctx));
+    __syncthreads();
+    if (p == 0 && ctx.step_dev) *ctx.step_dev += ctx.step_stride;
 }
 
 template <int W, int U>   // world size; float4 groups per thread and iteration (all loads are issued before the adds)
 __global__ void __launch_bounds__(256)
 peer_reduce_bcast_kernel(PeerCtx ctx, size_t n) {
-    if (threadIdx.x < W) wait_flag(ctx.flags[ctx.rank] + threadIdx.x, ctx.step);
+    if (threadIdx.x < W) wait_flag(ctx, ctx.flags[ctx.rank] + threadIdx.x, step_of(ctx));
     __syncthreads();
     // this rank's chunk, in units of float4 (the buffers come from cudaMalloc: 256-byte aligned)
     const size_t n4 = (n + 3) / 4, per = (n4 + W - 1) / W;
@@ -115,65 +127,16 @@ peer_reduce_bcast_kernel(PeerCtx ctx, size_t n) {
     __syncthreads();
     if (last && threadIdx.x < W) {
         __threadfence_system();
-        st_release_sys(ctx.flags[threadIdx.x] + 8 + ctx.rank, ctx.step);
+        st_release_sys(ctx.flags[threadIdx.x] + 8 + ctx.rank, step_of(ctx));
     }
 }
 
 }  // namespace
 
 size_t peer_flag_bytes() { return kFlagWords * sizeof(uint32_t); }
+int peer_error_word() { return kErrWord; }
 
-// The same reduction for a slab of g_R that is exchanged WHILE the product computes the next slab: 128 threads and at
-// most 32 registers per thread, so that one such CTA fits into the 4096 registers the GEMM CTA (640 x 96) leaves free on
-// its SM and the two kernels run side by side.
-template <int W>
-__global__ void __launch_bounds__(128, 16)
-peer_reduce_small_kernel(PeerCtx ctx, size_t n) {
-    if (threadIdx.x < W) wait_flag(ctx.flags[ctx.rank] + threadIdx.x, ctx.step);
-    __syncthreads();
-    const size_t n4 = (n + 3) / 4, per = (n4 + W - 1) / W, nfull = n / 4;    // nfull complete float4 groups
-    const size_t lo = (size_t)ctx.rank * per, hi = min(n4, lo + per), vhi = min(hi, nfull);
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < vhi; i += 2 * stride) {
-        const size_t j = i + stride;
-        const bool two = j < vhi;
-        // two groups in flight per thread, sources added in rank order
-        float4 a = reinterpret_cast<const float4*>(ctx.part[0])[i];
-        float4 b = two ? reinterpret_cast<const float4*>(ctx.part[0])[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int s = 1; s < W; ++s) {
-            const float4 t = reinterpret_cast<const float4*>(ctx.part[s])[i];
-            const float4 u = two ? reinterpret_cast<const float4*>(ctx.part[s])[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
-            b.x += u.x; b.y += u.y; b.z += u.z; b.w += u.w;
-        }
-#pragma unroll
-        for (int p = 0; p < W; ++p) {
-            reinterpret_cast<float4*>(ctx.g_r[p])[i] = a;
-            if (two) reinterpret_cast<float4*>(ctx.g_r[p])[j] = b;
-        }
-    }
-    if (nfull < n4 && nfull >= lo && nfull < hi && blockIdx.x == 0 && threadIdx.x == 0) {
-        for (size_t e = 4 * nfull; e < n; ++e) {       // the last, partial float4 of the array
-            float acc = 0.0f;
-            for (int s = 0; s < W; ++s) acc += ctx.part[s][e];
-            for (int p = 0; p < W; ++p) ctx.g_r[p][e] = acc;
-        }
-    }
-    __syncthreads();
-    __shared__ bool last;
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        uint32_t* counter = ctx.flags[ctx.rank] + 16;
-        last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-        if (last) *counter = 0;
-    }
-    __syncthreads();
-    if (last && threadIdx.x < W) {
-        __threadfence_system();
-        st_release_sys(ctx.flags[threadIdx.x] + 8 + ctx.rank, ctx.step);
-    }
-}
+namespace {
 
 // In-switch reduction (NVLS): `mc_part` / `mc_gr` are MULTICAST addresses of the ranks' part / g_R buffers.  One
 // multimem.ld_reduce returns the sum of all ranks' copies of 16 bytes (added inside the NVSwitch), one multimem.st writes
@@ -182,7 +145,7 @@ peer_reduce_small_kernel(PeerCtx ctx, size_t n) {
 // pull kernel at 2 or at 8 GPUs, so it is opt-in.  Same flag protocol.
 __global__ void __launch_bounds__(256)
 peer_reduce_nvls_kernel(PeerCtx ctx, const float* __restrict__ mc_part, float* __restrict__ mc_gr, size_t n) {
-    if (threadIdx.x < ctx.world) wait_flag(ctx.flags[ctx.rank] + threadIdx.x, ctx.step);
+    if (threadIdx.x < ctx.world) wait_flag(ctx, ctx.flags[ctx.rank] + threadIdx.x, step_of(ctx));
     __syncthreads();
     const int W = ctx.world;
     const size_t n4 = (n + 3) / 4, per = (n4 + W - 1) / W, nfull = n / 4;
@@ -228,12 +191,14 @@ peer_reduce_nvls_kernel(PeerCtx ctx, const float* __restrict__ mc_part, float* _
     __syncthreads();
     if (last && threadIdx.x < ctx.world) {
         __threadfence_system();
-        st_release_sys(ctx.flags[threadIdx.x] + 8 + ctx.rank, ctx.step);
+        st_release_sys(ctx.flags[threadIdx.x] + 8 + ctx.rank, step_of(ctx));
     }
 }
 
+}  // namespace
+
 template <int W>
-void launch_reduce_w(const PeerCtx& ctx, size_t n, int ctas, int unroll, cudaStream_t stream) {
+static void launch_reduce_w(const PeerCtx& ctx, size_t n, int ctas, int unroll, cudaStream_t stream) {
     if (unroll >= 4 && W <= 4) peer_reduce_bcast_kernel<W, 4><<<ctas, 256, 0, stream>>>(ctx, n);
     else if (unroll >= 2) peer_reduce_bcast_kernel<W, 2><<<ctas, 256, 0, stream>>>(ctx, n);
     else peer_reduce_bcast_kernel<W, 1><<<ctas, 256, 0, stream>>>(ctx, n);
@@ -265,26 +230,6 @@ int launch_peer_reduce_nvls(const PeerCtx& ctx, const float* mc_part, float* mc_
     if (int rc = check_launch("peer_signal_kernel")) return rc;
     peer_reduce_nvls_kernel<<<kReduceCtas, 256, 0, stream>>>(ctx, mc_part, mc_gr, n);
     if (int rc = check_launch("peer_reduce_nvls_kernel")) return rc;
-    peer_wait_kernel<<<1, 32, 0, stream>>>(ctx, 1);
-    return check_launch("peer_wait_kernel");
-}
-
-// Exchange of one slab on `stream`, with the small-footprint kernel (see above).  ctx pointers already address the slab.
-int launch_peer_reduce_small(const PeerCtx& ctx, size_t n, cudaStream_t stream) {
-    const int ctas = kNumSMs * 4;
-    peer_signal_kernel<<<1, 32, 0, stream>>>(ctx, 0);
-    if (int rc = check_launch("peer_signal_kernel")) return rc;
-    switch (ctx.world) {
-        case 2: peer_reduce_small_kernel<2><<<ctas, 128, 0, stream>>>(ctx, n); break;
-        case 3: peer_reduce_small_kernel<3><<<ctas, 128, 0, stream>>>(ctx, n); break;
-        case 4: peer_reduce_small_kernel<4><<<ctas, 128, 0, stream>>>(ctx, n); break;
-        case 5: peer_reduce_small_kernel<5><<<ctas, 128, 0, stream>>>(ctx, n); break;
-        case 6: peer_reduce_small_kernel<6><<<ctas, 128, 0, stream>>>(ctx, n); break;
-        case 7: peer_reduce_small_kernel<7><<<ctas, 128, 0, stream>>>(ctx, n); break;
-        case 8: peer_reduce_small_kernel<8><<<ctas, 128, 0, stream>>>(ctx, n); break;
-        default: set_error("peer reduce: world size %d not in [2, 8]", ctx.world); return 1;
-    }
-    if (int rc = check_launch("peer_reduce_small_kernel")) return rc;
     peer_wait_kernel<<<1, 32, 0, stream>>>(ctx, 1);
     return check_launch("peer_wait_kernel");
 }

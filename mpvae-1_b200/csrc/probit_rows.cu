@@ -13,6 +13,7 @@
 // hop when nwl > 1); log-likelihood sums are carried in fp64 so the result is independent of the
 // summation order to ~1e-13 (the fp32 reference itself carries ~ulp(lp) of order noise).
 #include "common.cuh"
+#include "fused_rows.cuh"
 #include "probit_math.cuh"
 #include "rows.h"
 
@@ -29,15 +30,18 @@ struct BlockCounts { int npos, nneg; };
 // One lane's inputs for one 32-label chunk and kST samples.
 struct RowChunk { float y, fe, fx, nr[kST]; };
 
-__device__ __forceinline__ void load_chunk(RowChunk& in, const float* __restrict__ nr, const float* __restrict__ yrow,
+// row index of (s, b) in the scratch matrices (RowArgs::row_sb / row_ss)
+__device__ __forceinline__ size_t row_of(const RowArgs& a, int s, int b) { return (size_t)b * a.row_sb + (size_t)s * a.row_ss; }
+
+__device__ __forceinline__ void load_chunk(RowChunk& in, const RowArgs& a, const float* __restrict__ yrow,
                                            const float* __restrict__ ferow, const float* __restrict__ fxrow, int c, int lane,
-                                           int L, int ldn, int S, int B, int b, int s0) {
+                                           int b, int s0) {
     const int l = (c << 5) + lane;
-    if (l < L) {
+    if (l < a.L) {
         in.y = yrow[l]; in.fe = ferow[l]; in.fx = fxrow[l];
 #pragma unroll
         for (int i = 0; i < kST; ++i)
-            in.nr[i] = (s0 + i < S) ? nr[((size_t)(s0 + i) * B + b) * ldn + l] : 0.0f;
+            in.nr[i] = (s0 + i < a.S) ? a.nr[row_of(a, s0 + i, b) * a.ldn + l] : 0.0f;
     }
 }
 
@@ -59,7 +63,9 @@ __device__ __forceinline__ BlockCounts count_labels(const float* __restrict__ yr
     return c;
 }
 
-template <bool STABLE>
+// PARTS: the product kernel's math warps have done the cell work (fused_rows.cuh); this kernel only adds their
+// per-tile partials in a fixed order and runs the per-row tail.
+template <bool STABLE, bool PARTS>
 __global__ void __launch_bounds__(kThreads, 4)
 probit_row_fwd_kernel(const RowArgs a) {
     extern __shared__ float s_pacc[];                 // [nws][2][L] prediction partial sums
@@ -80,10 +86,26 @@ probit_row_fwd_kernel(const RowArgs a) {
     const float* __restrict__ ferow = a.fe_out + (size_t)b * L;
     const float* __restrict__ fxrow = a.fx_out + (size_t)b * L;
 
-    for (int i = tid; i < nws * 2 * L; i += kThreads) s_pacc[i] = 0.0f;
+    if (!PARTS)
+        for (int i = tid; i < nws * 2 * L; i += kThreads) s_pacc[i] = 0.0f;
     const BlockCounts cnt = count_labels(yrow, L, s_cnt);   // contains a __syncthreads()
 
-    const int steps = (S + kST * nws - 1) / (kST * nws);
+    if (PARTS) {
+        for (int s = tid; s < S; s += kThreads) {
+            const FusePart* __restrict__ pp = a.part + ((size_t)b * S + s) * a.part_tiles;
+            double l0 = 0.0, l1 = 0.0;
+            float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+            for (int t = 0; t < a.part_tiles; ++t) {          // fixed order
+                const FusePart p = pp[t];
+                l0 += p.lp_l; l1 += p.lp_x;
+                q0 += p.pos_l; q1 += p.neg_l; q2 += p.pos_x; q3 += p.neg_x;
+            }
+            const size_t o = (size_t)b * S + s;
+            a.lp[o * 2 + 0] = l0; a.lp[o * 2 + 1] = l1;
+            reinterpret_cast<float4*>(a.stat)[o] = make_float4(q0, q1, q2, q3);
+        }
+    }
+    const int steps = PARTS ? 0 : (S + kST * nws - 1) / (kST * nws);
     for (int step = 0; step < steps; ++step) {
         const int s0 = (step * nws + ws) * kST;
         double lp[kST][2];
@@ -99,9 +121,9 @@ probit_row_fwd_kernel(const RowArgs a) {
             // (ncu: 31 % of the stall samples of the unpipelined loop sat on the first use of nr)
             RowChunk cur, nxt;
             int c = wl;
-            if (c < nchunks) load_chunk(cur, a.nr, yrow, ferow, fxrow, c, lane, L, a.ldn, S, B, b, s0);
+            if (c < nchunks) load_chunk(cur, a, yrow, ferow, fxrow, c, lane, b, s0);
             for (; c < nchunks; c += nwl) {
-                if (c + nwl < nchunks) load_chunk(nxt, a.nr, yrow, ferow, fxrow, c + nwl, lane, L, a.ldn, S, B, b, s0);
+                if (c + nwl < nchunks) load_chunk(nxt, a, yrow, ferow, fxrow, c + nwl, lane, b, s0);
                 const int l = (c << 5) + lane;
                 if (l < L) {
                     float pl = 0.0f, px = 0.0f;
@@ -155,7 +177,7 @@ probit_row_fwd_kernel(const RowArgs a) {
 
     // ---- predictions: mean over samples (mpvae.py:203-204) ----
     const float fS = (float)S;
-    for (int l = tid; l < L; l += kThreads) {
+    for (int l = tid; l < (PARTS ? 0 : L); l += kThreads) {
         float sl = 0.0f, sx = 0.0f;
         for (int g = 0; g < nws; ++g) { sl += s_pacc[(size_t)g * 2 * L + l]; sx += s_pacc[(size_t)g * 2 * L + L + l]; }
         a.indiv_prob_label[(size_t)b * L + l] = sl / fS;
@@ -336,9 +358,9 @@ probit_row_bwd_kernel(const RowArgs a) {
         float* __restrict__ gacc = s_gacc + (size_t)ws * 2 * L;
         RowChunk cur, nxt;
         int c = wl;
-        if (c < nchunks) load_chunk(cur, a.nr, yrow, ferow, fxrow, c, lane, L, a.ldn, S, B, b, s0);
+        if (c < nchunks) load_chunk(cur, a, yrow, ferow, fxrow, c, lane, b, s0);
         for (; c < nchunks; c += nwl) {
-            if (c + nwl < nchunks) load_chunk(nxt, a.nr, yrow, ferow, fxrow, c + nwl, lane, L, a.ldn, S, B, b, s0);
+            if (c + nwl < nchunks) load_chunk(nxt, a, yrow, ferow, fxrow, c + nwl, lane, b, s0);
             const int l = (c << 5) + lane;
             if (l < L) {
                 const float gpl = has_gpl ? a.g_indiv_prob_label[(size_t)b * L + l] / fS : 0.0f;
@@ -354,12 +376,12 @@ probit_row_bwd_kernel(const RowArgs a) {
                             // operand planes of gxs^T . noise: hi = fp16(g s), lo = fp16(g s - hi)
                             const float g = (dl + dx) * gscale;
                             const __half hi = __float2half_rn(g);
-                            __half* __restrict__ dst = a.gxs_planes + ((size_t)(s0 + i) * B + b) * a.gxs_pitch + l;
+                            __half* __restrict__ dst = a.gxs_planes + row_of(a, s0 + i, b) * a.gxs_pitch + l;
                             dst[0] = hi;
                             dst[a.gxs_plane_elems] = __float2half_rn(g - __half2float(hi));
                         } else if (a.gxs) {
                             const float g = dl + dx;
-                            a.gxs[((size_t)(s0 + i) * B + b) * a.ldn + l] = g;
+                            a.gxs[row_of(a, s0 + i, b) * a.ldn + l] = g;
                             const unsigned int gb = __float_as_uint(g) & 0x7FFFFFFFu;   // |g| as ordered bits, NaN highest
                             gmax = gb > gmax ? gb : gmax;
                         }
@@ -374,7 +396,7 @@ probit_row_bwd_kernel(const RowArgs a) {
     if (a.gxs_planes) {   // pad columns [L, pitch) of this row's S plane rows
         const int pad = a.gxs_pitch - L;
         for (int i = tid; i < S * pad; i += kThreads) {
-            __half* __restrict__ dst = a.gxs_planes + ((size_t)(i / pad) * B + b) * a.gxs_pitch + L + (i % pad);
+            __half* __restrict__ dst = a.gxs_planes + row_of(a, i / pad, b) * a.gxs_pitch + L + (i % pad);
             dst[0] = __float2half_rn(0.0f);
             dst[a.gxs_plane_elems] = __float2half_rn(0.0f);
         }
@@ -420,20 +442,37 @@ size_t row_smem_bytes(int L) {
     return (size_t)(kWarps / nwl) * 2 * (size_t)L * sizeof(float);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: set once per device, to the cap, so that later launches
+// (e.g. under CUDA-graph capture) make no driver calls
+constexpr int kMaxDevices = 64;
+int device_slot() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+
 int launch_row_forward(RowArgs a, cudaStream_t stream) {
     a.nwl = pick_nwl(a.L);
     const size_t smem = row_smem_bytes(a.L);
     if (smem > 200 * 1024) { set_error("label_dim %d needs %zu B of shared memory per row (limit 200 KiB)", a.L, smem); return 3; }
-    static bool configured = false;   // once, to the cap: later launches (e.g. under CUDA-graph capture) make no driver calls
-    if (smem > 48 * 1024 && !configured) {
-        cudaError_t e = cudaFuncSetAttribute(probit_row_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(probit_row_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    static bool configured[kMaxDevices] = {};
+    const int dev = device_slot();
+    if (smem > 48 * 1024 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(probit_row_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(probit_row_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(fwd): %s", cudaGetErrorString(e)); return 4; }
-        configured = true;
+        configured[dev] = true;
     }
-    if (a.stable) probit_row_fwd_kernel<true><<<a.B, kThreads, smem, stream>>>(a);
-    else probit_row_fwd_kernel<false><<<a.B, kThreads, smem, stream>>>(a);
+    if (a.stable) probit_row_fwd_kernel<true, false><<<a.B, kThreads, smem, stream>>>(a);
+    else probit_row_fwd_kernel<false, false><<<a.B, kThreads, smem, stream>>>(a);
     return check_launch("probit_row_fwd_kernel");
+}
+
+int launch_row_finalize(RowArgs a, cudaStream_t stream) {
+    if (a.part == nullptr || a.part_tiles <= 0) { set_error("row finalize: no partials"); return 1; }
+    a.nwl = pick_nwl(a.L);
+    probit_row_fwd_kernel<false, true><<<a.B, kThreads, 0, stream>>>(a);   // the tail has no cell arithmetic: one instance
+    return check_launch("probit_row_finalize_kernel");
 }
 
 int launch_gxs_bound(RowArgs a, const unsigned int* gp_absmax, unsigned int* out_bits, cudaStream_t stream) {
@@ -445,12 +484,13 @@ int launch_row_backward(RowArgs a, cudaStream_t stream) {
     a.nwl = pick_nwl(a.L);
     const size_t smem = row_smem_bytes(a.L);
     if (smem > 200 * 1024) { set_error("label_dim %d needs %zu B of shared memory per row (limit 200 KiB)", a.L, smem); return 3; }
-    static bool configured = false;
-    if (smem > 48 * 1024 && !configured) {
+    static bool configured[kMaxDevices] = {};
+    const int dev = device_slot();
+    if (smem > 48 * 1024 && !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(probit_row_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(probit_row_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(bwd): %s", cudaGetErrorString(e)); return 4; }
-        configured = true;
+        configured[dev] = true;
     }
     if (a.stable) probit_row_bwd_kernel<true><<<a.B, kThreads, smem, stream>>>(a);
     else probit_row_bwd_kernel<false><<<a.B, kThreads, smem, stream>>>(a);

@@ -7,16 +7,25 @@
 
 namespace mpv {
 
+struct FusePart;   // fused_rows.cuh
+
 // Arguments of the per-row kernels (probit_rows.cu).  Pointers are device pointers.
 struct RowArgs {
     int S, B, L, D;
+    // row of (sample s, batch row b) in the (S*B)-row scratch matrices nr / gxs / gxs planes = b * row_sb + s * row_ss:
+    // s-major (1, B) behind the CUDA-core contraction, b-major (S, 1) behind the tensor engine
+    int row_sb, row_ss;
     int nwl;        // warps along the label axis (filled by the launcher)
     int sanitize;   // MPVAE_FLAG_SANITIZE_DEGENERATE
     int stable;     // MPVAE_FLAG_STABLE_CDF
     float nll_coeff, c_coeff;
     const float *y, *fe_out, *fx_out, *fe_mu, *fe_logvar, *fx_mu, *fx_logvar;
     int ldn;           // row pitch (floats) of nr and gxs: L rounded up to a multiple of 4 (16-byte aligned rows)
-    const float* nr;   // (S,B,ldn) noise.R^T
+    const float* nr;   // (S*B,ldn) noise.R^T
+    // fused forward (tensor engine): per-(sample-row, tile) partial sums left by the product kernel's math warps; the
+    // finalize kernel adds them over the part_tiles column tiles in a fixed order
+    const FusePart* part;
+    int part_tiles;
     // saved statistics (workspace)
     double* lp;        // (B,S,2)  Bernoulli log-likelihood per sample: label branch, feature branch
     float* stat;       // (B,S,4)  pos_l, neg_l, pos_x, neg_x ranking factors
@@ -43,6 +52,8 @@ struct RowArgs {
 
 size_t row_smem_bytes(int L);
 int launch_row_forward(RowArgs a, cudaStream_t stream);
+// the tail of the forward when the product kernel has already done the cell work (a.part != nullptr)
+int launch_row_finalize(RowArgs a, cudaStream_t stream);
 int launch_row_backward(RowArgs a, cudaStream_t stream);
 // *out_bits = fp32 bits of an upper bound of max |gxs| over the whole batch (NaN for non-sanitised degenerate rows),
 // from the saved per-(row, sample) statistics and the upstream cotangents; gp_absmax: two slots holding max |g_indiv_prob|
@@ -67,14 +78,17 @@ int launch_label_curves(const float* sorted_scores, const float* sorted_targets,
 // g_R summed over ranks through peer memory (peer_reduce.cu)
 struct PeerCtx {
     int world, rank;
-    uint32_t step;
+    uint32_t step;             // flag value of this exchange (strictly increasing, the same on every rank)
+    uint32_t* step_dev;        // optional device counter added to `step` and advanced by step_stride after the exchange
+    uint32_t step_stride;      //   (a captured CUDA graph replays the same launch arguments)
+    long long timeout_cycles;  // a flag wait gives up after this many SM cycles and records the failure (peer_error_word)
     float* part[8];     // every rank's partial g_R (the rank's own product output)
     float* g_r[8];      // every rank's final g_R
     uint32_t* flags[8];
 };
 size_t peer_flag_bytes();
+int peer_error_word();   // index of the error word inside a rank's flag block (0 = no wait has timed out)
 int launch_peer_reduce(const PeerCtx& ctx, size_t n, cudaStream_t stream);
-int launch_peer_reduce_small(const PeerCtx& ctx, size_t n, cudaStream_t stream);   // fits beside a GEMM CTA on an SM
 int launch_peer_reduce_nvls(const PeerCtx& ctx, const float* mc_part, float* mc_gr, size_t n, cudaStream_t stream);
 
 // clip_grad_norm_ + Adam over flat buffers (optim.cu)

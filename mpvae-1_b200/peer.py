@@ -89,18 +89,46 @@ class PeerRing:
 
     def fill(self, p) -> torch.Tensor:
         """Put the peer tables of the next step into `p` (a _lib.ProbitParams); returns the tensor g_R lands in."""
-        self.step += 1
-        p.peer_world, p.peer_rank, p.peer_step = self.world, self.rank, self.step
+        step_dev = getattr(self, "step_dev", None)
+        if step_dev is None:
+            self.step += 1
+            p.peer_world, p.peer_rank, p.peer_step = self.world, self.rank, self.step
+        else:
+            # device counter: flag value = 1 + counter, the kernels bump the counter after every exchange
+            p.peer_world, p.peer_rank, p.peer_step = self.world, self.rank, 1
+            p.peer_step_dev = step_dev.data_ptr()
         for r in range(self.world):
             p.peer_part[r] = self.ptrs["part"][r]
             p.peer_g_r[r] = self.ptrs["g_r"][r]
             p.peer_flags[r] = self.ptrs["flags"][r]
         return self.g_r
 
+    def check(self):
+        """Raise if a flag wait of this rank has ever timed out (a peer was more than MPVAE_PEER_TIMEOUT_S late): the
+        sums of that step are invalid and the caller should fall back to the NCCL all-reduce.  Synchronises the stream."""
+        lib = _lib.lib()
+        step = C.c_uint32(0)
+        with torch.cuda.device(self.device):
+            stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(lib.mpvae_peer_error(C.c_void_p(self.ptrs["flags"][self.rank]), C.byref(step), stream), "mpvae_peer_error")
+        if step.value:
+            raise RuntimeError(f"PeerRing: rank {self.rank} gave up waiting for a peer at exchange step {step.value}")
+
+    def enable_graph_replay(self):
+        """Flag values come from a DEVICE counter the exchange kernels advance themselves, so that a captured CUDA graph
+        (which replays identical launch arguments) keeps them increasing.  Call on every rank before capturing; from
+        then on `fill` hands out the constant base step."""
+        if getattr(self, "step_dev", None) is None:
+            self.step_dev = torch.full((1,), self.step, dtype=torch.int32, device=self.device)
+        return self.step_dev
+
     def allreduce(self, n: int = None):
         """Stand-alone exchange: `self.g_r` (flat, first n floats) = sum over ranks of `self.part`."""
         lib = _lib.lib()
         n = self.L * self.Z if n is None else int(n)
+        if getattr(self, "step_dev", None) is not None:
+            raise RuntimeError("PeerRing.allreduce is not available once enable_graph_replay() has moved the step counter "
+                               "to the device")
         self.step += 1
         tables = []
         for name in ("part", "g_r", "flags"):
@@ -108,9 +136,8 @@ class PeerRing:
             tables.append(arr)
         with torch.cuda.device(self.device):
             stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-            # flag values: eight per step (the backward exchanges g_R in up to eight slabs, each with its own number)
             _lib.check(lib.mpvae_peer_allreduce(tables[0], tables[1], tables[2], self.world, self.rank,
-                                                (self.step - 1) * 8 + 1, n, stream),
+                                                self.step, n, stream),
                        "mpvae_peer_allreduce")
         return self.g_r
 
@@ -193,7 +220,7 @@ class NvlsRing(PeerRing):
             stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             _lib.check(lib.mpvae_peer_allreduce_nvls(tables[0], tables[1], tables[2], C.c_void_p(self.mc_part),
                                                      C.c_void_p(self.mc_g_r), self.world, self.rank,
-                                                     (self.step - 1) * 8 + 1, n, stream), "mpvae_peer_allreduce_nvls")
+                                                     self.step, n, stream), "mpvae_peer_allreduce_nvls")
         return self.g_r
 
     def close(self):

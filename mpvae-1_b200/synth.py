@@ -73,3 +73,11 @@ def loss_inputs(label_dim: int, z_dim: int, batch: int, n_sample: int, *, seed: 
 
 def features(batch: int, feature_dim: int, rng: np.random.RandomState) -> np.ndarray:
     return rng.standard_normal((batch, feature_dim)).astype(np.float32)
+
+
+def make_args(label_dim: int, z_dim: int, n_train_sample: int = 10, n_test_sample: int = 100, mode: str = "train",
+              nll_coeff: float = 0.5, c_coeff: float = 10.0, **extra):
+    """The fields `compute_loss` reads from `args` (mpvae.py:153,158,162,207-208), as the namespace main.py builds."""
+    from types import SimpleNamespace
+    return SimpleNamespace(label_dim=label_dim, z_dim=z_dim, n_train_sample=n_train_sample,
+                           n_test_sample=n_test_sample, mode=mode, nll_coeff=nll_coeff, c_coeff=c_coeff, **extra)

@@ -137,28 +137,42 @@ def test_contract_tn_fma(M, N1, N2):
 
 # ----------------------------------------------------------------------------- full-size properties
 def _run(inp, noise, args, scale=None, rows=None):
+    """`noise` None = the library's own Philox draw (args carries seed / offset); a row slice then draws the rows of the
+    GLOBAL batch it covers (dp_global_batch / dp_row0), exactly as a data-parallel rank would."""
+    import copy
     from mpvae_b200.mpvae import compute_loss
     sel = (lambda v: v) if rows is None else (lambda v: v[rows])
     t = {k: (torch.from_numpy(sel(v)) if k != "r_sqrt_sigma" else torch.from_numpy(v)).to(DEV).requires_grad_(k != "y")
          for k, v in inp.items()}
-    nz = torch.from_numpy(noise if rows is None else noise[:, rows]).to(DEV)
+    kw = {}
+    if noise is not None:
+        kw["noise"] = torch.from_numpy(noise if rows is None else noise[:, rows]).to(DEV)
+    else:
+        args = copy.copy(args)
+        args.dp_global_batch = inp["y"].shape[0]
+        args.dp_row0 = 0 if rows is None else rows.start
     out = compute_loss(t["y"], t["fe_out"], t["fe_mu"], t["fe_logvar"], t["fx_out"], t["fx_mu"], t["fx_logvar"],
-                       t["r_sqrt_sigma"], args, noise=nz)
+                       t["r_sqrt_sigma"], args, **kw)
     (out[0] * (1.0 if scale is None else scale)).backward()
     return out, {k: t[k].grad for k in H.GRAD_KEYS}
 
 
-@pytest.mark.parametrize("name,L,Z,B", [("eurlex_z10", 3993, 10, 1024), ("delicious", 983, 983, 128)])
-def test_full_size_properties(name, L, Z, B):
+@pytest.mark.parametrize("name,L,Z,B,library_noise", [("eurlex_z10", 3993, 10, 1024, False),
+                                                      ("delicious", 983, 983, 128, False),
+                                                      ("delicious_philox", 983, 983, 128, True),
+                                                      ("eurlex_philox", 3993, 3993, 1024, True)])
+def test_full_size_properties(name, L, Z, B, library_noise):
     """BASELINE.json full sizes, through properties that need no O(L^2) oracle:
       * every loss term is a mean over rows => halves recombine: term = (term_A + term_B) / 2, grads likewise
       * the backward is linear in the upstream cotangent
-      * predictions are probabilities inside the clamp [eps/2, 1 - eps/2]"""
+      * predictions are probabilities inside the clamp [eps/2, 1 - eps/2]
+    `eurlex_philox` is bench.py's headline configuration exactly: S10 B1024 L3993 Z3993, library Philox noise, two-pass
+    tensor product with the row forward fused into it."""
     from mpvae_b200 import synth
     S = 10
-    inp = synth.loss_inputs(L, Z, B, S, seed=3, label_rate=20.0 / L)
-    noise = inp.pop("noise")
-    args = orc.make_args(L, Z, n_train_sample=S)
+    inp = synth.loss_inputs(L, Z, B, S, seed=3, label_rate=20.0 / L, with_noise=not library_noise)
+    noise = None if library_noise else inp.pop("noise")
+    args = orc.make_args(L, Z, n_train_sample=S, noise_seed=777, noise_offset=5)
     full, g_full = _run(inp, noise, args)
     half = B // 2
     a, g_a = _run(inp, noise, args, rows=slice(0, half))
@@ -167,7 +181,9 @@ def test_full_size_properties(name, L, Z, B):
         assert H.rel_err(full[i].item(), 0.5 * (a[i].item() + b[i].item())) <= 2e-6, i
     assert torch.equal(full[6][:half], a[6]) and torch.equal(full[6][half:], b[6])
     recombined = 0.5 * (g_a["r_sqrt_sigma"] + g_b["r_sqrt_sigma"])
-    assert H.rel_err(g_full["r_sqrt_sigma"].cpu().numpy(), recombined.cpu().numpy()) <= 1e-5
+    err_r = H.rel_err(g_full["r_sqrt_sigma"].cpu().numpy(), recombined.cpu().numpy())
+    _tc_report(test="halves_recombine", name=name, err_g_r=err_r)
+    assert err_r <= 1e-5
     assert H.rel_err(g_full["fe_out"][:half].cpu().numpy(), 0.5 * g_a["fe_out"].cpu().numpy()) <= 1e-6
     _, g_scaled = _run(inp, noise, args, scale=-2.5)
     for k in H.GRAD_KEYS:
@@ -211,8 +227,6 @@ def test_contract_with_fp16_grid_noise_operand(M, N, K):
     """Engines 4/5: the noise operand (A of nt, B of tn) lies on the fp16 grid like the library's Philox noise, so it
     is a single operand piece and the product takes two MMA passes.  Same accuracy bar as the three-pass product."""
     from mpvae_b200.probit import contract_nt, contract_tn
-    if os.environ.get("MPVAE_TC_CTA") == "1":
-        pytest.skip("the single-piece operand variant exists for CTA pairs only")
     g = torch.Generator(device="cpu").manual_seed(M + 5 * N + 11 * K)
     noise = torch.randn(M, K, generator=g).half().float().to(DEV)
     r = ((torch.rand(N, K, generator=g) - 0.5) * 0.06).to(DEV)
@@ -234,8 +248,6 @@ def test_contract_with_fp16_grid_noise_operand(M, N, K):
 def test_contract_nt_pitched_rows(engine):
     """The loss kernels keep noise.R^T in rows padded to 16 bytes; the padded and the dense store paths agree bit for bit."""
     from mpvae_b200.probit import contract_nt
-    if engine == 4 and os.environ.get("MPVAE_TC_CTA") == "1":
-        pytest.skip("the single-piece operand variant exists for CTA pairs only")
     g = torch.Generator(device="cpu").manual_seed(77)
     a = torch.randn(1280, 983, generator=g).half().float().to(DEV)
     b = ((torch.rand(983, 983, generator=g) - 0.5) * 0.06).to(DEV)
