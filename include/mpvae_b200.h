@@ -36,8 +36,11 @@ extern "C" {
 #define MPVAE_FLAG_STABLE_CDF          0x8u /* opt-in: Phi and 1 - Phi from erfc(|x| / sqrt 2) (no cancellation in the tails)
                                                instead of the reference's 0.5 (1 + erf) and 1 - E.  More accurate than the
                                                reference, hence NOT within 1e-5 of it in saturated cells. */
-#define MPVAE_FLAG_NO_FUSED_FORWARD    0x10u /* dense regime: run the row forward as its own kernel after the tcgen05 product
-                                               instead of inside it (A/B measurements and cross-checks; same results) */
+#define MPVAE_FLAG_FUSED_FORWARD        0x10u /* dense regime, opt-in: run the row forward on extra "math" warps INSIDE the tcgen05
+                                               product kernel (csrc/fused_rows.cuh) instead of as its own kernel after it.
+                                               Same results bit for bit; measured slower on B200 (the product's register
+                                               accumulators leave room for 8 math warps per SM, a quarter of what the row
+                                               math needs to hide its latencies: profiles/r02_fused_forward.md) */
 
 /* order of the six scalar outputs (first six entries of the 8-tuple at mpvae.py:210) */
 enum { MPVAE_TOTAL = 0, MPVAE_NLL = 1, MPVAE_NLL_X = 2, MPVAE_C = 3, MPVAE_C_X = 4, MPVAE_KL = 5 };

@@ -17,7 +17,7 @@ FLAG_SANITIZE_DEGENERATE = 0x1
 FLAG_CONTRACT_TENSOR = 0x2
 FLAG_CONTRACT_FMA = 0x4
 FLAG_STABLE_CDF = 0x8
-FLAG_NO_FUSED_FORWARD = 0x10
+FLAG_FUSED_FORWARD = 0x10
 
 # every symbol include/mpvae_b200.h declares
 EXPORTS = (

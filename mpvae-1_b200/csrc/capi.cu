@@ -69,6 +69,7 @@ struct ProfScope {
 // Workspace carve-up.  Everything is 256-byte aligned; the same function sizes and places.
 struct Workspace {
     size_t nr, lp, stat, wts, rowaux, rowout, slots, gxs;
+    size_t e_l, e_x;                              // training: clamped probabilities of both branches, kept for the backward
     size_t fuse_part;                             // tensor engine, fused forward: per-(sample-row, tile) partial sums
     size_t noise_f32;                             // FMA engine, library-side noise
     size_t noise_planes, r_planes, gxs_planes;    // tensor engine operand planes (noise planes persist fwd -> bwd)
@@ -95,7 +96,7 @@ bool use_tensor(uint32_t flags, int S, int B, int L, int Z) {
 // the product kernel carries the row forward on its math warps (fused_rows.cuh); a group of S sample-rows may reach
 // back one tile at most
 bool use_fused_forward(uint32_t flags, int S, int B, int L, int Z) {
-    return use_tensor(flags, S, B, L, Z) && !(flags & MPVAE_FLAG_NO_FUSED_FORWARD) && S <= kFuseMaxS;
+    return use_tensor(flags, S, B, L, Z) && (flags & MPVAE_FLAG_FUSED_FORWARD) && S <= kFuseMaxS;
 }
 
 Workspace carve(int S, int B, int L, int Z, bool want_backward, uint32_t flags) {
@@ -124,6 +125,8 @@ Workspace carve(int S, int B, int L, int Z, bool want_backward, uint32_t flags) 
         w.noise_f32 = take((size_t)M * Z * sizeof(float));
     }
     if (want_backward) {
+        w.e_l = take(cube * sizeof(float));
+        w.e_x = take(cube * sizeof(float));
         if (tensor) {
             // the row backward writes gxs straight as operand planes (no fp32 cube, no split pass)
             w.tn_tail = take(tc_tail_scratch_bytes());
@@ -297,6 +300,13 @@ int mpvae_probit_forward(const mpvae_probit_params* p_in, void* cuda_stream) {
     if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return 2; }
     int rc;
     RowArgs a = row_args(p, w);
+    // a scratch block sized for the backward means a training call: the forward keeps E for it (same placement in
+    // both layouts: the backward-only buffers follow everything the forward shares)
+    const Workspace wb = carve(p->S, p->B, p->L, p->Z, true, p->flags);
+    if (p->workspace_bytes >= wb.total) {
+        a.E_l = reinterpret_cast<float*>(base + wb.e_l);
+        a.E_x = reinterpret_cast<float*>(base + wb.e_x);
+    }
     if (use_tensor(p->flags, p->S, p->B, p->L, p->Z)) {
         void* npl = base + w.noise_planes;
         void* rpl = base + w.r_planes;
@@ -320,6 +330,7 @@ int mpvae_probit_forward(const mpvae_probit_params* p_in, void* cuda_stream) {
             fz.y = p->y; fz.fe_out = p->fe_out; fz.fx_out = p->fx_out;
             fz.nr = nr;
             fz.indiv_prob = p->indiv_prob; fz.indiv_prob_label = p->indiv_prob_label;
+            fz.E_l = a.E_l; fz.E_x = a.E_x;
             fz.part = reinterpret_cast<FusePart*>(base + w.fuse_part);
             fz.done = slots + 64;
         }
@@ -368,6 +379,8 @@ int mpvae_probit_backward(const mpvae_probit_params* p_in, void* cuda_stream) {
     uint32_t* slots = reinterpret_cast<uint32_t*>(base + w.slots);
     const bool tensor = use_tensor(p->flags, p->S, p->B, p->L, p->Z);
     RowArgs a = row_args(p, w);
+    a.E_l = reinterpret_cast<float*>(base + w.e_l);
+    a.E_x = reinterpret_cast<float*>(base + w.e_x);
     const int M = p->S * p->B;
     if (p->g_r && tensor) {
         // slots 2..4: scale source of the gxs planes, max |g_indiv_prob|, max |g_indiv_prob_label|

@@ -39,6 +39,7 @@ struct FuseFwd {
     const float *y, *fe_out, *fx_out;       // (B, L)
     const float* nr;
     float *indiv_prob, *indiv_prob_label;   // (B, L)
+    float *E_l, *E_x;                       // (B*S, ldn) clamped probabilities kept for the backward, or nullptr
     FusePart* part;                         // [B*S][tiles_n]
     unsigned int* done;                     // [tiles_m * tiles_n], zeroed before the launch
 };
@@ -107,6 +108,7 @@ __device__ __forceinline__ void fuse_group(const FuseFwd& f, int b, int tn, int 
                     lp00 += (double)cl.ll; lp01 += (double)cx.ll;
                     pn0[0] += cl.epos; pn0[1] += cl.eneg; pn0[2] += cx.epos; pn0[3] += cx.eneg;
                     pl += cl.E; px += cx.E;
+                    if (f.E_l) { const size_t o = r0 + c0 + (c << 5) + lane; f.E_l[o] = cl.E; f.E_x[o] = cx.E; }
                 }
                 if (two) {
                     const CellFwd cl = cell_forward<STABLE>(cur.n1 + cur.fe, cur.y);
@@ -114,6 +116,7 @@ __device__ __forceinline__ void fuse_group(const FuseFwd& f, int b, int tn, int 
                     lp10 += (double)cl.ll; lp11 += (double)cx.ll;
                     pn1[0] += cl.epos; pn1[1] += cl.eneg; pn1[2] += cx.epos; pn1[3] += cx.eneg;
                     pl += cl.E; px += cx.E;
+                    if (f.E_l) { const size_t o = r0 + f.ldn + c0 + (c << 5) + lane; f.E_l[o] = cl.E; f.E_x[o] = cx.E; }
                 }
                 pacc[(c << 5) + lane] += pl;              // a lane only ever touches its own entries
                 pacc[256 + (c << 5) + lane] += px;

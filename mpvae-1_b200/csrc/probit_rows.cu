@@ -137,6 +137,10 @@ probit_row_fwd_kernel(const RowArgs a) {
                             pn[i][0] += cl.epos; pn[i][1] += cl.eneg;
                             pn[i][2] += cx.epos; pn[i][3] += cx.eneg;
                             pl += cl.E; px += cx.E;
+                            if (a.E_l) {   // kept for the backward (training)
+                                const size_t o = row_of(a, s0 + i, b) * a.ldn + l;
+                                a.E_l[o] = cl.E; a.E_x[o] = cx.E;
+                            }
                         }
                     }
                     pacc[l] += pl;
@@ -428,6 +432,107 @@ probit_row_bwd_kernel(const RowArgs a) {
     }
 }
 
+// Backward from the SAVED probabilities (training path, faithful mode): no erf, the special functions on the SFU
+// (cell_backward_saved), so the kernel is bound by its HBM streams (reads nr, E_l, E_x; writes the gxs planes) instead of
+// by instruction issue.  A warp owns 64 neighbouring labels of one batch row (a lane: two of them) and walks the S
+// samples with the logit-gradient sums in registers: no shared-memory accumulators, 8-byte loads, 4-byte plane stores.
+// Grid (B, G): the 64-label chunks of a row are dealt out to G CTAs so that small batches still fill the GPU.
+__global__ void __launch_bounds__(kThreads, 4)
+probit_row_bwd_saved_kernel(const RowArgs a) {
+    extern __shared__ float s_coef[];   // [S][6]: cn_l, cn_x, cp_l, cp_x, cq_l, cq_x
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int L = a.L, S = a.S;
+    const RowCoeffs rc = row_coeffs(a, b);
+    for (int s = tid; s < S; s += kThreads) {
+        const size_t o = (size_t)b * S + s;
+        const float4 st = reinterpret_cast<const float4*>(a.stat)[o];
+        const float2 w = reinterpret_cast<const float2*>(a.wts)[o];
+        float* c = s_coef + s * 6;
+        c[0] = rc.cnb[0] * w.x;           c[1] = rc.cnb[1] * w.y;
+        c[2] = -5.0f * rc.kb[0] * st.y;   c[3] = -5.0f * rc.kb[1] * st.w;   // x neg sums
+        c[4] = 5.0f * rc.kb[0] * st.x;    c[5] = 5.0f * rc.kb[1] * st.z;    // x pos sums
+    }
+    __syncthreads();
+    const float fS = (float)S, fB = (float)a.B;
+    const bool has_gp = a.g_indiv_prob != nullptr, has_gpl = a.g_indiv_prob_label != nullptr;
+    const float gscale = a.gxs_planes ? scale_from_absmax_bits(*a.gxs_scale) : 1.0f;
+    // chunks of 64 labels; with operand planes the chunks run to the plane pitch (a multiple of 64): pad columns get zeros
+    const int nchunks = a.gxs_planes ? a.gxs_pitch / 64 : (L + 63) / 64;
+    const size_t yoff = (size_t)b * L;
+    for (int c = blockIdx.y * kWarps + warp; c < nchunks; c += gridDim.y * kWarps) {
+        const int l0 = c * 64 + 2 * lane;
+        const bool in0 = l0 < L, in1 = l0 + 1 < L;
+        float y0 = 0.f, y1 = 0.f, fe0 = 0.f, fe1 = 0.f, fx0 = 0.f, fx1 = 0.f, gpl0 = 0.f, gpl1 = 0.f, gpx0 = 0.f, gpx1 = 0.f;
+        if (in0) { y0 = a.y[yoff + l0]; fe0 = a.fe_out[yoff + l0]; fx0 = a.fx_out[yoff + l0]; }
+        if (in1) { y1 = a.y[yoff + l0 + 1]; fe1 = a.fe_out[yoff + l0 + 1]; fx1 = a.fx_out[yoff + l0 + 1]; }
+        if (has_gpl) { if (in0) gpl0 = a.g_indiv_prob_label[yoff + l0] / fS; if (in1) gpl1 = a.g_indiv_prob_label[yoff + l0 + 1] / fS; }
+        if (has_gp) { if (in0) gpx0 = a.g_indiv_prob[yoff + l0] / fS; if (in1) gpx1 = a.g_indiv_prob[yoff + l0 + 1] / fS; }
+        float gl0 = 0.f, gl1 = 0.f, gx0 = 0.f, gx1 = 0.f;
+        // rows are 16-byte aligned (ldn % 4 == 0) and l0 is even: 8-byte loads; columns [L, ldn) of the cubes are pitch
+        // padding that is never read as a label (in0 / in1)
+        const bool pair = l0 + 1 < a.ldn;
+        float2 nn, el, ex, nn2, el2, ex2;
+        auto load = [&](int s, float2& n_, float2& l_, float2& x_) {
+            n_ = l_ = x_ = make_float2(0.f, 0.f);
+            if (s < S && in0) {
+                const size_t o = row_of(a, s, b) * a.ldn + l0;
+                if (pair) {
+                    n_ = __ldcs(reinterpret_cast<const float2*>(a.nr + o));
+                    l_ = __ldcs(reinterpret_cast<const float2*>(a.E_l + o));
+                    x_ = __ldcs(reinterpret_cast<const float2*>(a.E_x + o));
+                } else {
+                    n_.x = a.nr[o]; l_.x = a.E_l[o]; x_.x = a.E_x[o];
+                }
+            }
+        };
+        load(0, nn, el, ex);
+        for (int s = 0; s < S; ++s) {
+            load(s + 1, nn2, el2, ex2);             // next sample's loads in flight while this one is computed
+            const float* cf = s_coef + s * 6;
+            float d0 = 0.f, d1 = 0.f;
+            if (in0) {
+                const float dl = cell_backward_saved(nn.x + fe0, el.x, y0, cf[0], cf[2], cf[4], gpl0);
+                const float dx = cell_backward_saved(nn.x + fx0, ex.x, y0, cf[1], cf[3], cf[5], gpx0);
+                gl0 += dl; gx0 += dx; d0 = dl + dx;
+            }
+            if (in1) {
+                const float dl = cell_backward_saved(nn.y + fe1, el.y, y1, cf[0], cf[2], cf[4], gpl1);
+                const float dx = cell_backward_saved(nn.y + fx1, ex.y, y1, cf[1], cf[3], cf[5], gpx1);
+                gl1 += dl; gx1 += dx; d1 = dl + dx;
+            }
+            if (a.gxs_planes) {
+                // operand planes of gxs^T . noise: hi = fp16(g s), lo = fp16(g s - hi); two labels per 4-byte store
+                const float g0 = d0 * gscale, g1 = d1 * gscale;
+                const __half2 hi = __floats2half2_rn(g0, g1);
+                const float2 hf = __half22float2(hi);
+                const __half2 lo = __floats2half2_rn(g0 - hf.x, g1 - hf.y);
+                __half* __restrict__ dst = a.gxs_planes + row_of(a, s, b) * a.gxs_pitch + l0;
+                *reinterpret_cast<__half2*>(dst) = hi;
+                *reinterpret_cast<__half2*>(dst + a.gxs_plane_elems) = lo;
+            } else if (a.gxs) {
+                const size_t o = row_of(a, s, b) * a.ldn + l0;
+                if (in0) a.gxs[o] = d0;
+                if (in1) a.gxs[o + 1] = d1;
+            }
+            nn = nn2; el = el2; ex = ex2;
+        }
+        if (in0) { a.g_fe_out[yoff + l0] = gl0; a.g_fx_out[yoff + l0] = gx0; }
+        if (in1) { a.g_fe_out[yoff + l0 + 1] = gl1; a.g_fx_out[yoff + l0 + 1] = gx1; }
+    }
+    if (blockIdx.y == 0) {   // KL gradients: c = a_kl * 0.5 / B
+        const float kc = rc.a_kl * 0.5f / fB;
+        const size_t o = (size_t)b * a.D;
+        for (int d = tid; d < a.D; d += kThreads) {
+            const KlCell k = kl_cell(a.fe_mu[o + d], a.fe_logvar[o + d], a.fx_mu[o + d], a.fx_logvar[o + d]);
+            a.g_fe_mu[o + d] = kc * k.d_fe_mu;
+            a.g_fe_logvar[o + d] = kc * k.d_fe_lv;
+            a.g_fx_mu[o + d] = kc * k.d_fx_mu;
+            a.g_fx_logvar[o + d] = kc * k.d_fx_lv;
+        }
+    }
+}
+
 int pick_nwl(int L) {
     const int nchunks = (L + 31) / 32;
     int nwl = 1;
@@ -481,6 +586,17 @@ int launch_gxs_bound(RowArgs a, const unsigned int* gp_absmax, unsigned int* out
 }
 
 int launch_row_backward(RowArgs a, cudaStream_t stream) {
+    if (a.E_l != nullptr && a.E_x != nullptr && !a.stable) {
+        const size_t smem = (size_t)a.S * 6 * sizeof(float);
+        if (smem > 48 * 1024) { set_error("n_sample %d: per-sample coefficients exceed 48 KiB of shared memory", a.S); return 3; }
+        const int nchunks = a.gxs_planes ? a.gxs_pitch / 64 : (a.L + 63) / 64;
+        // enough CTAs for ~2 waves of 4 resident CTAs per SM, at most one CTA per 8 chunks (a warp each)
+        int gy = ceil_div(2 * 4 * kNumSMs, a.B);
+        if (gy > ceil_div(nchunks, kWarps)) gy = ceil_div(nchunks, kWarps);
+        if (gy < 1) gy = 1;
+        probit_row_bwd_saved_kernel<<<dim3(a.B, gy), kThreads, smem, stream>>>(a);
+        return check_launch("probit_row_bwd_saved_kernel");
+    }
     a.nwl = pick_nwl(a.L);
     const size_t smem = row_smem_bytes(a.L);
     if (smem > 200 * 1024) { set_error("label_dim %d needs %zu B of shared memory per row (limit 200 KiB)", a.L, smem); return 3; }

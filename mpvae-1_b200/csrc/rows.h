@@ -26,6 +26,9 @@ struct RowArgs {
     // finalize kernel adds them over the part_tiles column tiles in a fixed order
     const FusePart* part;
     int part_tiles;
+    // training forward: the clamped probabilities of both branches, (S*B, ldn) each, kept for the backward (which then
+    // needs no erf); nullptr on the inference path
+    float *E_l, *E_x;
     // saved statistics (workspace)
     double* lp;        // (B,S,2)  Bernoulli log-likelihood per sample: label branch, feature branch
     float* stat;       // (B,S,4)  pos_l, neg_l, pos_x, neg_x ranking factors

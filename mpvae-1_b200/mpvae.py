@@ -175,4 +175,4 @@ FLAG_SANITIZE_DEGENERATE = _lib.FLAG_SANITIZE_DEGENERATE
 FLAG_STABLE_CDF = _lib.FLAG_STABLE_CDF
 FLAG_CONTRACT_TENSOR = _lib.FLAG_CONTRACT_TENSOR
 FLAG_CONTRACT_FMA = _lib.FLAG_CONTRACT_FMA
-FLAG_NO_FUSED_FORWARD = _lib.FLAG_NO_FUSED_FORWARD
+FLAG_FUSED_FORWARD = _lib.FLAG_FUSED_FORWARD

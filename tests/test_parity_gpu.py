@@ -294,15 +294,20 @@ def test_library_noise_in_the_dense_regime(L, Z, B):
     assert float(np.max(np.abs(lib_o[6] - ref_o["indiv_prob"]))) <= 5e-6
     # gradients: the same rule as test_tensor_engine_is_as_accurate_as_the_reference -- at least as close to the
     # exact-contraction truth (Frobenius, x2 slack) as the reference's own fp32 torch path, for BOTH routes
+    bad = []
     for k in H.GRAD_KEYS:
         theirs = H.rel_err_l2(ref_g[k], tru_g[k])
         for route, g in (("two_pass", lib_g), ("three_pass", ext_g)):
             mine = H.rel_err_l2(g[k], tru_g[k])
             rec[f"g_{route}_{k}"] = mine
-            assert mine <= max(1e-5, 2.0 * theirs), (route, k, mine, theirs)
+            rec[f"gmax_{route}_{k}"] = H.rel_err(g[k], tru_g[k])
+            if mine > max(1e-5, 2.0 * theirs):
+                bad.append((route, k, mine, theirs))
         rec["ref_" + k] = theirs
+        rec["refmax_" + k] = H.rel_err(ref_g[k], tru_g[k])
         rec["two_vs_three_g_" + k] = H.rel_err_l2(lib_g[k], ext_g[k])
     report(tag=f"library_noise_dense/L{L}_Z{Z}_B{B}", **{k: float(v) for k, v in rec.items()})
+    assert not bad, bad
 
 
 @pytest.mark.parametrize("S,B,L,Z,external", [(10, 128, 983, 983, False), (10, 70, 300, 256, False), (3, 77, 130, 256, True),
@@ -310,8 +315,8 @@ def test_library_noise_in_the_dense_regime(L, Z, B):
                                               (256, 5, 257, 128, False), (10, 1024, 3993, 3993, False)])
 def test_fused_forward_equals_the_separate_row_kernel(S, B, L, Z, external):
     """Dense regime: the row forward runs on math warps inside the tcgen05 product kernel (csrc/fused_rows.cuh), a work
-    unit being the S sample-rows of one batch row over one 256-column tile.  MPVAE_FLAG_NO_FUSED_FORWARD runs the same
-    cells in probit_row_fwd_kernel instead.  Same cell arithmetic and the same sample order for the prediction means:
+    unit being the S sample-rows of one batch row over one 256-column tile (opt-in: MPVAE_FLAG_FUSED_FORWARD); the
+    default runs the same cells in probit_row_fwd_kernel.  Same cell arithmetic and the same sample order for the prediction means:
     predictions must be BIT-equal, scalars equal to a few ulps (the label sums are fp64 in a different order), gradients
     to ~1e-6 (softmax weights from those sums).  Shapes cover groups straddling tile boundaries (S = 3, 7, 100), a
     group as tall as a tile (S = 256), ragged last tiles, and bench.py's headline configuration."""
@@ -330,8 +335,8 @@ def test_fused_forward_equals_the_separate_row_kernel(S, B, L, Z, external):
         torch.cuda.synchronize()
         return [o.detach().cpu().numpy() for o in out], {k: t[k].grad.cpu().numpy() for k in H.GRAD_KEYS}
 
-    fused_o, fused_g = run(0)
-    plain_o, plain_g = run(_lib.FLAG_NO_FUSED_FORWARD)
+    fused_o, fused_g = run(_lib.FLAG_FUSED_FORWARD)
+    plain_o, plain_g = run(0)
     np.testing.assert_array_equal(fused_o[6], plain_o[6])
     np.testing.assert_array_equal(fused_o[7], plain_o[7])
     rec = {}
@@ -342,7 +347,7 @@ def test_fused_forward_equals_the_separate_row_kernel(S, B, L, Z, external):
         rec["g_" + k] = H.rel_err(fused_g[k], plain_g[k])
         assert rec["g_" + k] <= 2e-6, (k, rec["g_" + k])
     report(tag=f"fused_vs_separate/S{S}_B{B}_L{L}_Z{Z}", **{k: float(v) for k, v in rec.items()})
-    again_o, _ = run(0)
+    again_o, _ = run(_lib.FLAG_FUSED_FORWARD)
     for a, b in zip(fused_o, again_o):
         np.testing.assert_array_equal(a, b)             # fixed-order reductions: bit-reproducible
 
