@@ -70,7 +70,7 @@ struct ProfScope {
 struct Workspace {
     size_t nr, lp, stat, wts, rowaux, rowout, slots, gxs;
     size_t e_l, e_x;                              // training: clamped probabilities of both branches, kept for the backward
-    size_t fuse_part;                             // tensor engine, fused forward: per-(sample-row, tile) partial sums
+    size_t fuse_part;                             // forward: per-(sample-row, label chunk) partial sums
     size_t noise_f32;                             // FMA engine, library-side noise
     size_t noise_planes, r_planes, gxs_planes;    // tensor engine operand planes (noise planes persist fwd -> bwd)
     size_t fma_partials;                          // FMA engine split-K partials of g_R
@@ -117,8 +117,8 @@ Workspace carve(int S, int B, int L, int Z, bool want_backward, uint32_t flags) 
     w.slots = take(w.slots_bytes);
     // everything the forward writes and the backward reads sits before the backward-only buffers, so a forward
     // sized for inference and a forward sized for training place the shared buffers identically
+    w.fuse_part = take((size_t)M * row_chunks(L) * sizeof(FusePart));
     if (tensor) {
-        w.fuse_part = take((size_t)M * ceil_div(L, 256) * sizeof(FusePart));
         w.noise_planes = take(tc_planes_bytes(M, Z));
         w.r_planes = take(tc_planes_bytes(L, Z));
     } else {
@@ -220,6 +220,7 @@ RowArgs row_args(const mpvae_probit_params* p, const Workspace& w) {
     a.rowaux = reinterpret_cast<float*>(base + w.rowaux);
     a.rowout = reinterpret_cast<double*>(base + w.rowout);
     a.counter = reinterpret_cast<unsigned int*>(base + w.slots) + SLOT_COUNTER;
+    a.part = reinterpret_cast<const FusePart*>(base + w.fuse_part);
     for (int i = 0; i < 6; ++i) { a.scalars[i] = p->scalars[i]; a.g_scalars[i] = p->g_scalars[i]; }
     a.indiv_prob = p->indiv_prob; a.indiv_prob_label = p->indiv_prob_label;
     a.g_indiv_prob = p->g_indiv_prob; a.g_indiv_prob_label = p->g_indiv_prob_label;

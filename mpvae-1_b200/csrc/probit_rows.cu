@@ -263,6 +263,100 @@ probit_row_fwd_kernel(const RowArgs a) {
     }
 }
 
+// Cell work of the forward, tiled (b, 64-label chunk): a warp owns 64 neighbouring labels of one batch row (a lane: two
+// of them) and walks the S samples with y / logits / the prediction sums in registers -- no shared-memory accumulators,
+// 8-byte loads of nr and 8-byte stores of the saved probabilities.  Per (sample, chunk) the warp reduces the six label
+// sums and leaves them as a FusePart; probit_row_fwd_kernel<.., PARTS> adds the chunks in a fixed order and runs the
+// per-row tail.  Grid (B, G): the chunks of a row are dealt out to G CTAs so that the grid fills the GPU whatever B is.
+template <bool STABLE>
+__global__ void __launch_bounds__(kThreads, 4)
+probit_row_fwd_tiled_kernel(const RowArgs a, FusePart* __restrict__ part, int nchunks) {
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int L = a.L, S = a.S;
+    const size_t yoff = (size_t)b * L;
+    const float fS = (float)S;
+    for (int c = blockIdx.y * kWarps + warp; c < nchunks; c += gridDim.y * kWarps) {
+        const int l0 = c * 64 + 2 * lane;
+        const bool in0 = l0 < L, in1 = l0 + 1 < L;
+        float y0 = 0.f, y1 = 0.f, fe0 = 0.f, fe1 = 0.f, fx0 = 0.f, fx1 = 0.f;
+        if (in0) { y0 = a.y[yoff + l0]; fe0 = a.fe_out[yoff + l0]; fx0 = a.fx_out[yoff + l0]; }
+        if (in1) { y1 = a.y[yoff + l0 + 1]; fe1 = a.fe_out[yoff + l0 + 1]; fx1 = a.fx_out[yoff + l0 + 1]; }
+        // rows are 16-byte aligned (ldn % 4 == 0) and l0 is even: 8-byte accesses; the pitch padding [L, ldn) is never
+        // used as a label (in0 / in1)
+        const bool pair = l0 + 1 < a.ldn;
+        auto load = [&](int s) {
+            float2 n = make_float2(0.f, 0.f);
+            if (s < S && in0) {
+                const size_t o = row_of(a, s, b) * a.ldn + l0;
+                if (pair) n = __ldcs(reinterpret_cast<const float2*>(a.nr + o));
+                else n.x = a.nr[o];
+            }
+            return n;
+        };
+        float accl0 = 0.f, accl1 = 0.f, accx0 = 0.f, accx1 = 0.f;    // prediction sums over samples
+        float2 n0 = load(0), n1 = load(1);
+        for (int s0 = 0; s0 < S; s0 += kST) {
+            const float2 m0 = load(s0 + 2), m1 = load(s0 + 3);        // next pair in flight
+            float pl0 = 0.f, pl1 = 0.f, px0 = 0.f, px1 = 0.f;         // same pairwise order as probit_row_fwd_kernel
+            double lpl[kST], lpx[kST];
+            float pn[kST][4];
+#pragma unroll
+            for (int i = 0; i < kST; ++i) {
+                lpl[i] = lpx[i] = 0.0;
+                pn[i][0] = pn[i][1] = pn[i][2] = pn[i][3] = 0.f;
+                const int s = s0 + i;
+                if (s >= S) continue;
+                const float2 n = i == 0 ? n0 : n1;
+                float2 el = make_float2(0.f, 0.f), ex = make_float2(0.f, 0.f);
+                if (in0) {
+                    const CellFwd cl = cell_forward<STABLE>(n.x + fe0, y0);   // mpvae.py:168,177
+                    const CellFwd cx = cell_forward<STABLE>(n.x + fx0, y0);   // mpvae.py:170,180
+                    lpl[i] += (double)cl.ll; lpx[i] += (double)cx.ll;
+                    pn[i][0] += cl.epos; pn[i][1] += cl.eneg; pn[i][2] += cx.epos; pn[i][3] += cx.eneg;
+                    pl0 += cl.E; px0 += cx.E;
+                    el.x = cl.E; ex.x = cx.E;
+                }
+                if (in1) {
+                    const CellFwd cl = cell_forward<STABLE>(n.y + fe1, y1);
+                    const CellFwd cx = cell_forward<STABLE>(n.y + fx1, y1);
+                    lpl[i] += (double)cl.ll; lpx[i] += (double)cx.ll;
+                    pn[i][0] += cl.epos; pn[i][1] += cl.eneg; pn[i][2] += cx.epos; pn[i][3] += cx.eneg;
+                    pl1 += cl.E; px1 += cx.E;
+                    el.y = cl.E; ex.y = cx.E;
+                }
+                if (a.E_l && in0) {   // kept for the backward (training)
+                    const size_t o = row_of(a, s, b) * a.ldn + l0;
+                    if (pair) {
+                        *reinterpret_cast<float2*>(a.E_l + o) = el;
+                        *reinterpret_cast<float2*>(a.E_x + o) = ex;
+                    } else {
+                        a.E_l[o] = el.x; a.E_x[o] = ex.x;
+                    }
+                }
+            }
+            accl0 += pl0; accl1 += pl1; accx0 += px0; accx1 += px1;
+#pragma unroll
+            for (int i = 0; i < kST; ++i) {
+                if (s0 + i >= S) continue;
+                lpl[i] = warp_sum(lpl[i]); lpx[i] = warp_sum(lpx[i]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) pn[i][q] = warp_sum(pn[i][q]);
+                if (lane == 0) {
+                    FusePart p;
+                    p.lp_l = lpl[i]; p.lp_x = lpx[i];
+                    p.pos_l = pn[i][0]; p.neg_l = pn[i][1]; p.pos_x = pn[i][2]; p.neg_x = pn[i][3];
+                    part[((size_t)b * S + s0 + i) * nchunks + c] = p;
+                }
+            }
+            n0 = m0; n1 = m1;
+        }
+        // predictions: mean over samples (mpvae.py:203-204)
+        if (in0) { a.indiv_prob_label[yoff + l0] = (0.0f + accl0) / fS; a.indiv_prob[yoff + l0] = (0.0f + accx0) / fS; }
+        if (in1) { a.indiv_prob_label[yoff + l0 + 1] = (0.0f + accl1) / fS; a.indiv_prob[yoff + l0 + 1] = (0.0f + accx1) / fS; }
+    }
+}
+
 // Per-row coefficients of the backward (see cell_backward): effective weights of the loss terms = d objective / d term
 // (mpvae.py:207-208 + upstream cotangents), the ranking normaliser k_b and the log-likelihood factor -(a_nll / B).
 struct RowCoeffs { float kb[2], cnb[2], a_kl; };
@@ -472,50 +566,58 @@ probit_row_bwd_saved_kernel(const RowArgs a) {
         // rows are 16-byte aligned (ldn % 4 == 0) and l0 is even: 8-byte loads; columns [L, ldn) of the cubes are pitch
         // padding that is never read as a label (in0 / in1)
         const bool pair = l0 + 1 < a.ldn;
-        float2 nn, el, ex, nn2, el2, ex2;
-        auto load = [&](int s, float2& n_, float2& l_, float2& x_) {
-            n_ = l_ = x_ = make_float2(0.f, 0.f);
+        struct Cell3 { float2 n, l, x; };
+        auto load = [&](int s) {
+            Cell3 v;
+            v.n = v.l = v.x = make_float2(0.f, 0.f);
             if (s < S && in0) {
                 const size_t o = row_of(a, s, b) * a.ldn + l0;
                 if (pair) {
-                    n_ = __ldcs(reinterpret_cast<const float2*>(a.nr + o));
-                    l_ = __ldcs(reinterpret_cast<const float2*>(a.E_l + o));
-                    x_ = __ldcs(reinterpret_cast<const float2*>(a.E_x + o));
+                    v.n = __ldcs(reinterpret_cast<const float2*>(a.nr + o));
+                    v.l = __ldcs(reinterpret_cast<const float2*>(a.E_l + o));
+                    v.x = __ldcs(reinterpret_cast<const float2*>(a.E_x + o));
                 } else {
-                    n_.x = a.nr[o]; l_.x = a.E_l[o]; x_.x = a.E_x[o];
+                    v.n.x = a.nr[o]; v.l.x = a.E_l[o]; v.x.x = a.E_x[o];
                 }
             }
+            return v;
         };
-        load(0, nn, el, ex);
-        for (int s = 0; s < S; ++s) {
-            load(s + 1, nn2, el2, ex2);             // next sample's loads in flight while this one is computed
-            const float* cf = s_coef + s * 6;
-            float d0 = 0.f, d1 = 0.f;
-            if (in0) {
-                const float dl = cell_backward_saved(nn.x + fe0, el.x, y0, cf[0], cf[2], cf[4], gpl0);
-                const float dx = cell_backward_saved(nn.x + fx0, ex.x, y0, cf[1], cf[3], cf[5], gpx0);
-                gl0 += dl; gx0 += dx; d0 = dl + dx;
+        Cell3 cur[2] = {load(0), load(1)};
+        for (int s0 = 0; s0 < S; s0 += 2) {
+            const Cell3 nxt[2] = {load(s0 + 2), load(s0 + 3)};   // the next two samples' loads in flight meanwhile
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int s = s0 + i;
+                if (s >= S) continue;
+                const float* cf = s_coef + s * 6;
+                const Cell3& v = cur[i];
+                float d0 = 0.f, d1 = 0.f;
+                if (in0) {
+                    const float dl = cell_backward_saved(v.n.x + fe0, v.l.x, y0, cf[0], cf[2], cf[4], gpl0);
+                    const float dx = cell_backward_saved(v.n.x + fx0, v.x.x, y0, cf[1], cf[3], cf[5], gpx0);
+                    gl0 += dl; gx0 += dx; d0 = dl + dx;
+                }
+                if (in1) {
+                    const float dl = cell_backward_saved(v.n.y + fe1, v.l.y, y1, cf[0], cf[2], cf[4], gpl1);
+                    const float dx = cell_backward_saved(v.n.y + fx1, v.x.y, y1, cf[1], cf[3], cf[5], gpx1);
+                    gl1 += dl; gx1 += dx; d1 = dl + dx;
+                }
+                if (a.gxs_planes) {
+                    // operand planes of gxs^T . noise: hi = fp16(g s), lo = fp16(g s - hi); two labels per 4-byte store
+                    const float g0 = d0 * gscale, g1 = d1 * gscale;
+                    const __half2 hi = __floats2half2_rn(g0, g1);
+                    const float2 hf = __half22float2(hi);
+                    const __half2 lo = __floats2half2_rn(g0 - hf.x, g1 - hf.y);
+                    __half* __restrict__ dst = a.gxs_planes + row_of(a, s, b) * a.gxs_pitch + l0;
+                    *reinterpret_cast<__half2*>(dst) = hi;
+                    *reinterpret_cast<__half2*>(dst + a.gxs_plane_elems) = lo;
+                } else if (a.gxs) {
+                    const size_t o = row_of(a, s, b) * a.ldn + l0;
+                    if (in0) a.gxs[o] = d0;
+                    if (in1) a.gxs[o + 1] = d1;
+                }
             }
-            if (in1) {
-                const float dl = cell_backward_saved(nn.y + fe1, el.y, y1, cf[0], cf[2], cf[4], gpl1);
-                const float dx = cell_backward_saved(nn.y + fx1, ex.y, y1, cf[1], cf[3], cf[5], gpx1);
-                gl1 += dl; gx1 += dx; d1 = dl + dx;
-            }
-            if (a.gxs_planes) {
-                // operand planes of gxs^T . noise: hi = fp16(g s), lo = fp16(g s - hi); two labels per 4-byte store
-                const float g0 = d0 * gscale, g1 = d1 * gscale;
-                const __half2 hi = __floats2half2_rn(g0, g1);
-                const float2 hf = __half22float2(hi);
-                const __half2 lo = __floats2half2_rn(g0 - hf.x, g1 - hf.y);
-                __half* __restrict__ dst = a.gxs_planes + row_of(a, s, b) * a.gxs_pitch + l0;
-                *reinterpret_cast<__half2*>(dst) = hi;
-                *reinterpret_cast<__half2*>(dst + a.gxs_plane_elems) = lo;
-            } else if (a.gxs) {
-                const size_t o = row_of(a, s, b) * a.ldn + l0;
-                if (in0) a.gxs[o] = d0;
-                if (in1) a.gxs[o + 1] = d1;
-            }
-            nn = nn2; el = el2; ex = ex2;
+            cur[0] = nxt[0]; cur[1] = nxt[1];
         }
         if (in0) { a.g_fe_out[yoff + l0] = gl0; a.g_fx_out[yoff + l0] = gx0; }
         if (in1) { a.g_fe_out[yoff + l0 + 1] = gl1; a.g_fx_out[yoff + l0 + 1] = gx1; }
@@ -556,21 +658,23 @@ int device_slot() {
     return (d >= 0 && d < kMaxDevices) ? d : 0;
 }
 
+int row_chunks(int L) { return (L + 63) / 64; }
+
+// Forward = cell work tiled over (row, 64-label chunk) + the per-row tail over the chunk partials.  a.part must hold
+// B * S * row_chunks(L) FusePart records.
 int launch_row_forward(RowArgs a, cudaStream_t stream) {
-    a.nwl = pick_nwl(a.L);
-    const size_t smem = row_smem_bytes(a.L);
-    if (smem > 200 * 1024) { set_error("label_dim %d needs %zu B of shared memory per row (limit 200 KiB)", a.L, smem); return 3; }
-    static bool configured[kMaxDevices] = {};
-    const int dev = device_slot();
-    if (smem > 48 * 1024 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(probit_row_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(probit_row_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(fwd): %s", cudaGetErrorString(e)); return 4; }
-        configured[dev] = true;
-    }
-    if (a.stable) probit_row_fwd_kernel<true, false><<<a.B, kThreads, smem, stream>>>(a);
-    else probit_row_fwd_kernel<false, false><<<a.B, kThreads, smem, stream>>>(a);
-    return check_launch("probit_row_fwd_kernel");
+    if (a.part == nullptr) { set_error("row forward: no scratch for the chunk partials"); return 1; }
+    const int nchunks = row_chunks(a.L);
+    // enough CTAs for ~2 waves of 4 resident CTAs per SM, at most one CTA per 8 chunks (a warp each)
+    int gy = ceil_div(2 * 4 * kNumSMs, a.B);
+    if (gy > ceil_div(nchunks, kWarps)) gy = ceil_div(nchunks, kWarps);
+    if (gy < 1) gy = 1;
+    FusePart* part = const_cast<FusePart*>(a.part);
+    if (a.stable) probit_row_fwd_tiled_kernel<true><<<dim3(a.B, gy), kThreads, 0, stream>>>(a, part, nchunks);
+    else probit_row_fwd_tiled_kernel<false><<<dim3(a.B, gy), kThreads, 0, stream>>>(a, part, nchunks);
+    if (int rc = check_launch("probit_row_fwd_tiled_kernel")) return rc;
+    a.part_tiles = nchunks;
+    return launch_row_finalize(a, stream);
 }
 
 int launch_row_finalize(RowArgs a, cudaStream_t stream) {
