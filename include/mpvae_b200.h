@@ -237,6 +237,11 @@ int mpvae_profile(int32_t enable);
 int mpvae_profile_read(int32_t slot, double *total_ms, int32_t *count);
 const char *mpvae_profile_name(int32_t slot);
 
+/* Test hook: out[i] = the library's normal-domain logarithm of in[i] (csrc/probit_math.cuh::log_normal, the libdevice logf
+ * main path without its special-case blocks) and ref[i] = logf(in[i]), n device floats each; tests assert bit equality
+ * over the whole domain the loss uses, [4.7e-7, 1]. */
+int mpvae_test_log_normal(const float *in, float *out, float *ref, uint64_t n, void *cuda_stream);
+
 const char *mpvae_last_error(void);
 int mpvae_abi_version(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches claim) */

@@ -448,6 +448,11 @@ int mpvae_probit_backward(const mpvae_probit_params* p_in, void* cuda_stream) {
     return launch_peer_reduce(pctx, (size_t)p->L * p->Z, stream);
 }
 
+int mpvae_test_log_normal(const float* in, float* out, float* ref, uint64_t n, void* cuda_stream) {
+    if (!in || !out || !ref || n == 0) { set_error("test_log_normal: bad arguments"); return 1; }
+    return launch_log_normal_probe(in, out, ref, (size_t)n, static_cast<cudaStream_t>(cuda_stream));
+}
+
 int mpvae_philox_normal(float* noise, int32_t S, int32_t B, int32_t Z, int32_t B_global, int32_t row0, uint64_t seed,
                         uint64_t offset, void* cuda_stream) {
     if (!noise) { set_error("philox: NULL output"); return 1; }

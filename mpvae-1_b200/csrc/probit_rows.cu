@@ -12,6 +12,8 @@
 // rows (L = 14..81) still keep every warp busy.  Reductions over labels are warp shuffles (+ one smem
 // hop when nwl > 1); log-likelihood sums are carried in fp64 so the result is independent of the
 // summation order to ~1e-13 (the fp32 reference itself carries ~ulp(lp) of order noise).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "fused_rows.cuh"
 #include "probit_math.cuh"
@@ -91,18 +93,23 @@ probit_row_fwd_kernel(const RowArgs a) {
     const BlockCounts cnt = count_labels(yrow, L, s_cnt);   // contains a __syncthreads()
 
     if (PARTS) {
-        for (int s = tid; s < S; s += kThreads) {
+        // a warp per sample-row, a lane per chunk (stride 32), then a butterfly: a fixed order whatever the grid was
+        for (int s = warp; s < S; s += kWarps) {
             const FusePart* __restrict__ pp = a.part + ((size_t)b * S + s) * a.part_tiles;
             double l0 = 0.0, l1 = 0.0;
             float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-            for (int t = 0; t < a.part_tiles; ++t) {          // fixed order
+            for (int t = lane; t < a.part_tiles; t += 32) {
                 const FusePart p = pp[t];
                 l0 += p.lp_l; l1 += p.lp_x;
                 q0 += p.pos_l; q1 += p.neg_l; q2 += p.pos_x; q3 += p.neg_x;
             }
-            const size_t o = (size_t)b * S + s;
-            a.lp[o * 2 + 0] = l0; a.lp[o * 2 + 1] = l1;
-            reinterpret_cast<float4*>(a.stat)[o] = make_float4(q0, q1, q2, q3);
+            l0 = warp_sum(l0); l1 = warp_sum(l1);
+            q0 = warp_sum(q0); q1 = warp_sum(q1); q2 = warp_sum(q2); q3 = warp_sum(q3);
+            if (lane == 0) {
+                const size_t o = (size_t)b * S + s;
+                a.lp[o * 2 + 0] = l0; a.lp[o * 2 + 1] = l1;
+                reinterpret_cast<float4*>(a.stat)[o] = make_float4(q0, q1, q2, q3);
+            }
         }
     }
     const int steps = PARTS ? 0 : (S + kST * nws - 1) / (kST * nws);
@@ -263,13 +270,17 @@ probit_row_fwd_kernel(const RowArgs a) {
     }
 }
 
-// Cell work of the forward, tiled (b, 64-label chunk): a warp owns 64 neighbouring labels of one batch row (a lane: two
-// of them) and walks the S samples with y / logits / the prediction sums in registers -- no shared-memory accumulators,
-// 8-byte loads of nr and 8-byte stores of the saved probabilities.  Per (sample, chunk) the warp reduces the six label
-// sums and leaves them as a FusePart; probit_row_fwd_kernel<.., PARTS> adds the chunks in a fixed order and runs the
-// per-row tail.  Grid (B, G): the chunks of a row are dealt out to G CTAs so that the grid fills the GPU whatever B is.
-template <bool STABLE>
-__global__ void __launch_bounds__(kThreads, 4)
+// Cell work of the forward, tiled (b, 128-label chunk): a warp owns 128 neighbouring labels of one batch row (a lane:
+// four of them) and walks the S samples with y / logits / the prediction sums in registers -- no shared-memory
+// accumulators, 16-byte loads of nr and 16-byte stores of the saved probabilities.  Per (sample, chunk) the warp reduces
+// the six label sums and leaves them as a FusePart; probit_row_fwd_kernel<.., PARTS> adds the chunks in a fixed order
+// and runs the per-row tail.  Grid (B, G): the chunks of a row are dealt out to G CTAs so that the grid fills the GPU
+// whatever B is.
+constexpr int kChunk = 128;   // labels per warp and iteration
+constexpr int kLL = 4;        // labels per lane
+
+template <bool STABLE, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 probit_row_fwd_tiled_kernel(const RowArgs a, FusePart* __restrict__ part, int nchunks) {
     const int b = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -277,28 +288,25 @@ probit_row_fwd_tiled_kernel(const RowArgs a, FusePart* __restrict__ part, int nc
     const size_t yoff = (size_t)b * L;
     const float fS = (float)S;
     for (int c = blockIdx.y * kWarps + warp; c < nchunks; c += gridDim.y * kWarps) {
-        const int l0 = c * 64 + 2 * lane;
-        const bool in0 = l0 < L, in1 = l0 + 1 < L;
-        float y0 = 0.f, y1 = 0.f, fe0 = 0.f, fe1 = 0.f, fx0 = 0.f, fx1 = 0.f;
-        if (in0) { y0 = a.y[yoff + l0]; fe0 = a.fe_out[yoff + l0]; fx0 = a.fx_out[yoff + l0]; }
-        if (in1) { y1 = a.y[yoff + l0 + 1]; fe1 = a.fe_out[yoff + l0 + 1]; fx1 = a.fx_out[yoff + l0 + 1]; }
-        // rows are 16-byte aligned (ldn % 4 == 0) and l0 is even: 8-byte accesses; the pitch padding [L, ldn) is never
-        // used as a label (in0 / in1)
-        const bool pair = l0 + 1 < a.ldn;
+        const int l0 = c * kChunk + kLL * lane;
+        float y[kLL], fe[kLL], fx[kLL], accl[kLL], accx[kLL];
+#pragma unroll
+        for (int j = 0; j < kLL; ++j) {
+            y[j] = fe[j] = fx[j] = accl[j] = accx[j] = 0.f;
+            if (l0 + j < L) { y[j] = a.y[yoff + l0 + j]; fe[j] = a.fe_out[yoff + l0 + j]; fx[j] = a.fx_out[yoff + l0 + j]; }
+        }
+        // rows are 16-byte aligned (ldn % 4 == 0) and l0 is a multiple of 4: 16-byte accesses whenever the lane starts
+        // inside the row; the pitch padding [L, ldn) is loaded but never used as a label
+        const bool any = l0 < L;
         auto load = [&](int s) {
-            float2 n = make_float2(0.f, 0.f);
-            if (s < S && in0) {
-                const size_t o = row_of(a, s, b) * a.ldn + l0;
-                if (pair) n = __ldcs(reinterpret_cast<const float2*>(a.nr + o));
-                else n.x = a.nr[o];
-            }
+            float4 n = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s < S && any) n = __ldcs(reinterpret_cast<const float4*>(a.nr + row_of(a, s, b) * a.ldn + l0));
             return n;
         };
-        float accl0 = 0.f, accl1 = 0.f, accx0 = 0.f, accx1 = 0.f;    // prediction sums over samples
-        float2 n0 = load(0), n1 = load(1);
+        float4 n0 = load(0), n1 = load(1);
         for (int s0 = 0; s0 < S; s0 += kST) {
-            const float2 m0 = load(s0 + 2), m1 = load(s0 + 3);        // next pair in flight
-            float pl0 = 0.f, pl1 = 0.f, px0 = 0.f, px1 = 0.f;         // same pairwise order as probit_row_fwd_kernel
+            const float4 m0 = load(s0 + 2), m1 = load(s0 + 3);        // next pair in flight
+            float pl[kLL] = {0.f, 0.f, 0.f, 0.f}, px[kLL] = {0.f, 0.f, 0.f, 0.f};   // same pairwise order as before
             double lpl[kST], lpx[kST];
             float pn[kST][4];
 #pragma unroll
@@ -307,35 +315,31 @@ probit_row_fwd_tiled_kernel(const RowArgs a, FusePart* __restrict__ part, int nc
                 pn[i][0] = pn[i][1] = pn[i][2] = pn[i][3] = 0.f;
                 const int s = s0 + i;
                 if (s >= S) continue;
-                const float2 n = i == 0 ? n0 : n1;
-                float2 el = make_float2(0.f, 0.f), ex = make_float2(0.f, 0.f);
-                if (in0) {
-                    const CellFwd cl = cell_forward<STABLE>(n.x + fe0, y0);   // mpvae.py:168,177
-                    const CellFwd cx = cell_forward<STABLE>(n.x + fx0, y0);   // mpvae.py:170,180
-                    lpl[i] += (double)cl.ll; lpx[i] += (double)cx.ll;
-                    pn[i][0] += cl.epos; pn[i][1] += cl.eneg; pn[i][2] += cx.epos; pn[i][3] += cx.eneg;
-                    pl0 += cl.E; px0 += cx.E;
-                    el.x = cl.E; ex.x = cx.E;
-                }
-                if (in1) {
-                    const CellFwd cl = cell_forward<STABLE>(n.y + fe1, y1);
-                    const CellFwd cx = cell_forward<STABLE>(n.y + fx1, y1);
-                    lpl[i] += (double)cl.ll; lpx[i] += (double)cx.ll;
-                    pn[i][0] += cl.epos; pn[i][1] += cl.eneg; pn[i][2] += cx.epos; pn[i][3] += cx.eneg;
-                    pl1 += cl.E; px1 += cx.E;
-                    el.y = cl.E; ex.y = cx.E;
-                }
-                if (a.E_l && in0) {   // kept for the backward (training)
-                    const size_t o = row_of(a, s, b) * a.ldn + l0;
-                    if (pair) {
-                        *reinterpret_cast<float2*>(a.E_l + o) = el;
-                        *reinterpret_cast<float2*>(a.E_x + o) = ex;
-                    } else {
-                        a.E_l[o] = el.x; a.E_x[o] = ex.x;
+                const float4 n4 = i == 0 ? n0 : n1;
+                const float nv[kLL] = {n4.x, n4.y, n4.z, n4.w};
+                float el[kLL], ex[kLL];
+                float ll_l = 0.f, ll_x = 0.f;
+#pragma unroll
+                for (int j = 0; j < kLL; ++j) {
+                    el[j] = ex[j] = 0.f;
+                    if (l0 + j < L) {
+                        const CellFwd cl = cell_forward<STABLE>(nv[j] + fe[j], y[j]);   // mpvae.py:168,177
+                        const CellFwd cx = cell_forward<STABLE>(nv[j] + fx[j], y[j]);   // mpvae.py:170,180
+                        lpl[i] += (double)cl.ll; lpx[i] += (double)cx.ll;
+                        pn[i][0] += cl.epos; pn[i][1] += cl.eneg; pn[i][2] += cx.epos; pn[i][3] += cx.eneg;
+                        pl[j] += cl.E; px[j] += cx.E;
+                        el[j] = cl.E; ex[j] = cx.E;
                     }
                 }
+                (void)ll_l; (void)ll_x;
+                if (a.E_l && any) {   // kept for the backward (training)
+                    const size_t o = row_of(a, s, b) * a.ldn + l0;
+                    *reinterpret_cast<float4*>(a.E_l + o) = make_float4(el[0], el[1], el[2], el[3]);
+                    *reinterpret_cast<float4*>(a.E_x + o) = make_float4(ex[0], ex[1], ex[2], ex[3]);
+                }
             }
-            accl0 += pl0; accl1 += pl1; accx0 += px0; accx1 += px1;
+#pragma unroll
+            for (int j = 0; j < kLL; ++j) { accl[j] += pl[j]; accx[j] += px[j]; }
 #pragma unroll
             for (int i = 0; i < kST; ++i) {
                 if (s0 + i >= S) continue;
@@ -352,8 +356,12 @@ probit_row_fwd_tiled_kernel(const RowArgs a, FusePart* __restrict__ part, int nc
             n0 = m0; n1 = m1;
         }
         // predictions: mean over samples (mpvae.py:203-204)
-        if (in0) { a.indiv_prob_label[yoff + l0] = (0.0f + accl0) / fS; a.indiv_prob[yoff + l0] = (0.0f + accx0) / fS; }
-        if (in1) { a.indiv_prob_label[yoff + l0 + 1] = (0.0f + accl1) / fS; a.indiv_prob[yoff + l0 + 1] = (0.0f + accx1) / fS; }
+#pragma unroll
+        for (int j = 0; j < kLL; ++j)
+            if (l0 + j < L) {
+                a.indiv_prob_label[yoff + l0 + j] = accl[j] / fS;
+                a.indiv_prob[yoff + l0 + j] = accx[j] / fS;
+            }
     }
 }
 
@@ -635,6 +643,13 @@ probit_row_bwd_saved_kernel(const RowArgs a) {
     }
 }
 
+__global__ void log_normal_probe_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ ref, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        out[i] = MPV_LOG_NORMAL(in[i]);
+        ref[i] = logf(in[i]);
+    }
+}
+
 int pick_nwl(int L) {
     const int nchunks = (L + 31) / 32;
     int nwl = 1;
@@ -658,20 +673,27 @@ int device_slot() {
     return (d >= 0 && d < kMaxDevices) ? d : 0;
 }
 
-int row_chunks(int L) { return (L + 63) / 64; }
+int launch_log_normal_probe(const float* in, float* out, float* ref, size_t n, cudaStream_t stream) {
+    log_normal_probe_kernel<<<4 * kNumSMs, 256, 0, stream>>>(in, out, ref, n);
+    return check_launch("log_normal_probe_kernel");
+}
 
-// Forward = cell work tiled over (row, 64-label chunk) + the per-row tail over the chunk partials.  a.part must hold
+int row_chunks(int L) { return (L + kChunk - 1) / kChunk; }
+
+// Forward = cell work tiled over (row, 128-label chunk) + the per-row tail over the chunk partials.  a.part must hold
 // B * S * row_chunks(L) FusePart records.
 int launch_row_forward(RowArgs a, cudaStream_t stream) {
     if (a.part == nullptr) { set_error("row forward: no scratch for the chunk partials"); return 1; }
     const int nchunks = row_chunks(a.L);
     // enough CTAs for ~2 waves of 4 resident CTAs per SM, at most one CTA per 8 chunks (a warp each)
-    int gy = ceil_div(2 * 4 * kNumSMs, a.B);
+    int gy = ceil_div(2 * 2 * kNumSMs, a.B);
     if (gy > ceil_div(nchunks, kWarps)) gy = ceil_div(nchunks, kWarps);
     if (gy < 1) gy = 1;
     FusePart* part = const_cast<FusePart*>(a.part);
-    if (a.stable) probit_row_fwd_tiled_kernel<true><<<dim3(a.B, gy), kThreads, 0, stream>>>(a, part, nchunks);
-    else probit_row_fwd_tiled_kernel<false><<<dim3(a.B, gy), kThreads, 0, stream>>>(a, part, nchunks);
+    // two CTAs of 256 threads per SM (<= 128 registers: sixteen cells in flight per lane, no spills); measured equal
+    // to or faster than three (80 registers, spills) and four (64) on B200
+    if (a.stable) probit_row_fwd_tiled_kernel<true, 2><<<dim3(a.B, gy), kThreads, 0, stream>>>(a, part, nchunks);
+    else probit_row_fwd_tiled_kernel<false, 2><<<dim3(a.B, gy), kThreads, 0, stream>>>(a, part, nchunks);
     if (int rc = check_launch("probit_row_fwd_tiled_kernel")) return rc;
     a.part_tiles = nchunks;
     return launch_row_finalize(a, stream);

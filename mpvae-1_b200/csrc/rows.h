@@ -54,6 +54,7 @@ struct RowArgs {
 };
 
 size_t row_smem_bytes(int L);
+int launch_log_normal_probe(const float* in, float* out, float* ref, size_t n, cudaStream_t stream);   // test hook
 int row_chunks(int L);   // 64-label chunks of a row: launch_row_forward needs B * S * row_chunks(L) FusePart records in a.part
 int launch_row_forward(RowArgs a, cudaStream_t stream);
 // the tail of the forward when the product kernel has already done the cell work (a.part != nullptr)

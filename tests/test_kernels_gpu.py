@@ -108,6 +108,24 @@ def test_philox_noise_fed_to_oracle():
         assert H.rel_err(t[k].grad.cpu().numpy(), ref_g[k].cpu().numpy()) <= 1e-5, k
 
 
+def test_log_normal_bits():
+    """csrc/probit_math.cuh::log_normal (libdevice's logf main path without the denormal / inf / zero blocks) must equal
+    logf BIT FOR BIT on the domain the loss evaluates it on: every fp32 value of [4.7e-7, 1] is checked (115 M of them)."""
+    import ctypes as C
+    from mpvae_b200 import _lib
+    lo = np.array([4.7e-7], dtype=np.float32).view(np.int32)[0]
+    hi = np.array([1.0], dtype=np.float32).view(np.int32)[0]
+    bits = torch.arange(int(lo), int(hi) + 1, dtype=torch.int32, device=DEV)
+    x = bits.view(torch.float32)
+    out, ref = torch.empty_like(x), torch.empty_like(x)
+    stream = C.c_void_p(torch.cuda.current_stream(DEV).cuda_stream)
+    _lib.check(_lib.lib().mpvae_test_log_normal(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), C.c_void_p(ref.data_ptr()),
+                                                x.numel(), stream), "mpvae_test_log_normal")
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(torch.int32), ref.view(torch.int32)), int((out.view(torch.int32) != ref.view(torch.int32)).sum())
+    assert torch.allclose(ref.double(), torch.log(x.double()), rtol=0, atol=2e-7)
+
+
 # ----------------------------------------------------------------------------- contraction engines
 @pytest.mark.parametrize("M,N,K", [(1280, 38, 38), (1280, 14, 14), (12800, 81, 81), (333, 130, 5), (1280, 983, 10),
                                    (1280, 983, 983), (257, 129, 127), (64, 3993, 10)])
