@@ -123,7 +123,7 @@ def test_log_normal_bits():
                                                 x.numel(), stream), "mpvae_test_log_normal")
     torch.cuda.synchronize()
     assert torch.equal(out.view(torch.int32), ref.view(torch.int32)), int((out.view(torch.int32) != ref.view(torch.int32)).sum())
-    assert torch.allclose(ref.double(), torch.log(x.double()), rtol=0, atol=2e-7)
+    assert torch.allclose(ref.double(), torch.log(x.double()), rtol=3e-7, atol=1e-7)      # and logf itself is logf
 
 
 # ----------------------------------------------------------------------------- contraction engines
