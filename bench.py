@@ -520,7 +520,8 @@ def run_b200(a):
             roof = {"bound": "tensor", "achieved": flops / t_k / 1e12, "peak": peak, "unit": "TFLOP/s",
                     "frac": flops / t_k / 1e12 / peak,
                     "traffic": TRAFFIC.get((L, Z, S * Bl, bool(fused))),
-                    "kernel": "gemm_split_2sm_kernel<nt> (noise.R^T, mpvae.py:168" + (" + the row forward :177-204 on its math warps" if fused else "")
+                    "kernel": "gemm_split_2sm_kernel<nt> (noise.R^T, mpvae.py:168" + (" + the row forward :177-204 on its math warps" if fused
+                                                                                   else " + the Philox draw of mpvae.py:162 on its math warps")
                               + f"), tcgen05 fp16 hi/lo split, {passes} MMA passes",
                     "kernel_ms": t_k * 1e3, "timed": "CUDA events recorded by the library around the launch, inside the step",
                     "peak_basis": f"{peaks['_source']} bf16 burst {peaks['bf16_tflops']} TFLOP/s / {passes} "

@@ -42,6 +42,10 @@ extern "C" {
                                                accumulators leave room for 8 math warps per SM, a quarter of what the row
                                                math needs to hide its latencies: profiles/r02_fused_forward.md) */
 
+#define MPVAE_FLAG_SEPARATE_NOISE       0x20u /* dense regime, library-side noise: draw the Philox normals with a kernel of their own
+                                               before the product instead of on the product kernel's math warps, just
+                                               ahead of the tiles that read them (A/B measurements; same numbers) */
+
 /* order of the six scalar outputs (first six entries of the 8-tuple at mpvae.py:210) */
 enum { MPVAE_TOTAL = 0, MPVAE_NLL = 1, MPVAE_NLL_X = 2, MPVAE_C = 3, MPVAE_C_X = 4, MPVAE_KL = 5 };
 

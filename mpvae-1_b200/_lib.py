@@ -18,6 +18,7 @@ FLAG_CONTRACT_TENSOR = 0x2
 FLAG_CONTRACT_FMA = 0x4
 FLAG_STABLE_CDF = 0x8
 FLAG_FUSED_FORWARD = 0x10
+FLAG_SEPARATE_NOISE = 0x20
 
 # every symbol include/mpvae_b200.h declares
 EXPORTS = (

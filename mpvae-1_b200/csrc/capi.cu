@@ -75,7 +75,8 @@ struct Workspace {
     size_t noise_planes, r_planes, gxs_planes;    // tensor engine operand planes (noise planes persist fwd -> bwd)
     size_t fma_partials;                          // FMA engine split-K partials of g_R
     size_t tn_tail;                               // tensor engine: K-slices of the g_R product's last wave
-    size_t slots_bytes;                           // slots + the fused forward's per-tile completion counters
+    size_t slots_bytes;                           // slots + the counters below (zeroed together at the start of a forward)
+    size_t tile_counters, noise_counters;         // byte offsets inside the slots block
     size_t total;
 };
 // 32-bit slots of the first 256 bytes of the `slots` block; the per-tile counters of the fused forward follow
@@ -113,7 +114,10 @@ Workspace carve(int S, int B, int L, int Z, bool want_backward, uint32_t flags) 
     w.wts = take((size_t)B * S * 2 * sizeof(float));
     w.rowaux = take((size_t)B * 2 * sizeof(float));
     w.rowout = take((size_t)B * 8 * sizeof(double));
-    w.slots_bytes = 256 + (tensor ? align_up(tiles * sizeof(uint32_t), 256) : 0);
+    // [256 B of slots][per-tile counters of the fused forward][per-128-row-block counters of the just-in-time noise]
+    w.tile_counters = 256;
+    w.noise_counters = w.tile_counters + (tensor ? align_up(tiles * sizeof(uint32_t), 256) : 0);
+    w.slots_bytes = w.noise_counters + (tensor ? align_up((size_t)ceil_div(M, 128) * sizeof(uint32_t), 256) : 0);
     w.slots = take(w.slots_bytes);
     // everything the forward writes and the backward reads sits before the backward-only buffers, so a forward
     // sized for inference and a forward sized for training place the shared buffers identically
@@ -311,7 +315,12 @@ int mpvae_probit_forward(const mpvae_probit_params* p_in, void* cuda_stream) {
     if (use_tensor(p->flags, p->S, p->B, p->L, p->Z)) {
         void* npl = base + w.noise_planes;
         void* rpl = base + w.r_planes;
-        {
+        const bool fused = use_fused_forward(p->flags, p->S, p->B, p->L, p->Z);
+        // library noise: drawn by the product kernel's own math warps just ahead of the tiles (unless those warps carry
+        // the fused row forward, or the caller asks for the separate kernel)
+        const bool jit_noise = !p->noise && !fused && !(p->flags & MPVAE_FLAG_SEPARATE_NOISE);
+        rc = 0;
+        if (!jit_noise) {
             ProfScope ps(MPVAE_PROF_NOISE, stream);
             // operand rows are b-major (b * S + s): the S sample-rows of a batch row are neighbours
             if (p->noise) rc = tc_split(p->noise, M, p->Z, npl, nullptr, 0, stream, 0, p->S, p->B);   // |N(0,1)| fits fp16 at scale 1
@@ -323,8 +332,18 @@ int mpvae_probit_forward(const mpvae_probit_params* p_in, void* cuda_stream) {
             rc = tc_split(p->r, p->L, p->Z, rpl, slots + SLOT_ABSMAX_R, 1, stream);
         }
         if (rc) return rc;
-        const bool fused = use_fused_forward(p->flags, p->S, p->B, p->L, p->Z);
         FuseFwd fz{};
+        FuseNoise fnz{};
+        if (jit_noise) {
+            fnz.plane = static_cast<__half*>(npl);
+            fnz.S = p->S; fnz.B = p->B; fnz.Z = p->Z; fnz.pitch = tc_pitch(p->Z);
+            fnz.Bg = p->noise_b_global; fnz.row0 = p->noise_row0;
+            fnz.key = make_uint2((uint32_t)p->noise_seed, (uint32_t)(p->noise_seed >> 32));
+            fnz.off = make_uint2((uint32_t)p->noise_offset, (uint32_t)(p->noise_offset >> 32));
+            fnz.off_dev = reinterpret_cast<const unsigned long long*>(p->noise_offset_dev);
+            fnz.ready = slots + w.noise_counters / sizeof(uint32_t);
+            if ((long long)p->B * p->Z >= 0x7fffffffLL || p->Z < 4) { set_error("philox: B*Z=%lld, Z=%d out of range", (long long)p->B * p->Z, p->Z); return 6; }
+        }
         if (fused) {
             fz.S = p->S; fz.B = p->B; fz.L = p->L; fz.ldn = row_pitch(p->L);
             fz.stable = a.stable;
@@ -333,7 +352,7 @@ int mpvae_probit_forward(const mpvae_probit_params* p_in, void* cuda_stream) {
             fz.indiv_prob = p->indiv_prob; fz.indiv_prob_label = p->indiv_prob_label;
             fz.E_l = a.E_l; fz.E_x = a.E_x;
             fz.part = reinterpret_cast<FusePart*>(base + w.fuse_part);
-            fz.done = slots + 64;
+            fz.done = slots + w.tile_counters / sizeof(uint32_t);
         }
         {
             ProfScope ps(MPVAE_PROF_PRODUCT_NT, stream);
@@ -341,7 +360,7 @@ int mpvae_probit_forward(const mpvae_probit_params* p_in, void* cuda_stream) {
             // No tail scratch here: K-slicing the last wave would make the summation order of x = noise.R^T depend on
             // how many rows the call holds, and a row's predictions must not change with the shard it is computed in
             rc = tc_gemm_nt(npl, rpl, nr, M, p->L, p->Z, nullptr, slots + SLOT_ABSMAX_R, stream, row_pitch(p->L), p->noise ? 0 : 1,
-                            nullptr, 0, fused ? &fz : nullptr);
+                            nullptr, 0, fused ? &fz : nullptr, jit_noise ? &fnz : nullptr);
         }
         if (rc) return rc;
         ProfScope ps(MPVAE_PROF_ROW_FORWARD, stream);

@@ -47,7 +47,7 @@ constexpr int kCtrlWarps = 4;
 constexpr int kEpiWarps = 16;                            // 4 TMEM lane quadrants x 4 column quarters
 constexpr int HB = BN / 2;                               // B-tile columns staged by each CTA of a pair
 
-constexpr int threads_of(bool fuse) { return 32 * (kCtrlWarps + (fuse ? kFuseMathWarps : 0) + kEpiWarps); }
+constexpr int threads_of(int math) { return 32 * (kCtrlWarps + (math ? kFuseMathWarps : 0) + kEpiWarps); }
 
 // One k-block is one 128-byte swizzle row of K (K-major) or one TMA box of k-rows (MN-major); fp16 pieces.
 template <bool MN>
@@ -87,7 +87,7 @@ struct Ring {
 };
 constexpr int kFusePaccBytes = kFuseMathWarps * 2 * 256 * (int)sizeof(float);   // 16 KiB: per math warp [2][256]
 template <int EX>
-constexpr int smem_bytes_of(bool fuse) { return 1024 + Ring<EX>::RING_BYTES + BAR_BYTES + (fuse ? kFusePaccBytes : 0); }
+constexpr int smem_bytes_of(int math) { return 1024 + Ring<EX>::RING_BYTES + BAR_BYTES + (math == 1 ? kFusePaccBytes : 0); }
 
 // ------------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -219,10 +219,13 @@ struct GemmArgs {
     float* partials;
 };
 
-template <bool MN, int EX, bool FUSE, bool STABLE>
-__global__ void __launch_bounds__(threads_of(FUSE), 1)
+// MATH: what the eight extra "math" warps of the CTA do (fused_rows.cuh): 0 = there are none, 1 = the probit row
+// forward on finished tiles (opt-in), 2 = draw the Philox noise of the A operand just ahead of the tiles that read it.
+template <bool MN, int EX, int MATH, bool STABLE>
+__global__ void __launch_bounds__(threads_of(MATH), 1)
 gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g,
-                      const FuseFwd fz) {
+                      const FuseFwd fz, const FuseNoise fnz) {
+    constexpr bool FUSE = MATH != 0;
     using G = Geo<MN>;
     using R2 = Ring<EX>;
     constexpr int STAGES2 = R2::STAGES, STAGE2_BYTES = R2::STAGE_BYTES;
@@ -277,12 +280,16 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (warp < kCtrlWarps) {
         if (FUSE) reg_dec<kRegCtrl>();
         if (warp == 0 && lane == 0) {   // ------------------------------------------------ TMA producer (every CTA)
-            int stage = 0;
+            int stage = 0, noise_block = -1;
             uint32_t phase = 0;
             for (int w = cluster; w < num_items; w += num_clusters) {
                 const Item it = item_of(w, num_kb);
                 const int m0 = (it.st / g.tiles_n) * 256 + (int)rank * BM;     // this CTA's 128 rows of A
                 const int n0 = (it.st % g.tiles_n) * BN + (int)rank * HB;      // this CTA's half of the B tile
+                if (MATH == 2 && (m0 >> 7) != noise_block && m0 < g.Mc) {      // the math warps of the grid draw these rows
+                    noise_block = m0 >> 7;
+                    noise_wait_block(fnz.ready + noise_block, (unsigned)(gridDim.x * kFuseMathWarps));
+                }
                 for (int kb = it.kb_lo; kb < it.kb_hi; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t fb = map_to_cta(full_bar(stage), 0);        // the leader's barrier collects both CTAs' bytes
@@ -351,11 +358,15 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 }
             }
         }
-    } else if (FUSE && warp < kFirstEpi) {   // ------------------- row math of the probit forward on finished tiles
+    } else if (FUSE && warp < kFirstEpi) {   // ------------------- math warps
         reg_dec<kRegMath>();
         const int mw = warp - kCtrlWarps;
-        float* pacc = reinterpret_cast<float*>(gen + R2::RING_BYTES + BAR_BYTES) + mw * 512;
-        fuse_math_loop<STABLE>(fz, cluster, num_clusters, num_tiles, g.tiles_n, (int)rank * kFuseMathWarps + mw, pacc, lane);
+        if (MATH == 1) {         // row math of the probit forward on finished tiles
+            float* pacc = reinterpret_cast<float*>(gen + R2::RING_BYTES + BAR_BYTES) + mw * 512;
+            fuse_math_loop<STABLE>(fz, cluster, num_clusters, num_tiles, g.tiles_n, (int)rank * kFuseMathWarps + mw, pacc, lane);
+        } else {                 // the A operand's Philox noise, just ahead of the tiles
+            noise_math_loop(fnz, (int)blockIdx.x * kFuseMathWarps + mw, (int)gridDim.x * kFuseMathWarps, lane);
+        }
     } else {   // --------------------------------------------------- promotion + epilogue (both CTAs, own 128 rows)
         if (FUSE) reg_inc<kRegEpi>();
         const int q = warp & 3, h = (warp - kFirstEpi) >> 2;      // TMEM lane quadrant = warp id mod 4
@@ -423,7 +434,7 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         if (col0 + j < g.Nc) crow[col0 + j] = acc[j] * inv_scale;
                 }
             }
-            if (FUSE) fuse_signal_tile(fz.done, st, lane);        // this warp's part of the tile is in memory
+            if (MATH == 1) fuse_signal_tile(fz.done, st, lane);   // this warp's part of the tile is in memory
 #pragma unroll
             for (int j = 0; j < 64; ++j) acc[j] = 0.0f;
         }
@@ -593,17 +604,18 @@ int current_device() {
     return (d >= 0 && d < kMaxDevices) ? d : 0;
 }
 
-template <bool MN, int EX, bool FUSE, bool STABLE>
-int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, GemmArgs g, const FuseFwd& fz, cudaStream_t stream,
-                    size_t partials_bytes) {
-    auto kernel = gemm_split_2sm_kernel<MN, EX, FUSE, STABLE>;
+template <bool MN, int EX, int MATH, bool STABLE>
+int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, GemmArgs g, const FuseFwd& fz, const FuseNoise& fnz,
+                    cudaStream_t stream, size_t partials_bytes) {
+    constexpr bool FUSE = MATH != 0;
+    auto kernel = gemm_split_2sm_kernel<MN, EX, MATH, STABLE>;
     static int max_clusters[kMaxDevices] = {};     // co-resident clusters (a cluster must fit inside one GPC)
-    constexpr int smem = smem_bytes_of<EX>(FUSE);
+    constexpr int smem = smem_bytes_of<EX>(MATH);
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.blockDim = dim3(threads_of(FUSE));
+    cfg.blockDim = dim3(threads_of(MATH));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cfg.attrs = attr;
@@ -625,7 +637,7 @@ int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, GemmArgs g, cons
     g.full_tiles = tiles;
     g.ksplit = 1;
     static const bool no_split = getenv("MPVAE_TC_NO_KSPLIT") != nullptr;
-    if (!FUSE && g.partials != nullptr && !no_split) {
+    if (MATH != 1 && g.partials != nullptr && !no_split) {
         const int tail = tiles % mc, num_kb = ceil_div(g.K, Geo<MN>::BK);
         if (tail > 0) {
             int f = mc / tail;
@@ -637,7 +649,7 @@ int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, GemmArgs g, cons
     const int items = g.full_tiles + (tiles - g.full_tiles) * g.ksplit;
     const int clusters = items < mc ? items : mc;
     cfg.gridDim = dim3(2 * clusters);
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, a, b, g, fz);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, a, b, g, fz, fnz);
     if (e != cudaSuccess) { set_error("gemm_split_2sm_kernel launch: %s", cudaGetErrorString(e)); return 3; }
     if (int rc = check_launch("gemm_split_2sm_kernel")) return rc;
     if (g.ksplit > 1) {
@@ -653,7 +665,7 @@ int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, GemmArgs g, cons
 template <bool MN>
 int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc, int Nc, int K, int ldc, const uint32_t* ma,
                 const uint32_t* mb, cudaStream_t stream, int ex, float* partials, size_t partials_bytes,
-                const FuseFwd* fuse = nullptr) {
+                const FuseFwd* fuse = nullptr, const FuseNoise* noise = nullptr) {
     GemmArgs g{};
     g.C = C; g.Mc = Mc; g.Nc = Nc; g.K = K; g.ldc = ldc;
     g.tiles_m = ceil_div(Mc, 256); g.tiles_n = ceil_div(Nc, BN);
@@ -662,18 +674,23 @@ int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc, in
     g.absmax_a = ma; g.absmax_b = mb;
     g.partials = partials;
     const FuseFwd none{};
+    const FuseNoise nonoise{};
+    if (noise != nullptr) {
+        if (MN || ex != 1 || fuse != nullptr) { set_error("just-in-time noise: nt products with an exact A operand only"); return 7; }
+        return launch_gemm_2sm<false, 1, 2, false>(a, b, g, none, *noise, stream, 0);
+    }
     if (fuse != nullptr) {
         if (MN || ex == 2) { set_error("fused forward: nt products only"); return 7; }
         if (fuse->stable) {
-            if (ex == 1) return launch_gemm_2sm<false, 1, true, true>(a, b, g, *fuse, stream, 0);
-            return launch_gemm_2sm<false, 0, true, true>(a, b, g, *fuse, stream, 0);
+            if (ex == 1) return launch_gemm_2sm<false, 1, 1, true>(a, b, g, *fuse, nonoise, stream, 0);
+            return launch_gemm_2sm<false, 0, 1, true>(a, b, g, *fuse, nonoise, stream, 0);
         }
-        if (ex == 1) return launch_gemm_2sm<false, 1, true, false>(a, b, g, *fuse, stream, 0);
-        return launch_gemm_2sm<false, 0, true, false>(a, b, g, *fuse, stream, 0);
+        if (ex == 1) return launch_gemm_2sm<false, 1, 1, false>(a, b, g, *fuse, nonoise, stream, 0);
+        return launch_gemm_2sm<false, 0, 1, false>(a, b, g, *fuse, nonoise, stream, 0);
     }
-    if (ex == 1) return launch_gemm_2sm<MN, 1, false, false>(a, b, g, none, stream, partials_bytes);
-    if (ex == 2) return launch_gemm_2sm<MN, 2, false, false>(a, b, g, none, stream, partials_bytes);
-    return launch_gemm_2sm<MN, 0, false, false>(a, b, g, none, stream, partials_bytes);
+    if (ex == 1) return launch_gemm_2sm<MN, 1, 0, false>(a, b, g, none, nonoise, stream, partials_bytes);
+    if (ex == 2) return launch_gemm_2sm<MN, 2, 0, false>(a, b, g, none, nonoise, stream, partials_bytes);
+    return launch_gemm_2sm<MN, 0, 0, false>(a, b, g, none, nonoise, stream, partials_bytes);
 }
 
 }  // namespace
@@ -815,14 +832,14 @@ size_t tc_tail_scratch_bytes() { return (size_t)(kNumSMs / 2 - 1) * 256 * BN * s
 
 int tc_gemm_nt(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, const uint32_t* absmax_a,
                const uint32_t* absmax_b, cudaStream_t stream, int ldc, int a_exact, void* tail_scratch, size_t tail_scratch_bytes,
-               const FuseFwd* fuse) {
+               const FuseFwd* fuse, const FuseNoise* noise) {
     if (ldc <= 0) ldc = N;
     const int kp = pitch_of(K);
     CUtensorMap ma, mb;
     if (int rc = make_map(&ma, a_planes, K, M, kp, 64, BM, a_exact ? 1 : 2)) return rc;
     if (int rc = make_map(&mb, b_planes, K, N, kp, 64, HB)) return rc;
     return launch_gemm<false>(ma, mb, C, M, N, K, ldc, absmax_a, absmax_b, stream, a_exact ? 1 : 0, static_cast<float*>(tail_scratch),
-                              tail_scratch_bytes, fuse);
+                              tail_scratch_bytes, fuse, noise);
 }
 
 int tc_gemm_tn(const void* a_planes, const void* b_planes, float* C, int M, int N1, int N2, const uint32_t* absmax_a,

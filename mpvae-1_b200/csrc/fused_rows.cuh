@@ -18,7 +18,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
+#include "philox.cuh"
 #include "probit_math.cuh"
 
 namespace mpv {
@@ -176,6 +179,85 @@ __device__ __forceinline__ void fuse_math_loop(const FuseFwd& f, int first, int 
             }
             J += ng;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ noise just in time
+// The other job the product kernel's math warps can take (and the one that pays: pure integer / SFU work with plenty of
+// independent instructions per warp): DRAWING the Philox normals of mpvae.py:162 straight into the product's own A
+// operand plane while the tensor pipe works on earlier rows.  The plane is cut into blocks of 128 rows (one CTA's share
+// of a tile); all math warps of the grid fill block 0, then block 1, ... in the order the tiles consume them, bump the
+// block's counter when their share is written, and the TMA producer of a CTA waits for its block's counter before the
+// first load of a tile.  Same counter -> element mapping as philox_planes_kernel, so the numbers are identical.
+struct FuseNoise {
+    __half* plane;                 // [S*B][pitch] halves, rows b-major (b * S + s)
+    int S, B, Z, pitch, Bg, row0;  // Bg / row0: the global batch this shard's rows [row0, row0 + B) belong to
+    uint2 key, off;
+    const unsigned long long* off_dev;
+    unsigned int* ready;           // [ceil(S*B / 128)] counters, zeroed before the launch
+};
+
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+// TMA producer thread: block `u` of the plane is complete once every math warp of the grid has signalled it
+__device__ __forceinline__ void noise_wait_block(const unsigned int* cnt, unsigned int warps_total) {
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(cnt) < warps_total) {
+        __nanosleep(100);
+        if (clock64() - t0 > 8000000000LL) __trap();   // ~4 s: a protocol bug must not hang the GPU
+    }
+    fence_proxy_async_global();                         // generic-proxy stores -> async-proxy (TMA) loads
+}
+
+// One math warp's share of the whole plane.  gw = this warp's index among the `warps_total` math warps of the grid.
+__device__ __forceinline__ void noise_math_loop(const FuseNoise& f, int gw, int warps_total, int lane) {
+    const int M = f.S * f.B;
+    const int nblocks = (M + 127) >> 7;
+    const unsigned cpr = (unsigned)((f.Z + 3) / 4 + 1);           // counters that can touch one row
+    const unsigned units = 128u * cpr;
+    const unsigned stride = (unsigned)warps_total * 32u;
+    const uint2 off = philox_offset(f.off, f.off_dev);
+    for (int u = 0; u < nblocks; ++u) {
+        for (unsigned idx = (unsigned)gw * 32u + (unsigned)lane; idx < units; idx += stride) {
+            const int m = (u << 7) + (int)(idx / cpr);
+            if (m >= M) break;
+            const int b = m / f.S, s = m - b * f.S;
+            const unsigned long long flat0 = ((unsigned long long)s * f.Bg + f.row0 + b) * f.Z;   // (s, b_global, 0)
+            const unsigned long long c = (flat0 >> 2) + (idx % cpr);
+            const long long z0 = (long long)(c << 2) - (long long)flat0;                        // -3 .. Z + 3
+            if (z0 >= f.Z) continue;
+            float n[4];
+            philox_normal4(c, f.key, off, n);
+            __half* __restrict__ row = f.plane + (size_t)m * f.pitch;
+            if (z0 >= 0 && z0 + 4 <= f.Z) {
+                __half* dst = row + z0;
+                const __half2 p01 = __floats2half2_rn(n[0], n[1]), p23 = __floats2half2_rn(n[2], n[3]);
+                const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
+                if ((a & 7u) == 0) {
+                    uint2 v;
+                    v.x = *reinterpret_cast<const uint32_t*>(&p01);
+                    v.y = *reinterpret_cast<const uint32_t*>(&p23);
+                    *reinterpret_cast<uint2*>(dst) = v;
+                } else if ((a & 3u) == 0) {
+                    *reinterpret_cast<__half2*>(dst) = p01;
+                    *reinterpret_cast<__half2*>(dst + 2) = p23;
+                } else {
+                    dst[0] = __low2half(p01);
+                    *reinterpret_cast<__half2*>(dst + 1) = __halves2half2(__high2half(p01), __low2half(p23));
+                    dst[3] = __high2half(p23);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const long long z = z0 + j;
+                    if (z >= 0 && z < f.Z) row[z] = __float2half_rn(n[j]);
+                }
+            }
+        }
+        fence_proxy_async_global();
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(f.ready + u, 1u);
     }
 }
 

@@ -7,7 +7,8 @@
 
 namespace mpv {
 
-struct FuseFwd;   // fused_rows.cuh: the probit row forward carried by the nt product kernel
+struct FuseFwd;     // fused_rows.cuh: the probit row forward carried by the nt product kernel (opt-in)
+struct FuseNoise;   // fused_rows.cuh: the A operand's Philox noise drawn by the nt product kernel itself
 
 bool tc_available();
 
@@ -42,7 +43,8 @@ int tc_philox_planes(void* planes, int S, int B, int Z, int B_global, int row0, 
 // fuse != nullptr: the kernel also runs the probit row forward on its finished tiles (fused_rows.cuh; no K-slicing).
 int tc_gemm_nt(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, const uint32_t* absmax_a,
                const uint32_t* absmax_b, cudaStream_t stream, int ldc = 0, int a_exact = 0,   // ldc: pitch of C (0 = N)
-               void* tail_scratch = nullptr, size_t tail_scratch_bytes = 0, const FuseFwd* fuse = nullptr);
+               void* tail_scratch = nullptr, size_t tail_scratch_bytes = 0, const FuseFwd* fuse = nullptr,
+               const FuseNoise* noise = nullptr);   // noise != nullptr: a_planes is written by the kernel itself (a_exact)
 // tail_scratch (optional, tc_tail_scratch_bytes()): lets the kernel cut the tiles of the last, partial wave of its
 // persistent grid into K-slices so that the wave does not leave most SMs idle.
 size_t tc_tail_scratch_bytes();
