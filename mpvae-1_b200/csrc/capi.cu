@@ -74,6 +74,7 @@ struct Workspace {
     size_t noise_f32;                             // FMA engine, library-side noise
     size_t noise_planes, r_planes, gxs_planes;    // tensor engine operand planes (noise planes persist fwd -> bwd)
     size_t fma_partials;                          // FMA engine split-K partials of g_R
+    size_t small_partials;                        // small regime: per-row contributions to g_R
     size_t tn_tail;                               // tensor engine: K-slices of the g_R product's last wave
     size_t slots_bytes;                           // slots + the counters below (zeroed together at the start of a forward)
     size_t tile_counters, noise_counters;         // byte offsets inside the slots block
@@ -92,6 +93,12 @@ bool use_tensor(uint32_t flags, int S, int B, int L, int Z) {
     if (flags & MPVAE_FLAG_CONTRACT_TENSOR) return true;
     // dense-GEMM regime (north star: label / rank sets >= 128)
     return Z >= 128 && L >= 128 && (long long)S * B >= 128;
+}
+
+// label / rank sets that fit an SM: one fused CTA per batch row (probit_small_fwd_kernel)
+bool use_small(uint32_t flags, int S, int B, int L, int Z) {
+    if (flags & (MPVAE_FLAG_CONTRACT_FMA | MPVAE_FLAG_CONTRACT_TENSOR | MPVAE_FLAG_STABLE_CDF)) return false;
+    return !use_tensor(flags, S, B, L, Z) && small_regime_fits(S, B, L, Z);
 }
 
 // the product kernel carries the row forward on its math warps (fused_rows.cuh); a group of S sample-rows may reach
@@ -138,6 +145,7 @@ Workspace carve(int S, int B, int L, int Z, bool want_backward, uint32_t flags) 
         } else {
             w.gxs = take(cube * sizeof(float));
             w.fma_partials = take(contract_tn_fma_workspace(M, L, Z));
+            if (use_small(flags, S, B, L, Z)) w.small_partials = take(small_partial_bytes(B, L, Z));
         }
     }
     w.total = off;
@@ -371,6 +379,19 @@ int mpvae_probit_forward(const mpvae_probit_params* p_in, void* cuda_stream) {
         }
         return launch_row_forward(a, stream);
     }
+    if (use_small(p->flags, p->S, p->B, p->L, p->Z)) {
+        // one launch: R staged by TMA, Philox in registers, warp-FMA contraction, row math, per-row tail
+        ProfScope ps(MPVAE_PROF_FUSED_SMALL_FWD, stream);
+        SmallNoise sn{};
+        sn.r = p->r; sn.Z = p->Z;
+        sn.noise_ext = p->noise;
+        const bool training = a.E_l != nullptr;
+        sn.noise_out = (training && !p->noise) ? reinterpret_cast<float*>(base + w.noise_f32) : nullptr;
+        sn.nr_out = training ? nr : nullptr;
+        sn.Bg = p->noise_b_global; sn.row0 = p->noise_row0;
+        sn.seed = p->noise_seed; sn.offset = p->noise_offset; sn.offset_dev = p->noise_offset_dev;
+        return launch_small_forward(a, sn, stream);
+    }
     const float* nz = p->noise;
     if (!nz) {
         ProfScope ps(MPVAE_PROF_NOISE, stream);
@@ -418,14 +439,15 @@ int mpvae_probit_backward(const mpvae_probit_params* p_in, void* cuda_stream) {
     } else if (p->g_r) {
         a.gxs = reinterpret_cast<float*>(base + w.gxs);
     }
-    {
+    const bool small = use_small(p->flags, p->S, p->B, p->L, p->Z);
+    if (!small) {
         ProfScope ps(MPVAE_PROF_ROW_BACKWARD, stream);
         if (int rc = launch_row_backward(a, stream)) return rc;
     }
-    if (!p->g_r) return 0;
+    if (!p->g_r && !small) return 0;
     // data-parallel: the product writes this rank's partial into its own `part` buffer, peer_reduce.cu sums the world's
     // partials over NVLink and leaves the result in every rank's g_r
-    const bool peer = p->peer_world > 1;
+    const bool peer = p->peer_world > 1 && p->g_r != nullptr;
     PeerCtx pctx{};
     float* g_r_out = p->g_r;
     if (peer) {
@@ -445,7 +467,18 @@ int mpvae_probit_backward(const mpvae_probit_params* p_in, void* cuda_stream) {
         }
         g_r_out = pctx.part[p->peer_rank];
     }
-    {
+    if (small) {
+        // one CTA per row (cells from the kept E / nr, logit and KL gradients, the row's share of g_R), then the
+        // deterministic sum of the shares over the batch
+        ProfScope ps(MPVAE_PROF_FUSED_SMALL_BWD, stream);
+        SmallNoise sn{};
+        sn.r = p->r; sn.Z = p->Z;
+        sn.noise_ext = p->noise;
+        sn.noise_out = reinterpret_cast<float*>(base + w.noise_f32);
+        sn.partial = p->g_r ? reinterpret_cast<float*>(base + w.small_partials) : nullptr;
+        if (int rc = launch_small_backward(a, sn, p->g_r ? g_r_out : nullptr, stream)) return rc;
+        if (!p->g_r) return 0;
+    } else {
         ProfScope ps(MPVAE_PROF_PRODUCT_TN, stream);
         int rc;
         if (tensor) {

@@ -607,7 +607,6 @@ int current_device() {
 template <bool MN, int EX, int MATH, bool STABLE>
 int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, GemmArgs g, const FuseFwd& fz, const FuseNoise& fnz,
                     cudaStream_t stream, size_t partials_bytes) {
-    constexpr bool FUSE = MATH != 0;
     auto kernel = gemm_split_2sm_kernel<MN, EX, MATH, STABLE>;
     static int max_clusters[kMaxDevices] = {};     // co-resident clusters (a cluster must fit inside one GPC)
     constexpr int smem = smem_bytes_of<EX>(MATH);

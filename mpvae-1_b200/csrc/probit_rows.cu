@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "fused_rows.cuh"
+#include "philox.cuh"
 #include "probit_math.cuh"
 #include "rows.h"
 
@@ -47,10 +48,12 @@ __device__ __forceinline__ void load_chunk(RowChunk& in, const RowArgs& a, const
     }
 }
 
+template <int NT = kThreads>
 __device__ __forceinline__ BlockCounts count_labels(const float* __restrict__ yrow, int L, int* s_tmp) {
+    constexpr int kWarps = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int cp = 0, cn = 0;
-    for (int l = tid; l < L; l += kThreads) {
+    for (int l = tid; l < L; l += NT) {
         const float v = yrow[l];
         cp += (v == 1.0f);   // torch.eq(labels, ones)   mpvae.py:107
         cn += (v == 0.0f);   // torch.eq(labels, zeros)  mpvae.py:108
@@ -65,148 +68,30 @@ __device__ __forceinline__ BlockCounts count_labels(const float* __restrict__ yr
     return c;
 }
 
-// PARTS: the product kernel's math warps have done the cell work (fused_rows.cuh); this kernel only adds their
-// per-tile partials in a fixed order and runs the per-row tail.
-template <bool STABLE, bool PARTS>
-__global__ void __launch_bounds__(kThreads, 4)
-probit_row_fwd_kernel(const RowArgs a) {
-    extern __shared__ float s_pacc[];                 // [nws][2][L] prediction partial sums
-    __shared__ double s_lp[kWarps][kST][2];
-    __shared__ float s_pn[kWarps][kST][4];
+// The per-row tail of the forward, shared by every forward kernel: label counts, KL row term (mpvae.py:147-148), per-row
+// log-mean-exp over samples, softmax weights, ranking sums (mpvae.py:188-190,115-122), and -- in the last CTA to
+// arrive -- the batch means and the total (mpvae.py:190,122,147,207-208) in a fixed summation order.  Expects the
+// row's a.lp / a.stat entries to have been written by threads of this CTA (any of them); blockDim.x == NT.
+template <int NT = kThreads>
+__device__ __forceinline__ void row_tail(const RowArgs& a, int b) {
+    constexpr int kWarps = NT / 32;
     __shared__ int s_cnt[2 * kWarps];
     __shared__ double s_kl[kWarps];
     __shared__ double s_fin[8];
     __shared__ int s_last;
-
-    const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int L = a.L, S = a.S, B = a.B;
-    const int nwl = a.nwl, nws = kWarps / nwl;
-    const int wl = warp % nwl, ws = warp / nwl;
-    const int nchunks = (L + 31) >> 5;
-    const float* __restrict__ yrow = a.y + (size_t)b * L;
-    const float* __restrict__ ferow = a.fe_out + (size_t)b * L;
-    const float* __restrict__ fxrow = a.fx_out + (size_t)b * L;
-
-    if (!PARTS)
-        for (int i = tid; i < nws * 2 * L; i += kThreads) s_pacc[i] = 0.0f;
-    const BlockCounts cnt = count_labels(yrow, L, s_cnt);   // contains a __syncthreads()
-
-    if (PARTS) {
-        // a warp per sample-row, a lane per chunk (stride 32), then a butterfly: a fixed order whatever the grid was
-        for (int s = warp; s < S; s += kWarps) {
-            const FusePart* __restrict__ pp = a.part + ((size_t)b * S + s) * a.part_tiles;
-            double l0 = 0.0, l1 = 0.0;
-            float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-            for (int t = lane; t < a.part_tiles; t += 32) {
-                const FusePart p = pp[t];
-                l0 += p.lp_l; l1 += p.lp_x;
-                q0 += p.pos_l; q1 += p.neg_l; q2 += p.pos_x; q3 += p.neg_x;
-            }
-            l0 = warp_sum(l0); l1 = warp_sum(l1);
-            q0 = warp_sum(q0); q1 = warp_sum(q1); q2 = warp_sum(q2); q3 = warp_sum(q3);
-            if (lane == 0) {
-                const size_t o = (size_t)b * S + s;
-                a.lp[o * 2 + 0] = l0; a.lp[o * 2 + 1] = l1;
-                reinterpret_cast<float4*>(a.stat)[o] = make_float4(q0, q1, q2, q3);
-            }
-        }
-    }
-    const int steps = PARTS ? 0 : (S + kST * nws - 1) / (kST * nws);
-    for (int step = 0; step < steps; ++step) {
-        const int s0 = (step * nws + ws) * kST;
-        double lp[kST][2];
-        float pn[kST][4];
-#pragma unroll
-        for (int i = 0; i < kST; ++i) {
-            lp[i][0] = lp[i][1] = 0.0;
-            pn[i][0] = pn[i][1] = pn[i][2] = pn[i][3] = 0.0f;
-        }
-        if (s0 < S) {
-            float* __restrict__ pacc = s_pacc + (size_t)ws * 2 * L;
-            // software pipeline: the loads of the next 32-label chunk are in flight while this one is computed
-            // (ncu: 31 % of the stall samples of the unpipelined loop sat on the first use of nr)
-            RowChunk cur, nxt;
-            int c = wl;
-            if (c < nchunks) load_chunk(cur, a, yrow, ferow, fxrow, c, lane, b, s0);
-            for (; c < nchunks; c += nwl) {
-                if (c + nwl < nchunks) load_chunk(nxt, a, yrow, ferow, fxrow, c + nwl, lane, b, s0);
-                const int l = (c << 5) + lane;
-                if (l < L) {
-                    float pl = 0.0f, px = 0.0f;
-#pragma unroll
-                    for (int i = 0; i < kST; ++i) {
-                        if (s0 + i < S) {
-                            const CellFwd cl = cell_forward<STABLE>(cur.nr[i] + cur.fe, cur.y);   // mpvae.py:168,177
-                            const CellFwd cx = cell_forward<STABLE>(cur.nr[i] + cur.fx, cur.y);   // mpvae.py:170,180
-                            lp[i][0] += (double)cl.ll;
-                            lp[i][1] += (double)cx.ll;
-                            pn[i][0] += cl.epos; pn[i][1] += cl.eneg;
-                            pn[i][2] += cx.epos; pn[i][3] += cx.eneg;
-                            pl += cl.E; px += cx.E;
-                            if (a.E_l) {   // kept for the backward (training)
-                                const size_t o = row_of(a, s0 + i, b) * a.ldn + l;
-                                a.E_l[o] = cl.E; a.E_x[o] = cx.E;
-                            }
-                        }
-                    }
-                    pacc[l] += pl;
-                    pacc[L + l] += px;
-                }
-                cur = nxt;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < kST; ++i) {
-            lp[i][0] = warp_sum(lp[i][0]); lp[i][1] = warp_sum(lp[i][1]);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) pn[i][q] = warp_sum(pn[i][q]);
-            if (lane == 0) {
-                s_lp[warp][i][0] = lp[i][0]; s_lp[warp][i][1] = lp[i][1];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) s_pn[warp][i][q] = pn[i][q];
-            }
-        }
-        __syncthreads();
-        if (tid < nws * kST) {
-            const int g = tid / kST, i = tid % kST;
-            const int s = (step * nws + g) * kST + i;
-            if (s < S) {
-                double l0 = 0.0, l1 = 0.0;
-                float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-                for (int w = g * nwl; w < (g + 1) * nwl; ++w) {   // fixed order
-                    l0 += s_lp[w][i][0]; l1 += s_lp[w][i][1];
-                    q0 += s_pn[w][i][0]; q1 += s_pn[w][i][1]; q2 += s_pn[w][i][2]; q3 += s_pn[w][i][3];
-                }
-                const size_t o = (size_t)b * S + s;
-                a.lp[o * 2 + 0] = l0; a.lp[o * 2 + 1] = l1;
-                reinterpret_cast<float4*>(a.stat)[o] = make_float4(q0, q1, q2, q3);
-            }
-        }
-        __syncthreads();
-    }
-
-    // ---- predictions: mean over samples (mpvae.py:203-204) ----
+    const int S = a.S, B = a.B;
     const float fS = (float)S;
-    for (int l = tid; l < (PARTS ? 0 : L); l += kThreads) {
-        float sl = 0.0f, sx = 0.0f;
-        for (int g = 0; g < nws; ++g) { sl += s_pacc[(size_t)g * 2 * L + l]; sx += s_pacc[(size_t)g * 2 * L + L + l]; }
-        a.indiv_prob_label[(size_t)b * L + l] = sl / fS;
-        a.indiv_prob[(size_t)b * L + l] = sx / fS;
-    }
-
-    // ---- KL row term (mpvae.py:147-148) ----
+    const BlockCounts cnt = count_labels<NT>(a.y + (size_t)b * a.L, a.L, s_cnt);   // contains a __syncthreads()
     {
         double kp = 0.0;
         const size_t o = (size_t)b * a.D;
-        for (int d = tid; d < a.D; d += kThreads)
+        for (int d = tid; d < a.D; d += NT)
             kp += (double)kl_cell(a.fe_mu[o + d], a.fe_logvar[o + d], a.fx_mu[o + d], a.fx_logvar[o + d]).term;
         kp = warp_sum(kp);
         if (lane == 0) s_kl[warp] = kp;
     }
-    __syncthreads();   // also orders the lp/stat global writes above before warp 0 reads them back
-
-    // ---- per-row log-mean-exp over samples, softmax weights, ranking sums (mpvae.py:188-190,115-122) ----
+    __syncthreads();   // also orders the lp/stat global writes before warp 0 reads them back
     if (warp == 0) {
         const float norm5 = 5.0f * ((float)cnt.npos * (float)cnt.nneg);
         double outv[5];
@@ -242,8 +127,6 @@ probit_row_fwd_kernel(const RowArgs a) {
             a.rowaux[(size_t)b * 2 + 1] = (float)cnt.nneg;
         }
     }
-
-    // ---- last CTA: batch means and the total (mpvae.py:190,122,147,207-208), fixed summation order ----
     __threadfence();
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
@@ -270,11 +153,38 @@ probit_row_fwd_kernel(const RowArgs a) {
     }
 }
 
+// Second half of the tiled forward: adds the per-(sample-row, chunk) partials the cell kernel (or the product kernel's
+// math warps, fused_rows.cuh) left, in a fixed order, and runs the per-row tail.  One CTA per batch row.
+__global__ void __launch_bounds__(kThreads, 4)
+probit_row_finalize_kernel(const RowArgs a) {
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // a warp per sample-row, a lane per chunk (stride 32), then a butterfly: a fixed order whatever the grid was
+    for (int s = warp; s < a.S; s += kWarps) {
+        const FusePart* __restrict__ pp = a.part + ((size_t)b * a.S + s) * a.part_tiles;
+        double l0 = 0.0, l1 = 0.0;
+        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+        for (int t = lane; t < a.part_tiles; t += 32) {
+            const FusePart p = pp[t];
+            l0 += p.lp_l; l1 += p.lp_x;
+            q0 += p.pos_l; q1 += p.neg_l; q2 += p.pos_x; q3 += p.neg_x;
+        }
+        l0 = warp_sum(l0); l1 = warp_sum(l1);
+        q0 = warp_sum(q0); q1 = warp_sum(q1); q2 = warp_sum(q2); q3 = warp_sum(q3);
+        if (lane == 0) {
+            const size_t o = (size_t)b * a.S + s;
+            a.lp[o * 2 + 0] = l0; a.lp[o * 2 + 1] = l1;
+            reinterpret_cast<float4*>(a.stat)[o] = make_float4(q0, q1, q2, q3);
+        }
+    }
+    row_tail(a, b);
+}
+
 // Cell work of the forward, tiled (b, 128-label chunk): a warp owns 128 neighbouring labels of one batch row (a lane:
 // four of them) and walks the S samples with y / logits / the prediction sums in registers -- no shared-memory
 // accumulators, 16-byte loads of nr and 16-byte stores of the saved probabilities.  Per (sample, chunk) the warp reduces
-// the six label sums and leaves them as a FusePart; probit_row_fwd_kernel<.., PARTS> adds the chunks in a fixed order
-// and runs the per-row tail.  Grid (B, G): the chunks of a row are dealt out to G CTAs so that the grid fills the GPU
+// the six label sums and leaves them as a FusePart; probit_row_finalize_kernel adds the chunks in a fixed order and
+// runs the per-row tail.  Grid (B, G): the chunks of a row are dealt out to G CTAs so that the grid fills the GPU
 // whatever B is.
 constexpr int kChunk = 128;   // labels per warp and iteration
 constexpr int kLL = 4;        // labels per lane
@@ -643,6 +553,271 @@ probit_row_bwd_saved_kernel(const RowArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ small regime
+// Label / rank sets that fit an SM (L, Z <= 128, L * Z <= 8192: the mirflickr, yeast and NUS-WIDE shapes of BASELINE.json)
+// are not GEMM-shaped work: the whole forward of a batch row is ONE CTA of ONE launch.
+//   R (L x Z fp32)  staged in shared memory by a TMA bulk copy (cp.async.bulk + mbarrier)
+//   noise           Philox4x32-10 + Box-Muller in registers, two sample rows at a time per warp (or read from the
+//                   caller's tensor), staged through 2 x Z floats of shared memory per warp; also written out as fp32
+//                   for the backward's g_R product
+//   contraction     nr[s, l] = sum_z noise[s, z] R[l, z]: a lane per label, warp-level FMA chain in k order -- the same
+//                   chain as contract_fma.cu, so the two paths agree bit for bit
+//   row math        cell_forward for both branches; label sums by warp shuffles; prediction sums in the sample order of
+//                   the other forward kernels (pair sums, then pairs in order), so predictions are bit-equal too
+//   tail            row_tail(): KL, log-mean-exp over samples, softmax weights, ranking sums, last-CTA batch means
+// The backward is one CTA per row as well (cell_backward_saved from the kept E and nr, logit gradients, KL gradients)
+// and leaves the row's contribution to g_R = gxs^T . noise in a scratch slab; a second, tiny kernel adds the slabs over
+// the batch in row order (deterministic).
+struct SmallArgs {
+    RowArgs a;
+    const float* r;            // (L, Z) fp32
+    int Z;
+    const float* noise_ext;    // (S, B, Z) caller's noise or nullptr
+    float* noise_out;          // (S, B, Z) fp32 copy kept for the backward, or nullptr (inference)
+    float* nr_out;             // (S*B, ldn) kept for the backward, or nullptr
+    int Bg, row0;
+    uint2 key, off;
+    const unsigned long long* off_dev;
+    float* partial;            // backward: (B, L*Z) per-row contributions to g_R
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+constexpr int kSmallThreads = 512;   // sixteen warps: a sample pair each per round
+constexpr int kSmallWarps = kSmallThreads / 32;
+
+template <bool STABLE>
+__global__ void __launch_bounds__(kSmallThreads)
+probit_small_fwd_kernel(const SmallArgs p) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    const RowArgs& a = p.a;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int L = a.L, S = a.S, Z = p.Z, B = a.B;
+    const int npairs = (S + 1) >> 1;
+    float* Rs = reinterpret_cast<float*>(s_raw);                           // [L][Z]
+    float* nz = Rs + (((size_t)L * Z + 3) & ~(size_t)3);                   // [kSmallWarps][2][Z]
+    float* ps = nz + (size_t)kSmallWarps * 2 * Z;                               // [npairs][2][L] pair sums of E
+    // ---- R -> shared memory: one TMA bulk copy for the 16-byte multiple, plain loads for the last few floats ----
+    const uint32_t bytes16 = ((uint32_t)(L * Z) * 4u) & ~15u;
+    const bool bulk = bytes16 != 0 && (reinterpret_cast<uintptr_t>(p.r) & 15u) == 0;
+    const uint32_t bar = smem_addr(&s_bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0 && bulk) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes16) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_addr(Rs)), "l"(p.r), "r"(bytes16), "r"(bar)
+                     : "memory");
+    }
+    for (int i = (bulk ? (int)(bytes16 >> 2) : 0) + tid; i < L * Z; i += kSmallThreads) Rs[i] = p.r[i];
+    // this lane's labels (L <= 128: at most four 32-label chunks)
+    const int nch = (L + 31) >> 5;
+    float yv[4], fev[4], fxv[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int l = (c << 5) + lane;
+        yv[c] = fev[c] = fxv[c] = 0.f;
+        if (c < nch && l < L) { yv[c] = a.y[(size_t)b * L + l]; fev[c] = a.fe_out[(size_t)b * L + l]; fxv[c] = a.fx_out[(size_t)b * L + l]; }
+    }
+    if (bulk) {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred q;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\t"
+                "selp.u32 %0, 1, 0, q;\n\t}"
+                : "=r"(done)
+                : "r"(bar)
+                : "memory");
+        }
+    }
+    __syncthreads();
+    // ---- pairs of samples, a warp each ----
+    const uint2 off = philox_offset(p.off, p.off_dev);
+    float* nzw = nz + (size_t)warp * 2 * Z;
+    for (int pair = warp; pair < npairs; pair += kSmallWarps) {
+        const int s0 = pair << 1;
+        const bool two = s0 + 1 < S;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int s = s0 + i;
+            if (s >= S) break;
+            if (p.noise_ext) {
+                const float* src = p.noise_ext + ((size_t)s * B + b) * Z;
+                for (int z = lane; z < Z; z += 32) nzw[i * Z + z] = src[z];
+            } else {
+                // the normals of (s, global row, 0 .. Z): counters flat0 / 4 .. (flat0 + Z - 1) / 4 of the global tensor
+                const unsigned long long flat0 = ((unsigned long long)s * p.Bg + p.row0 + b) * Z;
+                const unsigned long long c0 = flat0 >> 2, c1 = (flat0 + Z - 1) >> 2;
+                for (unsigned long long c = c0 + lane; c <= c1; c += 32) {
+                    float n[4];
+                    philox_normal4(c, p.key, off, n);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const long long z = (long long)(c << 2) + j - (long long)flat0;
+                        if (z >= 0 && z < Z) nzw[i * Z + z] = n[j];
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (p.noise_out) {
+            for (int i = 0; i < (two ? 2 : 1); ++i)
+                for (int z = lane; z < Z; z += 32) p.noise_out[((size_t)(s0 + i) * B + b) * Z + z] = nzw[i * Z + z];
+        }
+        double lpl[2] = {0.0, 0.0}, lpx[2] = {0.0, 0.0};
+        float pn[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int l = (c << 5) + lane;
+            if (c >= nch || l >= L) continue;
+            // warp-level FMA chain in k order (the chain of contract_fma.cu: bit-equal results)
+            float acc0 = 0.f, acc1 = 0.f;
+            const float* rl = Rs + (size_t)l * Z;
+            for (int z = 0; z < Z; ++z) {
+                const float r = rl[z];
+                acc0 = fmaf(nzw[z], r, acc0);
+                acc1 = fmaf(nzw[Z + z], r, acc1);
+            }
+            float pl = 0.f, px = 0.f;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (s0 + i >= S) continue;
+                const float nr = i == 0 ? acc0 : acc1;
+                const CellFwd cl = cell_forward<STABLE>(nr + fev[c], yv[c]);   // mpvae.py:168,177
+                const CellFwd cx = cell_forward<STABLE>(nr + fxv[c], yv[c]);   // mpvae.py:170,180
+                lpl[i] += (double)cl.ll; lpx[i] += (double)cx.ll;
+                pn[i][0] += cl.epos; pn[i][1] += cl.eneg; pn[i][2] += cx.epos; pn[i][3] += cx.eneg;
+                pl += cl.E; px += cx.E;
+                if (p.nr_out) {   // kept for the backward (training)
+                    const size_t o = row_of(a, s0 + i, b) * a.ldn + l;
+                    p.nr_out[o] = nr; a.E_l[o] = cl.E; a.E_x[o] = cx.E;
+                }
+            }
+            ps[((size_t)pair * 2 + 0) * L + l] = pl;
+            ps[((size_t)pair * 2 + 1) * L + l] = px;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            if (s0 + i >= S) continue;
+            lpl[i] = warp_sum(lpl[i]); lpx[i] = warp_sum(lpx[i]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pn[i][q] = warp_sum(pn[i][q]);
+            if (lane == 0) {
+                const size_t o = (size_t)b * S + s0 + i;
+                a.lp[o * 2 + 0] = lpl[i]; a.lp[o * 2 + 1] = lpx[i];
+                reinterpret_cast<float4*>(a.stat)[o] = make_float4(pn[i][0], pn[i][1], pn[i][2], pn[i][3]);
+            }
+        }
+        __syncwarp();   // nzw is rewritten by the next pair
+    }
+    __syncthreads();
+    // ---- predictions: mean over samples (mpvae.py:203-204), pairs added in order ----
+    const float fS = (float)S;
+    for (int l = tid; l < L; l += kSmallThreads) {
+        float sl = 0.f, sx = 0.f;
+        for (int q = 0; q < npairs; ++q) { sl += ps[((size_t)q * 2 + 0) * L + l]; sx += ps[((size_t)q * 2 + 1) * L + l]; }
+        a.indiv_prob_label[(size_t)b * L + l] = sl / fS;
+        a.indiv_prob[(size_t)b * L + l] = sx / fS;
+    }
+    row_tail<kSmallThreads>(a, b);
+}
+
+__global__ void __launch_bounds__(kThreads)
+probit_small_bwd_kernel(const SmallArgs p) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const RowArgs& a = p.a;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int L = a.L, S = a.S, Z = p.Z, B = a.B;
+    const int npairs = (S + 1) >> 1;
+    float* coef = reinterpret_cast<float*>(s_raw);         // [S][6]
+    float* gxs = coef + (size_t)S * 6;                      // [S][L]
+    float* nzs = gxs + (size_t)S * L;                       // [S][Z]
+    float* gsum = nzs + (size_t)S * Z;                      // [kWarps][2][L]
+    const RowCoeffs rc = row_coeffs(a, b);
+    for (int s = tid; s < S; s += kThreads) {
+        const size_t o = (size_t)b * S + s;
+        const float4 st = reinterpret_cast<const float4*>(a.stat)[o];
+        const float2 w = reinterpret_cast<const float2*>(a.wts)[o];
+        float* c = coef + s * 6;
+        c[0] = rc.cnb[0] * w.x;           c[1] = rc.cnb[1] * w.y;
+        c[2] = -5.0f * rc.kb[0] * st.y;   c[3] = -5.0f * rc.kb[1] * st.w;
+        c[4] = 5.0f * rc.kb[0] * st.x;    c[5] = 5.0f * rc.kb[1] * st.z;
+    }
+    const float* nsrc = p.noise_ext ? p.noise_ext : p.noise_out;
+    for (int i = tid; i < S * Z; i += kThreads) nzs[i] = nsrc[((size_t)(i / Z) * B + b) * Z + (i % Z)];
+    for (int i = tid; i < kWarps * 2 * L; i += kThreads) gsum[i] = 0.f;
+    __syncthreads();
+    const float fS = (float)S, fB = (float)B;
+    const int nch = (L + 31) >> 5;
+    for (int pair = warp; pair < npairs; pair += kWarps) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int l = (c << 5) + lane;
+            if (c >= nch || l >= L) continue;
+            const float y = a.y[(size_t)b * L + l], fe = a.fe_out[(size_t)b * L + l], fx = a.fx_out[(size_t)b * L + l];
+            const float gpl = a.g_indiv_prob_label ? a.g_indiv_prob_label[(size_t)b * L + l] / fS : 0.f;
+            const float gpx = a.g_indiv_prob ? a.g_indiv_prob[(size_t)b * L + l] / fS : 0.f;
+            float gl = 0.f, gx = 0.f;
+            for (int i = 0; i < 2; ++i) {
+                const int s = (pair << 1) + i;
+                if (s >= S) break;
+                const size_t o = row_of(a, s, b) * a.ldn + l;
+                const float nr = a.nr[o];
+                const float* cf = coef + s * 6;
+                const float dl = cell_backward_saved(nr + fe, a.E_l[o], y, cf[0], cf[2], cf[4], gpl);
+                const float dx = cell_backward_saved(nr + fx, a.E_x[o], y, cf[1], cf[3], cf[5], gpx);
+                gl += dl; gx += dx;
+                gxs[(size_t)s * L + l] = dl + dx;
+            }
+            gsum[((size_t)warp * 2 + 0) * L + l] += gl;     // a warp's lane is the only writer of its entries
+            gsum[((size_t)warp * 2 + 1) * L + l] += gx;
+        }
+    }
+    __syncthreads();
+    for (int l = tid; l < L; l += kThreads) {
+        float sl = 0.f, sx = 0.f;
+        for (int w = 0; w < kWarps; ++w) { sl += gsum[((size_t)w * 2 + 0) * L + l]; sx += gsum[((size_t)w * 2 + 1) * L + l]; }
+        a.g_fe_out[(size_t)b * L + l] = sl;
+        a.g_fx_out[(size_t)b * L + l] = sx;
+    }
+    // this row's contribution to g_R[l, z] = sum_s gxs[s, l] noise[s, z]
+    if (p.partial) {
+        float* out = p.partial + (size_t)b * L * Z;
+        for (int e = tid; e < L * Z; e += kThreads) {
+            const int l = e / Z, z = e - l * Z;
+            float acc = 0.f;
+            for (int s = 0; s < S; ++s) acc = fmaf(gxs[(size_t)s * L + l], nzs[(size_t)s * Z + z], acc);
+            out[e] = acc;
+        }
+    }
+    const float kc = rc.a_kl * 0.5f / fB;
+    const size_t o = (size_t)b * a.D;
+    for (int d = tid; d < a.D; d += kThreads) {
+        const KlCell k = kl_cell(a.fe_mu[o + d], a.fe_logvar[o + d], a.fx_mu[o + d], a.fx_logvar[o + d]);
+        a.g_fe_mu[o + d] = kc * k.d_fe_mu;
+        a.g_fe_logvar[o + d] = kc * k.d_fe_lv;
+        a.g_fx_mu[o + d] = kc * k.d_fx_mu;
+        a.g_fx_logvar[o + d] = kc * k.d_fx_lv;
+    }
+}
+
+// g_R[e] = sum_b partial[b][e], rows added in order (deterministic)
+__global__ void __launch_bounds__(256)
+small_gr_reduce_kernel(const float* __restrict__ partial, float* __restrict__ g_r, int B, int n) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += partial[(size_t)b * n + e];
+    g_r[e] = acc;
+}
+
 __global__ void log_normal_probe_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ ref, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         out[i] = MPV_LOG_NORMAL(in[i]);
@@ -673,6 +848,59 @@ int device_slot() {
     return (d >= 0 && d < kMaxDevices) ? d : 0;
 }
 
+// ---- small regime (see probit_small_fwd_kernel) ----
+static size_t small_fwd_smem(int S, int L, int Z) {
+    return ((((size_t)L * Z + 3) & ~(size_t)3) + (size_t)kSmallWarps * 2 * Z + (size_t)((S + 1) / 2) * 2 * L) * sizeof(float);
+}
+static size_t small_bwd_smem(int S, int L, int Z) {
+    return ((size_t)S * 6 + (size_t)S * L + (size_t)S * Z + (size_t)kWarps * 2 * L) * sizeof(float);
+}
+bool small_regime_fits(int S, int B, int L, int Z) {
+    if (L > 128 || Z > 128 || L < 1 || Z < 1 || (long long)L * Z > 8192) return false;
+    return small_fwd_smem(S, L, Z) <= 160 * 1024 && small_bwd_smem(S, L, Z) <= 160 * 1024;
+}
+size_t small_partial_bytes(int B, int L, int Z) { return (size_t)B * L * Z * sizeof(float); }
+
+static SmallArgs small_args(const RowArgs& a, const SmallNoise& n) {
+    SmallArgs p{};
+    p.a = a;
+    p.r = n.r; p.Z = n.Z;
+    p.noise_ext = n.noise_ext; p.noise_out = n.noise_out; p.nr_out = n.nr_out;
+    p.Bg = n.Bg; p.row0 = n.row0;
+    p.key = make_uint2((uint32_t)n.seed, (uint32_t)(n.seed >> 32));
+    p.off = make_uint2((uint32_t)n.offset, (uint32_t)(n.offset >> 32));
+    p.off_dev = reinterpret_cast<const unsigned long long*>(n.offset_dev);
+    p.partial = n.partial;
+    return p;
+}
+
+int launch_small_forward(RowArgs a, const SmallNoise& n, cudaStream_t stream) {
+    const size_t smem = small_fwd_smem(a.S, a.L, n.Z);
+    static bool configured[kMaxDevices] = {};
+    const int dev = device_slot();
+    if (!configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(probit_small_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(probit_small_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(probit_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(small): %s", cudaGetErrorString(e)); return 4; }
+        configured[dev] = true;
+    }
+    const SmallArgs p = small_args(a, n);
+    if (a.stable) probit_small_fwd_kernel<true><<<a.B, kSmallThreads, smem, stream>>>(p);
+    else probit_small_fwd_kernel<false><<<a.B, kSmallThreads, smem, stream>>>(p);
+    return check_launch("probit_small_fwd_kernel");
+}
+
+int launch_small_backward(RowArgs a, const SmallNoise& n, float* g_r, cudaStream_t stream) {
+    const SmallArgs p = small_args(a, n);
+    probit_small_bwd_kernel<<<a.B, kThreads, small_bwd_smem(a.S, a.L, n.Z), stream>>>(p);
+    if (int rc = check_launch("probit_small_bwd_kernel")) return rc;
+    if (g_r == nullptr) return 0;
+    const int cnt = a.L * n.Z;
+    small_gr_reduce_kernel<<<ceil_div(cnt, 256), 256, 0, stream>>>(n.partial, g_r, a.B, cnt);
+    return check_launch("small_gr_reduce_kernel");
+}
+
 int launch_log_normal_probe(const float* in, float* out, float* ref, size_t n, cudaStream_t stream) {
     log_normal_probe_kernel<<<4 * kNumSMs, 256, 0, stream>>>(in, out, ref, n);
     return check_launch("log_normal_probe_kernel");
@@ -701,8 +929,7 @@ int launch_row_forward(RowArgs a, cudaStream_t stream) {
 
 int launch_row_finalize(RowArgs a, cudaStream_t stream) {
     if (a.part == nullptr || a.part_tiles <= 0) { set_error("row finalize: no partials"); return 1; }
-    a.nwl = pick_nwl(a.L);
-    probit_row_fwd_kernel<false, true><<<a.B, kThreads, 0, stream>>>(a);   // the tail has no cell arithmetic: one instance
+    probit_row_finalize_kernel<<<a.B, kThreads, 0, stream>>>(a);
     return check_launch("probit_row_finalize_kernel");
 }
 

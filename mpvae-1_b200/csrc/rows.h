@@ -54,6 +54,23 @@ struct RowArgs {
 };
 
 size_t row_smem_bytes(int L);
+// Small regime (L, Z <= 128, L * Z <= 8192): the whole forward of a batch row in one CTA of one launch (probit_rows.cu).
+struct SmallNoise {
+    const float* r;            // (L, Z) fp32
+    int Z;
+    const float* noise_ext;    // caller's (S, B, Z) noise, or nullptr: Philox inside the kernel
+    float* noise_out;          // fp32 (S, B, Z) copy kept for the backward (training), or nullptr
+    float* nr_out;             // (S*B, ldn) noise.R^T kept for the backward (training), or nullptr
+    int Bg, row0;
+    uint64_t seed, offset;
+    const uint64_t* offset_dev;
+    float* partial;            // backward: (B, L*Z) scratch for the per-row contributions to g_R, or nullptr
+};
+bool small_regime_fits(int S, int B, int L, int Z);
+size_t small_partial_bytes(int B, int L, int Z);
+int launch_small_forward(RowArgs a, const SmallNoise& n, cudaStream_t stream);
+// g_r may be nullptr (R frozen); needs the forward's kept nr / E / noise
+int launch_small_backward(RowArgs a, const SmallNoise& n, float* g_r, cudaStream_t stream);
 int launch_log_normal_probe(const float* in, float* out, float* ref, size_t n, cudaStream_t stream);   // test hook
 int row_chunks(int L);   // 64-label chunks of a row: launch_row_forward needs B * S * row_chunks(L) FusePart records in a.part
 int launch_row_forward(RowArgs a, cudaStream_t stream);

@@ -355,6 +355,53 @@ def test_fused_forward_equals_the_separate_row_kernel(S, B, L, Z, external):
         np.testing.assert_array_equal(a, b)             # fixed-order reductions: bit-reproducible
 
 
+@pytest.mark.parametrize("S,B,L,Z,external,mode", [(10, 128, 38, 38, True, "train"), (10, 128, 38, 38, False, "train"),
+                                                   (10, 128, 14, 14, False, "train"), (100, 128, 81, 81, False, "test"),
+                                                   (3, 33, 128, 5, True, "train"), (7, 77, 81, 81, False, "train"),
+                                                   (1, 5, 2, 1, True, "train"), (100, 32, 38, 38, False, "train"),
+                                                   (11, 300, 50, 127, False, "train")])
+def test_small_regime_kernel_equals_the_general_path(S, B, L, Z, external, mode):
+    """Label / rank sets that fit an SM (C1-C3 of BASELINE.json) run as ONE fused launch per direction
+    (probit_small_fwd_kernel: R staged by a TMA bulk copy, Philox in registers, warp-FMA contraction, row math, tail).
+    MPVAE_FLAG_CONTRACT_FMA forces the general path (Philox kernel, CUDA-core GEMM, tiled forward, finalize).  Same FMA
+    chain, same cell arithmetic, same sample order: every forward output must be BIT-equal; gradients differ only in
+    summation order (samples for the logit gradients, batch rows for g_R)."""
+    from mpvae_b200 import _lib, synth
+    from mpvae_b200.mpvae import compute_loss
+    inp = synth.loss_inputs(L, Z, B, S, seed=7 * S + B, sigma=1.0, label_rate=0.1, with_noise=external)
+    dev = torch.device("cuda:0")
+    noise = torch.from_numpy(inp.pop("noise")).to(dev) if external else None
+    train = mode == "train"
+
+    def run(flags):
+        args = orc.make_args(L, Z, n_train_sample=S, n_test_sample=S, mode=mode, noise_seed=4711, noise_offset=2, mpvae_flags=flags)
+        t = {k: torch.from_numpy(v).to(dev).requires_grad_(train and k != "y") for k, v in inp.items()}
+        launches0 = _lib.launch_count()
+        with torch.enable_grad() if train else torch.no_grad():
+            out = compute_loss(t["y"], t["fe_out"], t["fe_mu"], t["fe_logvar"], t["fx_out"], t["fx_mu"], t["fx_logvar"],
+                               t["r_sqrt_sigma"], args, **({"noise": noise} if external else {}))
+            if train:
+                out[0].backward()
+        torch.cuda.synchronize()
+        n_launch = _lib.launch_count() - launches0
+        return ([o.detach().cpu().numpy() for o in out], {k: t[k].grad.cpu().numpy() for k in H.GRAD_KEYS} if train else {}, n_launch)
+
+    small_o, small_g, n_small = run(0)
+    gen_o, gen_g, n_gen = run(_lib.FLAG_CONTRACT_FMA)
+    assert n_small == (3 if train else 1), n_small           # forward 1, backward 2 (rows + the ordered g_R sum)
+    assert n_gen > n_small
+    for a, b in zip(small_o, gen_o):
+        np.testing.assert_array_equal(a, b)
+    for k in small_g:
+        # logit gradients: the same cells summed over samples in a different (fixed) order; g_R: rows summed in order
+        assert H.rel_err(small_g[k], gen_g[k]) <= (2e-6 if k == "r_sqrt_sigma" else 5e-7), (k, H.rel_err(small_g[k], gen_g[k]))
+    again_o, again_g, _ = run(0)
+    for a, b in zip(small_o, again_o):
+        np.testing.assert_array_equal(a, b)
+    for k in small_g:
+        np.testing.assert_array_equal(small_g[k], again_g[k])
+
+
 def test_headline_configuration_rows_against_the_oracle():
     """bench.py's default workload -- eurlex-shaped S10 B1024 L3993 Z3993, the library's own Philox noise, two-pass tensor
     product with the fused row forward -- has no O(L^2)-sized oracle run.  It is tied to the oracle through a 16-row
