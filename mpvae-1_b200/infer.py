@@ -36,7 +36,9 @@ def predict_proba(model, feats: torch.Tensor, labels: torch.Tensor, args, batch_
         a, b = lo + bs * i, min(lo + bs * (i + 1), hi)
         x, y = feats[a:b], labels[a:b].float()
         args.dp_global_batch, args.dp_row0 = n, a
-        args.noise_offset = getattr(args, "noise_offset_base", 0) + i
+        # one Philox offset for the whole pass: a row's noise is keyed by its GLOBAL row index (dp_row0 + local row), so
+        # predictions do not depend on the world size or on how the rows are batched
+        args.noise_offset = getattr(args, "noise_offset_base", 0)
         label_out, label_mu, label_logvar, feat_out, feat_mu, feat_logvar = model(y, x)
         out = loss_fn(y, label_out, label_mu, label_logvar, feat_out, feat_mu, feat_logvar, model.r_sqrt_sigma, args)
         probs.append(out[6])

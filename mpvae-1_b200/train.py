@@ -85,6 +85,13 @@ class DataParallelStep:
         self.group = group
         self.world = dist.get_world_size(group) if (distributed and dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
+        # Only the probit noise is keyed by the GLOBAL row (Philox), so the loss is independent of the world size given
+        # the encoder outputs.  Dropout masks and the reparameterisation eps come from torch's generator, which every
+        # rank seeds identically (needed for identical initial weights): without the offset below all ranks would draw
+        # the SAME eps / masks for their different rows.  `decorrelate_rng()` moves this rank's generators to a
+        # rank-specific stream; call it AFTER the model has been built.  (Those draws then still depend on the world
+        # size: that is inherent to sharding torch's generator and is a documented limitation.)
+        self._rng_decorrelated = False
         self._library_loss = loss_fn is None
         if loss_fn is None:
             from .mpvae import compute_loss as loss_fn
@@ -101,6 +108,7 @@ class DataParallelStep:
         others = [p for n, p in model.named_parameters() if p is not self.r_param]
         self.bucket = GradBucket(self.r_shadow, others)
         self._pending = []
+        self._r_issued = False          # the g_R segment's all-reduce of this step has been issued
         # peer_g_r=True: g_R is summed over the ranks inside the probit backward, over NVLink peer memory (peer.py),
         # instead of the NCCL all-reduce of that bucket segment.  Off by default: measured on 2 and 4 B200 the
         # exchange itself is 5-15 % faster than NCCL's (both move the same bytes over NVLink), but inside the
@@ -111,6 +119,13 @@ class DataParallelStep:
         self._shadow_fresh = False      # the fused optimizer wrote the fp32 shadow of R during the last step
         if self.world > 1 and self.r_shadow is not None:
             self.r_shadow.register_post_accumulate_grad_hook(self._reduce_r_early)
+
+    def decorrelate_rng(self, base_seed: Optional[int] = None):
+        """Give this rank its own dropout / reparameterisation random stream (see __init__)."""
+        if self.world > 1 and not self._rng_decorrelated:
+            seed = (torch.initial_seed() if base_seed is None else int(base_seed)) + 7919 * (self.rank + 1)
+            torch.manual_seed(seed)
+            self._rng_decorrelated = True
 
     # -- collectives --------------------------------------------------------------------------------------
     def _peer_ring(self, n_rows: int):
@@ -129,21 +144,27 @@ class DataParallelStep:
 
     def _reduce_r_early(self, _):
         """Fires as soon as the probit backward has written g_R: overlap its all-reduce with the MLP backward."""
-        if self._ring_step:
-            return                                # g_R arrived already summed (peer ring)
+        if self._ring_step or self._r_issued:
+            return                                # g_R arrived already summed (peer ring) / already on its way
+        self._r_issued = True
         seg = self.bucket.flat[:self.bucket.r_numel]
         self._pending.append(dist.all_reduce(seg, group=self.group, async_op=True))
 
     def _finish_reduce(self, divide: bool = True):
+        """Every rank issues the SAME collectives in the SAME order whatever its local data was: first the g_R segment
+        (from the hook if the probit backward ran on this rank, else here -- an empty shard, a frozen forward),
+        then the MLP gradients.  A rank whose sequence depended on its shard would hang NCCL."""
         if self.world == 1:
             return
-        start = self.bucket.r_numel if (self._pending or self._ring_step) else 0
-        seg = self.bucket.flat[start:]
+        if self.bucket.r_numel and not self._ring_step:
+            self._reduce_r_early(None)            # no-op when the hook already issued it
+        seg = self.bucket.flat[self.bucket.r_numel:]
         if seg.numel():
             self._pending.append(dist.all_reduce(seg, group=self.group, async_op=True))
         for w in self._pending:
             w.wait()
         self._pending = []
+        self._r_issued = False
         if divide:
             self.bucket.flat.div_(self.world)
 
@@ -169,20 +190,28 @@ class DataParallelStep:
             with torch.no_grad():
                 self.r_shadow.copy_(self.r_param)
         self.bucket.attach(self.r_shadow)             # optimizer.zero_grad() of train.py:103 (in place, one memset)
+        self._r_issued = False
 
-        label_out, label_mu, label_logvar, feat_out, feat_mu, feat_logvar = self.model(y, x)
-        r = r_override if r_override is not None else (self.r_shadow if self.r_shadow is not None
-                                                        else self.model.r_sqrt_sigma)
-        kw = {} if noise is None else {"noise": noise[:, lo:hi]}
-        out = self.loss_fn(y, label_out, label_mu, label_logvar, feat_out, feat_mu, feat_logvar, r, args, **kw)
-        total = out[0]
-        if self.regulariser is not None:
-            extra = self.regulariser(out, slice(lo, hi))
-            if extra is not None:
-                total = total + extra
-        # every term is a mean over this rank's rows; weight by the shard size so unequal shards still average right
-        weight = (hi - lo) * self.world / max(n_rows, 1)
-        (total * weight if weight != 1.0 else total).backward()
+        if hi > lo or self.world == 1:
+            label_out, label_mu, label_logvar, feat_out, feat_mu, feat_logvar = self.model(y, x)
+            r = r_override if r_override is not None else (self.r_shadow if self.r_shadow is not None
+                                                            else self.model.r_sqrt_sigma)
+            kw = {} if noise is None else {"noise": noise[:, lo:hi]}
+            out = self.loss_fn(y, label_out, label_mu, label_logvar, feat_out, feat_mu, feat_logvar, r, args, **kw)
+            total = out[0]
+            if self.regulariser is not None:
+                extra = self.regulariser(out, slice(lo, hi))
+                if extra is not None:
+                    total = total + extra
+            # every term is a mean over this rank's rows; weight by the shard size so unequal shards still average right
+            weight = (hi - lo) * self.world / max(n_rows, 1)
+            (total * weight if weight != 1.0 else total).backward()
+        else:
+            # a ragged last batch with fewer rows than ranks leaves this rank without a row: it contributes zero
+            # gradients (the bucket was just zeroed) and zero-weighted scalars, and still joins every collective below
+            zero = self.bucket.flat.new_zeros(())
+            empty = input_label.new_zeros((0, input_label.shape[1]), dtype=torch.float32)
+            out = (zero,) * 6 + (empty, empty)
         from .optim import FusedAdam
         fused = isinstance(self.optimizer, FusedAdam) and not self.skip_nonfinite and total.is_cuda
         self._finish_reduce(divide=not fused)
@@ -213,23 +242,25 @@ class DataParallelStep:
         self.step_no += 1
         scal = [t.detach() for t in out[:6]]
         if self.world > 1:
-            packed = torch.stack(scal) * ((hi - lo) / max(n_rows, 1))
+            packed = torch.stack([t.float() for t in scal]) * ((hi - lo) / max(n_rows, 1))
             dist.all_reduce(packed, group=self.group)
             scal = list(packed.unbind(0))
         return StepOutput(*scal, out[6].detach(), out[7].detach(), grad_norm, stepped)
 
 
-def train_one_epoch(step: DataParallelStep, feats, labels, batch_size: int, order=None):
+def train_one_epoch(step: DataParallelStep, feats, labels, batch_size: int, order=None, skip_empty: bool = True):
     """Epoch driver with the reference's batching (train.py:98-111): int(N/bs)+1 steps, ragged (possibly empty)
-    last batch.  `feats` / `labels` are device tensors (kept resident: SURVEY 8f-N4); returns per-step outputs."""
+    last batch.  `feats` / `labels` are device tensors (kept resident: SURVEY 8f-N4); returns per-step outputs.
+    `skip_empty=False` reproduces the reference literally when bs | N: it runs the step on the empty batch, whose
+    losses are NaN means (train.py:102; compute_loss returns them) and whose NaN gradients then reach Adam."""
     n = feats.shape[0]
     if order is None:
         order = torch.arange(n, device=feats.device)
     outs = []
     for i in range(int(n / float(batch_size)) + 1):
         idx = order[i * batch_size:min(batch_size * (i + 1), n)]
-        if idx.numel() == 0:
-            continue          # the reference computes NaN losses on the empty batch and steps on them; we skip it
+        if idx.numel() == 0 and skip_empty:
+            continue          # the reference computes NaN losses on the empty batch and steps on them
         outs.append(step.step(labels[idx], feats[idx]))
     return outs
 
@@ -273,9 +304,52 @@ class GraphedTrainStep:
                 # a Python float would be baked into the captured launch; StepLR writes into the tensor between replays
                 raise ValueError("FusedAdam under graph capture needs lr as a CUDA tensor: lr=torch.tensor(1e-3, device=...)")
 
+    # -- warm-up runs on a snapshot: the first step() must be exactly ONE update, like the reference loop ----------
+    def _snapshot(self):
+        from .optim import FusedAdam
+        st, opt = self.stepper, self.stepper.optimizer
+        if isinstance(opt, FusedAdam) and opt._segments is None:
+            opt._build()                                                  # flat buffers first: p.data become views of them
+        snap = {"params": [p.detach().clone() for p in st.model.parameters()],
+                "r_shadow": None if st.r_shadow is None else st.r_shadow.detach().clone(),
+                "step_no": st.step_no, "shadow_fresh": st._shadow_fresh, "counter": self.counter.clone(),
+                "rng_cuda": torch.cuda.get_rng_state(self.device), "rng_cpu": torch.get_rng_state()}
+        if isinstance(opt, FusedAdam):
+            snap["fused"] = ([(seg.flat_m.clone(), seg.flat_v.clone()) for seg in opt._segments], opt._scal.clone())
+        else:
+            snap["opt"] = {p: {k: (v.clone() if torch.is_tensor(v) else v) for k, v in s.items()} for p, s in opt.state.items()}
+        return snap
+
+    @torch.no_grad()
+    def _restore(self, snap):
+        from .optim import FusedAdam
+        st, opt = self.stepper, self.stepper.optimizer
+        for p, saved in zip(st.model.parameters(), snap["params"]):
+            p.data.copy_(saved)
+        if snap["r_shadow"] is not None:
+            st.r_shadow.copy_(snap["r_shadow"])
+        st.step_no, st._shadow_fresh = snap["step_no"], snap["shadow_fresh"]
+        self.counter.copy_(snap["counter"])
+        torch.cuda.set_rng_state(snap["rng_cuda"], self.device)
+        torch.set_rng_state(snap["rng_cpu"])
+        if isinstance(opt, FusedAdam):
+            for seg, (m, v) in zip(opt._segments, snap["fused"][0]):
+                seg.flat_m.copy_(m); seg.flat_v.copy_(v)
+            opt._scal.copy_(snap["fused"][1])
+        else:
+            # in place: the captured graph holds the addresses of the state tensors the warm-up created
+            for p, s in opt.state.items():
+                old = snap["opt"].get(p)
+                for k, v in s.items():
+                    if torch.is_tensor(v):
+                        if old is not None and k in old:
+                            v.copy_(old[k])
+                        else:
+                            v.zero_()                                     # state born during the warm-up: back to "fresh"
+
     def _capture(self, y, x):
-        st = self.stepper
         static_y, static_x = y.clone(), x.clone()
+        snap = self._snapshot()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -285,6 +359,7 @@ class GraphedTrainStep:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             out = self._body(static_y, static_x)
+        self._restore(snap)                                               # parameters, moments, counters, RNG: as before
         return {"graph": graph, "y": static_y, "x": static_x, "out": out}
 
     def _body(self, y, x):
@@ -301,8 +376,7 @@ class GraphedTrainStep:
         key = (tuple(input_label.shape), tuple(input_feat.shape))
         entry = self.graphs.get(key)
         if entry is None:
-            entry = self.graphs[key] = self._capture(input_label, input_feat)
-            # the warm-up + capture already consumed this batch `warmup` times; from here on every call is one step
+            entry = self.graphs[key] = self._capture(input_label, input_feat)   # warm-up ran on a snapshot: no update yet
         entry["y"].copy_(input_label)
         entry["x"].copy_(input_feat)
         entry["graph"].replay()

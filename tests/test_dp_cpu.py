@@ -80,6 +80,12 @@ def _worker(rank, world, port, ret):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         torch.set_num_threads(1)
+        if ret.get("mode") == "one_row":
+            # a ragged last batch with fewer rows than ranks: rank 1 owns no row and must still join every collective
+            model, outs = run_steps(n_steps=2, batch=1)
+            ret[rank] = ({k: v.clone() for k, v in model.state_dict().items()},
+                         [tuple(float(t) for t in o[:6]) for o in outs], [float(o.grad_norm) for o in outs], None)
+            return
         model, outs = run_steps()
         sd = {k: v.clone() for k, v in model.state_dict().items()}
         # inference: sharded scoring + gather
@@ -133,6 +139,37 @@ def test_two_ranks_equal_one_process():
         assert torch.equal(ret[0][0][k], ret[1][0][k]), k
     assert torch.equal(ret[0][3], ret[1][3])
     assert ret[0][3].shape == (23, 9)
+
+
+@pytest.mark.timeout(300)
+def test_fewer_rows_than_ranks():
+    """N % batch in [1, world) leaves a rank with an empty shard.  The collective sequence must not depend
+    on local data (no hang), the empty rank contributes zero gradients and zero-weighted scalars (no NaN), and the result
+    equals the single-process step on that one row."""
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    ret["mode"] = "one_row"
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+        assert p.exitcode == 0
+    model, outs = run_steps(n_steps=2, batch=1)
+    ref_sd = model.state_dict()
+    for rank in range(2):
+        sd, scal, norms, _ = ret[rank]
+        for k in ref_sd:
+            assert torch.allclose(sd[k].double(), ref_sd[k].double(), rtol=2e-4, atol=2e-6), (rank, k)
+        for got, want in zip(scal, outs):
+            for a, b in zip(got, want[:6]):
+                assert np.isfinite(a) and abs(a - float(b)) <= 2e-5 * max(1.0, abs(float(b))), (rank, a, float(b))
+        for a, b in zip(norms, outs):
+            assert abs(a - float(b.grad_norm)) <= 1e-4 * max(1.0, float(b.grad_norm))
 
 
 def test_shard_rows_cover_everything():

@@ -59,7 +59,7 @@ def test_workspace_sizes(lib):
     both = lib.mpvae_workspace_bytes(S, B, L, Z, 1, 0)
     cube = S * B * L * 4
     assert fwd >= cube and both >= fwd + cube
-    assert both < 4 * cube + (1 << 20)
+    assert both < 6 * cube + (2 << 20)        # nr, E_l, E_x, gxs, fp32 noise + the per-row g_R shares and statistics
     assert lib.mpvae_workspace_bytes(10, 1024, 3993, 3993, 1, 0) < 2 << 30
     assert lib.mpvae_workspace_bytes(0, 0, 0, 0, 1, 0) == 256
 
@@ -158,3 +158,32 @@ def test_host_wrappers_have_no_cpu_path():
     layer, x = torch.nn.Linear(2048, 1024), torch.randn(256, 2048)
     assert not uses_tensor_engine(layer, x)
     assert torch.equal(linear(layer, x), layer(x))
+
+
+def _integration_stub_source():
+    """The ```python block of INTEGRATION.md section 2 (the binding a reference maintainer would paste into mpvae.py)."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    sec = text[text.index("## 2. Raw C-ABI"):]
+    block = sec[sec.index("```python") + len("```python"):]
+    block = block[:block.index("```")]
+    from mpvae_b200 import _lib
+    return block.replace('"libmpvae_b200.so"', repr(_lib.LIB_PATH))
+
+
+def test_integration_stub_struct_matches_the_header(lib):
+    """The stub's struct is a PREFIX of mpvae_probit_params (it stops before the peer_* fields): its size must be the
+    MPVAE_PARAMS_BASE_BYTES the library accepts, field by field the same offsets as the maintained binding."""
+    import ctypes as C
+    from mpvae_b200 import _lib
+    ns = {}
+    exec(_integration_stub_source(), ns)           # defines P, _ProbitELBO, compute_loss against the built library
+    P = ns["P"]
+    assert C.sizeof(P) == _lib.PARAMS_BASE_BYTES
+    full = {n: getattr(_lib.ProbitParams, n).offset for n, _ in _lib.ProbitParams._fields_}
+    for name, _ in P._fields_:
+        assert getattr(P, name).offset == full[name], name
+    # the library takes exactly the two sizes: a params block of any other size is refused before anything is launched
+    p = _lib.ProbitParams()
+    p.struct_bytes = _lib.PARAMS_BASE_BYTES - 8
+    assert lib.mpvae_probit_forward(C.byref(p), None) == 1
+    assert b"struct_bytes" in lib.mpvae_last_error()

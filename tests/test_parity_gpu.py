@@ -584,3 +584,25 @@ def test_inference_with_many_samples():
         assert H.rel_err(got_o[k], dev_o[k]) <= 1e-5, (k, H.rel_err(got_o[k], dev_o[k]))
     assert H.threshold_mismatches(got_o["indiv_prob"], dev_o["indiv_prob"], tie=2.5e-7) == 0
     assert float(np.max(np.abs(got_o["indiv_prob"] - dev_o["indiv_prob"]))) <= 2e-6   # S = 2000 fp32 mean
+
+
+def test_integration_stub_runs():
+    """the condensed ctypes binding (struct without the peer_* fields) drives the library's
+    forward and agrees with the maintained binding on the same noise."""
+    from tests.test_lib_cpu import _integration_stub_source
+    from mpvae_b200.mpvae import compute_loss
+    ns = {}
+    exec(_integration_stub_source(), ns)
+    case = H.load_golden("mirflickr_b16")
+    dev = torch.device("cuda:0")
+    t = {k: torch.from_numpy(v).to(dev) for k, v in case["inputs"].items()}
+    noise = torch.from_numpy(case["noise"]).to(dev)
+    args = orc.make_args(case["L"], case["Z"], n_train_sample=case["S"])
+    with torch.no_grad():
+        got = ns["_ProbitELBO"].apply(t["y"], t["fe_out"], t["fe_mu"], t["fe_logvar"], t["fx_out"], t["fx_mu"], t["fx_logvar"],
+                                      t["r_sqrt_sigma"].float(), noise, args.nll_coeff, args.c_coeff)
+        want = compute_loss(t["y"], t["fe_out"], t["fe_mu"], t["fe_logvar"], t["fx_out"], t["fx_mu"], t["fx_logvar"],
+                            t["r_sqrt_sigma"], args, noise=noise)
+    torch.cuda.synchronize()
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
