@@ -92,6 +92,7 @@ class DataParallelStep:
         # rank-specific stream; call it AFTER the model has been built.  (Those draws then still depend on the world
         # size: that is inherent to sharding torch's generator and is a documented limitation.)
         self._rng_decorrelated = False
+        self._inline_collectives = False
         self._library_loss = loss_fn is None
         if loss_fn is None:
             from .mpvae import compute_loss as loss_fn
@@ -109,6 +110,8 @@ class DataParallelStep:
         self.bucket = GradBucket(self.r_shadow, others)
         self._pending = []
         self._r_issued = False          # the g_R segment's all-reduce of this step has been issued
+        # CUDA-graph capture (GraphedTrainStep): every collective is issued from the main thread, on the capture stream,
+        # synchronously -- an all-reduce launched from the autograd hook thread hung the capture at 2 ranks
         # peer_g_r=True: g_R is summed over the ranks inside the probit backward, over NVLink peer memory (peer.py),
         # instead of the NCCL all-reduce of that bucket segment.  Off by default: measured on 2 and 4 B200 the
         # exchange itself is 5-15 % faster than NCCL's (both move the same bytes over NVLink), but inside the
@@ -144,11 +147,14 @@ class DataParallelStep:
 
     def _reduce_r_early(self, _):
         """Fires as soon as the probit backward has written g_R: overlap its all-reduce with the MLP backward."""
-        if self._ring_step or self._r_issued:
-            return                                # g_R arrived already summed (peer ring) / already on its way
+        if self._ring_step or self._r_issued or (self._inline_collectives and _ is not None):
+            return                                # g_R arrived already summed (peer ring) / already on its way / inline mode
         self._r_issued = True
         seg = self.bucket.flat[:self.bucket.r_numel]
-        self._pending.append(dist.all_reduce(seg, group=self.group, async_op=True))
+        if self._inline_collectives:
+            dist.all_reduce(seg, group=self.group)
+        else:
+            self._pending.append(dist.all_reduce(seg, group=self.group, async_op=True))
 
     def _finish_reduce(self, divide: bool = True):
         """Every rank issues the SAME collectives in the SAME order whatever its local data was: first the g_R segment
@@ -160,7 +166,10 @@ class DataParallelStep:
             self._reduce_r_early(None)            # no-op when the hook already issued it
         seg = self.bucket.flat[self.bucket.r_numel:]
         if seg.numel():
-            self._pending.append(dist.all_reduce(seg, group=self.group, async_op=True))
+            if self._inline_collectives:
+                dist.all_reduce(seg, group=self.group)
+            else:
+                self._pending.append(dist.all_reduce(seg, group=self.group, async_op=True))
         for w in self._pending:
             w.wait()
         self._pending = []
@@ -277,16 +286,19 @@ class GraphedTrainStep:
       * Adam runs with `capturable=True` and a tensor learning rate; StepLR keeps running on the host between
         replays and writes the new rate into that tensor;
       * gradients are views into the flat bucket (no per-step allocation).
-    Not supported in graph mode: world_size > 1 (see __init__), `skip_nonfinite` (needs a host decision) and Python-side regularisers that branch
+    With world_size > 1 the collectives are captured too (issued inline from the capturing thread, see __init__).
+    Not supported in graph mode: `skip_nonfinite` (needs a host decision) and Python-side regularisers that branch
     on data.  Outputs are static tensors that the next replay overwrites."""
 
     def __init__(self, stepper: DataParallelStep, warmup: int = 3):
         if stepper.skip_nonfinite:
             raise ValueError("GraphedTrainStep cannot skip non-finite steps (host decision); use DataParallelStep")
         if stepper.world > 1:
-            # capturing the NCCL all-reduces (one of them issued from an autograd hook thread) hung a 2-rank run on
-            # B200; until that is understood the graph path is single-process only
-            raise NotImplementedError("GraphedTrainStep is single-process only; use DataParallelStep under torchrun")
+            # Captured collectives must come from the capturing thread on the capture stream: the early all-reduce of
+            # g_R from the autograd hook thread is what hung a 2-rank capture in round 1.  In graph mode the stepper
+            # issues its all-reduces inline after the backward; with the peer ring the flag values come from a device
+            # counter the exchange kernels advance themselves (PeerRing.enable_graph_replay).
+            stepper._inline_collectives = True
         self.stepper = stepper
         self.warmup = warmup
         self.graphs = {}
@@ -349,6 +361,11 @@ class GraphedTrainStep:
 
     def _capture(self, y, x):
         static_y, static_x = y.clone(), x.clone()
+        st = self.stepper
+        if st.world > 1 and st._want_ring:
+            ring = st._peer_ring(y.shape[0])
+            if ring is not None:
+                ring.enable_graph_replay()
         snap = self._snapshot()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))

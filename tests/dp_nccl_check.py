@@ -67,6 +67,29 @@ def main():
         if step.ring is not None:
             step.ring.close()
         ok &= worst < 2e-4 and dl < 1e-5
+    # the CUDA-graph step under N ranks: collectives captured (issued inline from the capturing thread); same trajectory
+    # as the eager N-rank step
+    if os.environ.get("DP_CHECK_GRAPH", "1") == "1":
+        for (L, Z, F, B, peer) in ((38, 38, 100, 128, False), (983, 983, 64, 256, False), (983, 983, 64, 256, True)):
+            rng = np.random.RandomState(2)
+            x = torch.from_numpy(synth.features(B, F, rng)).to(dev)
+            y = torch.from_numpy(synth.labels(B, L, 0.1, rng)).to(dev)
+            losses = []
+            for graphed in (False, True):
+                vae, _, args = build(dev, L, Z, F, True)
+                from mpvae_b200.optim import FusedAdam
+                opt = FusedAdam(vae.parameters(), lr=torch.tensor(1e-3, device=dev), weight_decay=1e-5)
+                step = DataParallelStep(vae, opt, None, args, clip_norm=100.0, peer_g_r=peer)
+                fn = GraphedTrainStep(step).step if graphed else step.step
+                losses.append([float(fn(y, x).total_loss) for _ in range(4)])
+                torch.cuda.synchronize()
+                if step.ring is not None:
+                    step.ring.check()
+                    step.ring.close()
+            dl = max(abs(a - b) / abs(b) for a, b in zip(losses[1], losses[0]))
+            if rank == 0:
+                print(f"graphed vs eager, {world} ranks, L={L} peer_g_r={peer}: worst loss rel diff {dl:.2e}", flush=True)
+            ok &= dl < 2e-4
     t = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -14,7 +14,6 @@ import torch.distributed as dist
 from mpvae_b200 import synth
 from mpvae_b200.mpvae import compute_loss
 from mpvae_b200.peer import NvlsRing, PeerRing
-from oracle.probit_elbo_oracle import make_args          # args factory only (no oracle arithmetic is used here)
 
 
 def main():
@@ -31,7 +30,7 @@ def main():
         ring = (NvlsRing if os.environ.get("PEER_CHECK_RING") == "nvls" else PeerRing)(L, Z, dev)
 
         def run(use_ring, step):
-            args = make_args(L, Z, n_train_sample=S, noise_seed=5, noise_offset=step)
+            args = synth.make_args(L, Z, n_train_sample=S, noise_seed=5, noise_offset=step)
             args.dp_global_batch, args.dp_row0 = B * world, rank * B
             args.peer_ring = ring if use_ring else None
             leaves = {k: (v if k in ("y", "r_sqrt_sigma") else v.clone().requires_grad_(True)) for k, v in t.items()}
