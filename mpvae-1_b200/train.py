@@ -286,19 +286,21 @@ class GraphedTrainStep:
       * Adam runs with `capturable=True` and a tensor learning rate; StepLR keeps running on the host between
         replays and writes the new rate into that tensor;
       * gradients are views into the flat bucket (no per-step allocation).
-    With world_size > 1 the collectives are captured too (issued inline from the capturing thread, see __init__).
-    Not supported in graph mode: `skip_nonfinite` (needs a host decision) and Python-side regularisers that branch
-    on data.  Outputs are static tensors that the next replay overwrites."""
+    Not supported in graph mode: world_size > 1 (see __init__), `skip_nonfinite` (needs a host decision) and Python-side
+    regularisers that branch on data.  Outputs are static tensors that the next replay overwrites."""
 
     def __init__(self, stepper: DataParallelStep, warmup: int = 3):
         if stepper.skip_nonfinite:
             raise ValueError("GraphedTrainStep cannot skip non-finite steps (host decision); use DataParallelStep")
         if stepper.world > 1:
-            # Captured collectives must come from the capturing thread on the capture stream: the early all-reduce of
-            # g_R from the autograd hook thread is what hung a 2-rank capture in round 1.  In graph mode the stepper
-            # issues its all-reduces inline after the backward; with the peer ring the flag values come from a device
-            # counter the exchange kernels advance themselves (PeerRing.enable_graph_replay).
-            stepper._inline_collectives = True
+            # Capturing NCCL all-reduces hangs on this stack (torch 2.11 / NCCL 2.28.9, 2 x B200): in round 1 with the
+            # early all-reduce issued from the autograd hook thread, and again in round 2 with every collective issued
+            # inline from the capturing thread on the capture stream (DataParallelStep._inline_collectives; 10 min
+            # until the test's timeout, profiles/r02_graph_multi_gpu.md).  The library side is ready for an NCCL-free
+            # graph step -- the peer-memory exchange takes its flag values from a device counter
+            # (PeerRing.enable_graph_replay, mpvae_probit_params.peer_step_dev) -- but the MLP gradients still travel
+            # by NCCL, so the graph path stays single-process.
+            raise NotImplementedError("GraphedTrainStep is single-process only; use DataParallelStep under torchrun")
         self.stepper = stepper
         self.warmup = warmup
         self.graphs = {}

@@ -1,7 +1,6 @@
 """Multi-GPU correctness as -m gpu tests: each runs one of the torchrun check scripts on 2 GPUs of this box and is skipped
 when the box has fewer (the driver's single-GPU tiers).  tests/dp_nccl_check.py: N ranks on shards walk the trajectory of
-one rank on the full batch (NCCL bucket, g_R over the peer ring, fused Adam, and the CUDA-graph step with captured
-collectives).  tests/peer_check.py: g_R summed over NVLink peer memory inside the backward == NCCL all-reduce of the
+one rank on the full batch (NCCL bucket, g_R over the peer ring, fused Adam).  tests/peer_check.py: g_R summed over NVLink peer memory inside the backward == NCCL all-reduce of the
 partials, bit-identical on every rank, buffers reused over steps."""
 import os
 import socket
@@ -15,7 +14,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _torchrun(script, nproc=2, env=None, timeout=600):
+def _torchrun(script, nproc=2, env=None, timeout=240):
     if torch.cuda.device_count() < nproc:
         pytest.skip(f"needs {nproc} GPUs, this box has {torch.cuda.device_count()}")
     with socket.socket() as s:
