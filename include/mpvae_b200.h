@@ -46,6 +46,9 @@ extern "C" {
                                                before the product instead of on the product kernel's math warps, just
                                                ahead of the tiles that read them (A/B measurements; same numbers) */
 
+#define MPVAE_FLAG_SEPARATE_EXCHANGE    0x40u /* data-parallel dense regime: sum g_R over the ranks with the stand-alone reduce kernel
+                                               after the product instead of tile by tile inside it (A/B; same sums) */
+
 /* order of the six scalar outputs (first six entries of the 8-tuple at mpvae.py:210) */
 enum { MPVAE_TOTAL = 0, MPVAE_NLL = 1, MPVAE_NLL_X = 2, MPVAE_C = 3, MPVAE_C_X = 4, MPVAE_KL = 5 };
 
@@ -118,7 +121,14 @@ typedef struct mpvae_probit_params {
     /* optional DEVICE counter added to peer_step inside the exchange kernels and advanced by them after every exchange,
        so that a captured CUDA graph (which replays the same peer_step) keeps the flag values increasing; NULL = unused */
     uint32_t *peer_step_dev;
+    /* optional: every rank's per-tile completion counters (mpvae_peer_alloc'ed, MPVAE_PEER_TILE_BYTES each, zeroed once).
+       With them the g_R product of the dense regime sums its finished 256 x 256 tiles over the ranks INSIDE the product
+       kernel (csrc/fused_rows.cuh: tile t belongs to rank t mod world, whose math warps pull it from every rank over
+       NVLink, add in rank order and store to every rank) while the tensor pipe computes later tiles; NULL = the
+       stand-alone reduce kernel after the product */
+    void *peer_tile_done[8];
 } mpvae_probit_params;
+#define MPVAE_PEER_TILE_BYTES 65536u
 
 /* size of the struct up to (not including) peer_world: what a binding without the multi-GPU fields fills in */
 #define MPVAE_PARAMS_BASE_BYTES ((uint32_t)offsetof(mpvae_probit_params, peer_world))

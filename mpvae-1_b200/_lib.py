@@ -19,6 +19,8 @@ FLAG_CONTRACT_FMA = 0x4
 FLAG_STABLE_CDF = 0x8
 FLAG_FUSED_FORWARD = 0x10
 FLAG_SEPARATE_NOISE = 0x20
+FLAG_SEPARATE_EXCHANGE = 0x40
+PEER_TILE_BYTES = 65536
 
 # every symbol include/mpvae_b200.h declares
 EXPORTS = (
@@ -54,6 +56,7 @@ class ProbitParams(C.Structure):
         ("peer_part", _f * 8), ("peer_g_r", _f * 8), ("peer_flags", _f * 8),
         ("peer_mc_part", _f), ("peer_mc_g_r", _f),
         ("peer_step_dev", _f),
+        ("peer_tile_done", _f * 8),
     ]
 
 

@@ -482,9 +482,36 @@ int mpvae_probit_backward(const mpvae_probit_params* p_in, void* cuda_stream) {
         ProfScope ps(MPVAE_PROF_PRODUCT_TN, stream);
         int rc;
         if (tensor) {
+            // data-parallel: the finished tiles are summed over the ranks inside the product kernel (fused_rows.cuh)
+            FusePeer fp{};
+            const bool fused_x = peer && p->peer_tile_done[p->peer_rank] != nullptr && !(p->flags & MPVAE_FLAG_SEPARATE_EXCHANGE) &&
+                                 !(p->peer_mc_part && p->peer_mc_g_r) &&
+                                 (size_t)ceil_div(p->L, 256) * ceil_div(p->Z, 256) * sizeof(uint32_t) <= MPVAE_PEER_TILE_BYTES;
+            if (fused_x) {
+                fp.world = pctx.world; fp.rank = pctx.rank; fp.step = pctx.step; fp.step_dev = pctx.step_dev;
+                fp.timeout_cycles = pctx.timeout_cycles;
+                fp.err = pctx.flags[pctx.rank] + peer_error_word();
+                for (int i = 0; i < pctx.world; ++i) {
+                    fp.part[i] = pctx.part[i]; fp.g_r[i] = pctx.g_r[i];
+                    fp.done[i] = static_cast<unsigned int*>(p->peer_tile_done[i]);
+                    if (!fp.done[i]) { set_error("peer tables: NULL tile counters for rank %d", i); return 1; }
+                }
+                fp.Mc = p->L; fp.Nc = p->Z; fp.ldc = p->Z;
+            }
+            int exchanged = 0;
             // the noise planes the forward left in the workspace are the MN-major B operand as they are
             rc = tc_gemm_tn(base + w.gxs_planes, base + w.noise_planes, g_r_out, M, p->L, p->Z, slots + SLOT_ABSMAX_GXS, nullptr, stream,
-                            p->noise ? 0 : 1, base + w.tn_tail, tc_tail_scratch_bytes());
+                            p->noise ? 0 : 1, base + w.tn_tail, tc_tail_scratch_bytes(), 0, fused_x ? &fp : nullptr, &exchanged);
+            if (rc) return rc;
+            if (fused_x) {
+                // what is left: the rows of the K-sliced tail tiles (complete only now, after the fix-up kernel), and the
+                // two flag phases that tell every rank that all deliveries of this step have landed
+                const int tiles_n = ceil_div(p->Z, 256);
+                const size_t first_row = (size_t)(exchanged / tiles_n) * 256;
+                const size_t first = first_row < (size_t)p->L ? first_row * p->Z : (size_t)p->L * p->Z;
+                ProfScope px(MPVAE_PROF_EXCHANGE, stream);
+                return launch_peer_reduce(pctx, (size_t)p->L * p->Z - first, stream, first);
+            }
         } else {
             const float* nz = p->noise ? p->noise : reinterpret_cast<const float*>(base + w.noise_f32);
             rc = launch_contract_tn_fma(a.gxs, nz, g_r_out, M, p->L, p->Z, base + w.fma_partials, w.total - w.fma_partials, stream,

@@ -220,11 +220,12 @@ struct GemmArgs {
 };
 
 // MATH: what the eight extra "math" warps of the CTA do (fused_rows.cuh): 0 = there are none, 1 = the probit row
-// forward on finished tiles (opt-in), 2 = draw the Philox noise of the A operand just ahead of the tiles that read it.
+// forward on finished tiles (opt-in), 2 = draw the Philox noise of the A operand just ahead of the tiles that read it,
+// 3 = sum the finished tiles over the ranks of a data-parallel run through NVLink peer memory.
 template <bool MN, int EX, int MATH, bool STABLE>
 __global__ void __launch_bounds__(threads_of(MATH), 1)
 gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g,
-                      const FuseFwd fz, const FuseNoise fnz) {
+                      const FuseFwd fz, const FuseNoise fnz, const FusePeer fpz) {
     constexpr bool FUSE = MATH != 0;
     using G = Geo<MN>;
     using R2 = Ring<EX>;
@@ -364,8 +365,10 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (MATH == 1) {         // row math of the probit forward on finished tiles
             float* pacc = reinterpret_cast<float*>(gen + R2::RING_BYTES + BAR_BYTES) + mw * 512;
             fuse_math_loop<STABLE>(fz, cluster, num_clusters, num_tiles, g.tiles_n, (int)rank * kFuseMathWarps + mw, pacc, lane);
-        } else {                 // the A operand's Philox noise, just ahead of the tiles
+        } else if (MATH == 2) {  // the A operand's Philox noise, just ahead of the tiles
             noise_math_loop(fnz, (int)blockIdx.x * kFuseMathWarps + mw, (int)gridDim.x * kFuseMathWarps, lane);
+        } else {                 // this rank's tiles of the sum over the ranks
+            peer_math_loop(fpz, (int)blockIdx.x * kFuseMathWarps + mw, (int)gridDim.x * kFuseMathWarps, lane);
         }
     } else {   // --------------------------------------------------- promotion + epilogue (both CTAs, own 128 rows)
         if (FUSE) reg_inc<kRegEpi>();
@@ -435,6 +438,7 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 }
             }
             if (MATH == 1) fuse_signal_tile(fz.done, st, lane);   // this warp's part of the tile is in memory
+            if (MATH == 3 && it.slice == 0 && st < fpz.full_tiles) peer_signal_tile(fpz, st, lane);
 #pragma unroll
             for (int j = 0; j < 64; ++j) acc[j] = 0.0f;
         }
@@ -606,7 +610,7 @@ int current_device() {
 
 template <bool MN, int EX, int MATH, bool STABLE>
 int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, GemmArgs g, const FuseFwd& fz, const FuseNoise& fnz,
-                    cudaStream_t stream, size_t partials_bytes) {
+                    cudaStream_t stream, size_t partials_bytes, FusePeer fpz = FusePeer{}, int* exchanged_tiles = nullptr) {
     auto kernel = gemm_split_2sm_kernel<MN, EX, MATH, STABLE>;
     static int max_clusters[kMaxDevices] = {};     // co-resident clusters (a cluster must fit inside one GPC)
     constexpr int smem = smem_bytes_of<EX>(MATH);
@@ -648,7 +652,13 @@ int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, GemmArgs g, cons
     const int items = g.full_tiles + (tiles - g.full_tiles) * g.ksplit;
     const int clusters = items < mc ? items : mc;
     cfg.gridDim = dim3(2 * clusters);
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, a, b, g, fz, fnz);
+    if (MATH == 3) {
+        // the K-sliced tail tiles are complete only after tail_fixup_kernel: they are exchanged after this kernel
+        fpz.full_tiles = g.full_tiles;
+        fpz.tiles_n = g.tiles_n;
+        if (exchanged_tiles) *exchanged_tiles = g.full_tiles;
+    }
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, a, b, g, fz, fnz, fpz);
     if (e != cudaSuccess) { set_error("gemm_split_2sm_kernel launch: %s", cudaGetErrorString(e)); return 3; }
     if (int rc = check_launch("gemm_split_2sm_kernel")) return rc;
     if (g.ksplit > 1) {
@@ -664,7 +674,8 @@ int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, GemmArgs g, cons
 template <bool MN>
 int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc, int Nc, int K, int ldc, const uint32_t* ma,
                 const uint32_t* mb, cudaStream_t stream, int ex, float* partials, size_t partials_bytes,
-                const FuseFwd* fuse = nullptr, const FuseNoise* noise = nullptr) {
+                const FuseFwd* fuse = nullptr, const FuseNoise* noise = nullptr, const FusePeer* peer = nullptr,
+                int* exchanged_tiles = nullptr) {
     GemmArgs g{};
     g.C = C; g.Mc = Mc; g.Nc = Nc; g.K = K; g.ldc = ldc;
     g.tiles_m = ceil_div(Mc, 256); g.tiles_n = ceil_div(Nc, BN);
@@ -674,6 +685,11 @@ int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc, in
     g.partials = partials;
     const FuseFwd none{};
     const FuseNoise nonoise{};
+    if (peer != nullptr) {
+        if (!MN || ex == 1 || fuse != nullptr || noise != nullptr) { set_error("fused exchange: tn products only"); return 7; }
+        if (ex == 2) return launch_gemm_2sm<true, 2, 3, false>(a, b, g, none, nonoise, stream, partials_bytes, *peer, exchanged_tiles);
+        return launch_gemm_2sm<true, 0, 3, false>(a, b, g, none, nonoise, stream, partials_bytes, *peer, exchanged_tiles);
+    }
     if (noise != nullptr) {
         if (MN || ex != 1 || fuse != nullptr) { set_error("just-in-time noise: nt products with an exact A operand only"); return 7; }
         return launch_gemm_2sm<false, 1, 2, false>(a, b, g, none, *noise, stream, 0);
@@ -843,14 +859,14 @@ int tc_gemm_nt(const void* a_planes, const void* b_planes, float* C, int M, int 
 
 int tc_gemm_tn(const void* a_planes, const void* b_planes, float* C, int M, int N1, int N2, const uint32_t* absmax_a,
                const uint32_t* absmax_b, cudaStream_t stream, int b_exact, void* tail_scratch, size_t tail_scratch_bytes,
-               int a_pitch) {
+               int a_pitch, const FusePeer* peer, int* exchanged_tiles) {
     // a_pitch > 0: A is a column range of wider planes (row slab of C): a_planes points at its first column
     const int p1 = a_pitch > 0 ? a_pitch : pitch_of(N1), p2 = pitch_of(N2);
     CUtensorMap ma, mb;
     if (int rc = make_map(&ma, a_planes, N1, M, p1, 64, 64)) return rc;
     if (int rc = make_map(&mb, b_planes, N2, M, p2, 64, 64, b_exact ? 1 : 2)) return rc;
     return launch_gemm<true>(ma, mb, C, N1, N2, M, N2, absmax_a, absmax_b, stream, b_exact ? 2 : 0, static_cast<float*>(tail_scratch),
-                             tail_scratch_bytes);
+                             tail_scratch_bytes, nullptr, nullptr, peer, exchanged_tiles);
 }
 
 }  // namespace mpv

@@ -261,4 +261,91 @@ __device__ __forceinline__ void noise_math_loop(const FuseNoise& f, int gw, int 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ tile exchange
+// The third job for the math warps, in the BACKWARD product g_R = gxs^T . noise of a data-parallel run: the sum of g_R over
+// the ranks, tile by tile, while the tensor pipe is still producing later tiles.  Every rank's product writes its
+// partial g_R into its own peer-mapped `part` buffer and bumps a per-tile counter (in peer memory too) when a tile is
+// stored.  Tile t belongs to rank t mod world: that rank's math warps wait until the tile is complete on EVERY rank
+// (remote acquire loads of the counters over NVLink), pull it from all ranks, add the partials in rank order (fixed
+// order: every rank ends up with bit-identical sums) and store the result into every rank's g_R -- compute and
+// collective in ONE kernel over peer memory.  Counters are monotonic (a tile is complete when its counter reaches
+// 32 x the exchange's step number), so nothing is reset between steps.  The K-sliced tail wave of the product (finished by
+// tail_fixup_kernel after this kernel) is exchanged afterwards by the stand-alone reduce kernel over that row range.
+struct FusePeer {
+    int world, rank;
+    unsigned int step;                 // flag value of this exchange; a tile's counter target is 32 * (step + *step_dev)
+    const unsigned int* step_dev;
+    long long timeout_cycles;
+    unsigned int* err;                 // this rank's error word (a wait that timed out records the step there)
+    float* part[8];                    // every rank's partial g_R (this rank's = the product's C), (Mc, Nc) pitch ldc
+    float* g_r[8];                     // every rank's final g_R
+    unsigned int* done[8];             // every rank's per-tile counters
+    int Mc, Nc, ldc, tiles_n;
+    int full_tiles;                    // tiles [0, full_tiles) are exchanged in the kernel (filled in by the launcher)
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// promotion warp, after the stores of its part of tile `t` into this rank's `part`
+__device__ __forceinline__ void peer_signal_tile(const FusePeer& f, int t, int lane) {
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) atomicAdd(f.done[f.rank] + t, 1u);
+}
+
+// One math warp's share of this rank's tiles.  gw = this warp's index among the `warps_total` math warps of the grid.
+__device__ __forceinline__ void peer_math_loop(const FusePeer& f, int gw, int warps_total, int lane) {
+    const unsigned int target = 32u * (f.step + (f.step_dev ? *f.step_dev : 0u));
+    const int owned = (f.full_tiles - f.rank + f.world - 1) / f.world;       // tiles rank, rank + world, ...
+    int waited = -1;
+    for (long long u = gw; u < (long long)owned * 256; u += warps_total) {
+        const int k = (int)(u >> 8), row_in = (int)(u & 255);
+        const int t = f.rank + k * f.world;
+        if (t != waited) {
+            // lane r watches rank r's counter of this tile
+            if (lane < f.world) {
+                const long long t0 = clock64();
+                while ((int)(ld_acquire_sys(f.done[lane] + t) - target) < 0) {
+                    __nanosleep(500);
+                    if (clock64() - t0 > f.timeout_cycles) { atomicMax(f.err, f.step); break; }
+                }
+            }
+            __syncwarp();
+            waited = t;
+        }
+        const int row = (t / f.tiles_n) * 256 + row_in;
+        if (row >= f.Mc) continue;
+        const int c0 = (t % f.tiles_n) * 256;
+        const size_t o = (size_t)row * f.ldc + c0;
+#pragma unroll
+        for (int jj = 0; jj < 8; jj += 4) {
+            float v[4][8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = lane + 32 * (jj + j);
+                const bool in = c0 + c < f.Nc;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) v[j][r] = (in && r < f.world) ? __ldcg(f.part[r] + o + c) : 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = lane + 32 * (jj + j);
+                if (c0 + c >= f.Nc) continue;
+                float a = v[j][0];
+#pragma unroll
+                for (int r = 1; r < 8; ++r)
+                    if (r < f.world) a += v[j][r];
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (r < f.world) f.g_r[r][o + c] = a;
+            }
+        }
+    }
+    __threadfence_system();      // this warp's deliveries are visible before the kernel ends (and the rank signals)
+}
+
 }  // namespace mpv

@@ -204,7 +204,11 @@ static void launch_reduce_w(const PeerCtx& ctx, size_t n, int ctas, int unroll, 
     else peer_reduce_bcast_kernel<W, 1><<<ctas, 256, 0, stream>>>(ctx, n);
 }
 
-int launch_peer_reduce(const PeerCtx& ctx, size_t n, cudaStream_t stream) {
+int launch_peer_reduce(const PeerCtx& ctx_in, size_t n, cudaStream_t stream, size_t first) {
+    // [first, first + n): a sub-range of the buffers (the rows the fused exchange left over); n == 0 still runs the two
+    // flag phases, which is what tells every rank that all deliveries of this step are done
+    PeerCtx ctx = ctx_in;
+    for (int i = 0; i < ctx.world; ++i) { ctx.part[i] += first; ctx.g_r[i] += first; }
     static const int ctas = getenv("MPVAE_PEER_CTAS") ? atoi(getenv("MPVAE_PEER_CTAS")) : kReduceCtas;
     static const int unroll = getenv("MPVAE_PEER_UNROLL") ? atoi(getenv("MPVAE_PEER_UNROLL")) : 2;
     peer_signal_kernel<<<1, 32, 0, stream>>>(ctx, 0);

@@ -110,7 +110,7 @@ struct PeerCtx {
 };
 size_t peer_flag_bytes();
 int peer_error_word();   // index of the error word inside a rank's flag block (0 = no wait has timed out)
-int launch_peer_reduce(const PeerCtx& ctx, size_t n, cudaStream_t stream);
+int launch_peer_reduce(const PeerCtx& ctx, size_t n, cudaStream_t stream, size_t first = 0);   // elements [first, first + n)
 int launch_peer_reduce_nvls(const PeerCtx& ctx, const float* mc_part, float* mc_gr, size_t n, cudaStream_t stream);
 
 // clip_grad_norm_ + Adam over flat buffers (optim.cu)

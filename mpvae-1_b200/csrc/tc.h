@@ -9,6 +9,7 @@ namespace mpv {
 
 struct FuseFwd;     // fused_rows.cuh: the probit row forward carried by the nt product kernel (opt-in)
 struct FuseNoise;   // fused_rows.cuh: the A operand's Philox noise drawn by the nt product kernel itself
+struct FusePeer;    // fused_rows.cuh: the finished tiles of the tn product summed over the ranks through peer memory
 
 bool tc_available();
 
@@ -52,6 +53,9 @@ int tc_pitch(int cols);                                      // plane row pitch 
 int tc_absmax(const float* src, size_t n, uint32_t* out_bits, cudaStream_t stream);   // atomicMax of |x| bits into *out
 int tc_gemm_tn(const void* a_planes, const void* b_planes, float* C, int M, int N1, int N2, const uint32_t* absmax_a,
                const uint32_t* absmax_b, cudaStream_t stream, int b_exact = 0, void* tail_scratch = nullptr,
-               size_t tail_scratch_bytes = 0, int a_pitch = 0);
+               size_t tail_scratch_bytes = 0, int a_pitch = 0,
+               // peer != nullptr: C is this rank's partial; tiles [0, *exchanged_tiles) are summed over the ranks inside the
+               // kernel (into every rank's g_r), the K-sliced tail tiles are left to the caller
+               const FusePeer* peer = nullptr, int* exchanged_tiles = nullptr);
 
 }  // namespace mpv

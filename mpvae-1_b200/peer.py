@@ -39,7 +39,9 @@ class PeerRing:
         lib = _lib.lib()
         self.L, self.Z = int(L), int(Z)
         self.device = torch.device(device)
-        sizes = {"part": self.L * self.Z * 4, "g_r": self.L * self.Z * 4, "flags": int(lib.mpvae_peer_flag_bytes())}
+        # "tiles": per-tile completion counters of the exchange fused into the g_R product (monotonic, zeroed once here)
+        sizes = {"part": self.L * self.Z * 4, "g_r": self.L * self.Z * 4, "flags": int(lib.mpvae_peer_flag_bytes()),
+                 "tiles": _lib.PEER_TILE_BYTES}
         self._local, self._remote, handles = {}, {}, {}
         # Every collective below is entered by EVERY rank whatever happened locally, and the outcome is agreed on
         # collectively: either all ranks own a working ring or all of them raise (no rank is left waiting).
@@ -101,6 +103,8 @@ class PeerRing:
             p.peer_part[r] = self.ptrs["part"][r]
             p.peer_g_r[r] = self.ptrs["g_r"][r]
             p.peer_flags[r] = self.ptrs["flags"][r]
+            if "tiles" in self.ptrs:
+                p.peer_tile_done[r] = self.ptrs["tiles"][r]
         return self.g_r
 
     def check(self):
