@@ -261,6 +261,10 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         return it;
     };
     if (threadIdx.x == 0) {
+        if (MATH == 3) {   // the peer exchange's watermark and the promotion warps' arrival count
+            *reinterpret_cast<volatile int*>(gen + R2::RING_BYTES + 192) = 0;
+            *reinterpret_cast<volatile int*>(gen + R2::RING_BYTES + 196) = 0;
+        }
         for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -358,6 +362,13 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     if (++buf == 2) { buf = 0; bphase ^= 1u; }
                 }
             }
+        } else if (MATH == 3 && warp == 3 && lane == 0) {   // ------------------------------- tile publisher
+            int n = 0;
+            for (int w = cluster; w < num_items; w += num_clusters) {
+                const Item it = item_of(w, num_kb);
+                if (it.slice == 0 && it.st < fpz.full_tiles)
+                    peer_publish_tile(fpz, reinterpret_cast<volatile int*>(gen + R2::RING_BYTES + 196), n++, it.st);
+            }
         }
     } else if (FUSE && warp < kFirstEpi) {   // ------------------- math warps
         reg_dec<kRegMath>();
@@ -368,7 +379,7 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         } else if (MATH == 2) {  // the A operand's Philox noise, just ahead of the tiles
             noise_math_loop(fnz, (int)blockIdx.x * kFuseMathWarps + mw, (int)gridDim.x * kFuseMathWarps, lane);
         } else {                 // this rank's tiles of the sum over the ranks
-            peer_math_loop(fpz, (int)blockIdx.x * kFuseMathWarps + mw, (int)gridDim.x * kFuseMathWarps, lane);
+            peer_math_loop(fpz, (int)blockIdx.x, (int)gridDim.x, mw, lane, reinterpret_cast<volatile int*>(gen + R2::RING_BYTES + 192));
         }
     } else {   // --------------------------------------------------- promotion + epilogue (both CTAs, own 128 rows)
         if (FUSE) reg_inc<kRegEpi>();
@@ -438,7 +449,8 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 }
             }
             if (MATH == 1) fuse_signal_tile(fz.done, st, lane);   // this warp's part of the tile is in memory
-            if (MATH == 3 && it.slice == 0 && st < fpz.full_tiles) peer_signal_tile(fpz, st, lane);
+            if (MATH == 3 && it.slice == 0 && st < fpz.full_tiles)
+                peer_arrive_tile(reinterpret_cast<volatile int*>(gen + R2::RING_BYTES + 196), lane);
 #pragma unroll
             for (int j = 0; j < 64; ++j) acc[j] = 0.0f;
         }

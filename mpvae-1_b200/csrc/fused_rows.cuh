@@ -47,20 +47,31 @@ struct FuseFwd {
     unsigned int* done;                     // [tiles_m * tiles_n], zeroed before the launch
 };
 
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+// Flag polling.  An acquire LOAD compiles to LDG.STRONG + CCTL.IVALL (an L1 invalidation) on every poll, and a few
+// hundred spinning warps doing that starve the whole SM (measured: the g_R product went from 0.44 to 0.65 ms).  So the
+// polls are RELAXED loads and one acquire FENCE follows the successful one.
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
     unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned int ld_relaxed_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_acquire_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 
 // whole warp: block until the tile's counter says every promotion warp has stored its part
 __device__ __forceinline__ void fuse_wait_tile(const unsigned int* cnt, int lane) {
     if (lane == 0) {
         const long long t0 = clock64();
-        while (ld_acquire_gpu(cnt) < (unsigned)kFuseTileArrivals) {
+        while (ld_relaxed_gpu(cnt) < (unsigned)kFuseTileArrivals) {
             __nanosleep(200);
             if (clock64() - t0 > 8000000000LL) __trap();   // ~4 s: a protocol bug must not hang the GPU
         }
+        fence_acquire_gpu();
     }
     __syncwarp();
 }
@@ -202,10 +213,11 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 // TMA producer thread: block `u` of the plane is complete once every math warp of the grid has signalled it
 __device__ __forceinline__ void noise_wait_block(const unsigned int* cnt, unsigned int warps_total) {
     const long long t0 = clock64();
-    while (ld_acquire_gpu(cnt) < warps_total) {
+    while (ld_relaxed_gpu(cnt) < warps_total) {
         __nanosleep(100);
         if (clock64() - t0 > 8000000000LL) __trap();   // ~4 s: a protocol bug must not hang the GPU
     }
+    fence_acquire_gpu();
     fence_proxy_async_global();                         // generic-proxy stores -> async-proxy (TMA) loads
 }
 
@@ -284,38 +296,63 @@ struct FusePeer {
     int full_tiles;                    // tiles [0, full_tiles) are exchanged in the kernel (filled in by the launcher)
 };
 
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// promotion warp, after the stores of its part of tile `t` into this rank's `part`
-__device__ __forceinline__ void peer_signal_tile(const FusePeer& f, int t, int lane) {
-    __threadfence_system();
+// Publishing a finished tile.  A system-scope fence in each of the 512 promotion threads (MEMBAR.SC.SYS + an L1
+// invalidation) stalls the warps the tensor pipe is waiting for, so the promotion warps only count themselves in shared
+// memory (CTA-scope release) and ONE otherwise idle control thread per CTA turns sixteen arrivals into one system-scope
+// release and one bump of the tile's counter by 16 (release / acquire chains are cumulative).
+__device__ __forceinline__ void peer_arrive_tile(volatile int* arrivals, int lane) {
+    __threadfence_block();
     __syncwarp();
-    if (lane == 0) atomicAdd(f.done[f.rank] + t, 1u);
+    if (lane == 0) atomicAdd_block(const_cast<int*>(arrivals), 1);
+}
+// control warp 3, one thread: the n-th exchangeable tile of this CTA is `t`
+__device__ __forceinline__ void peer_publish_tile(const FusePeer& f, volatile int* arrivals, int n, int t) {
+    while (*arrivals < 16 * (n + 1)) __nanosleep(100);
+    fence_acquire_sys();                                  // acq_rel: the promotion warps' stores, then the counter
+    atomicAdd(f.done[f.rank] + t, 16u);
 }
 
-// One math warp's share of this rank's tiles.  gw = this warp's index among the `warps_total` math warps of the grid.
-__device__ __forceinline__ void peer_math_loop(const FusePeer& f, int gw, int warps_total, int lane) {
+// The math warps of one CTA.  Warp 0 is the CTA's WATCHER: it follows this rank's tiles in order, waits until tile k is
+// complete on every rank (lane r polls rank r's counter over NVLink: one poller per CTA, not one per warp) and publishes
+// the number of exchangeable tiles in shared memory.  The other seven pull rows: unit u = (owned tile u / 256, row
+// u % 256), dealt round-robin over all worker warps of the grid.  `ready` is an int in shared memory, zeroed by the
+// caller before the CTA-wide barrier that precedes the role split.
+__device__ __forceinline__ void peer_math_loop(const FusePeer& f, int cta, int ctas, int mw, int lane, volatile int* ready) {
     const unsigned int target = 32u * (f.step + (f.step_dev ? *f.step_dev : 0u));
     const int owned = (f.full_tiles - f.rank + f.world - 1) / f.world;       // tiles rank, rank + world, ...
-    int waited = -1;
+    if (mw == 0) {
+        // a round looks at the next 32 / world tiles at once (lane = (tile offset, rank)): the remote loads of a round
+        // are in flight together, and the ready prefix advances by as many tiles as are complete everywhere
+        const int per = 32 / f.world, r = lane % f.world, dk = lane / f.world;
+        int k0 = 0;
+        const long long t0 = clock64();
+        while (k0 < owned) {
+            const int k = k0 + dk;
+            bool ok = true;
+            if (dk < per && k < owned) ok = (int)(ld_relaxed_sys(f.done[r] + f.rank + k * f.world) - target) >= 0;
+            const unsigned pending = __ballot_sync(0xffffffffu, !ok);
+            // tiles k0 .. k0 + adv - 1 are complete on every rank: the first pending lane bounds the prefix
+            int adv = pending ? (__ffs(pending) - 1) / f.world : per;
+            if (adv > owned - k0) adv = owned - k0;
+            if (adv > 0) {
+                k0 += adv;
+                if (lane == 0) { fence_acquire_sys(); *ready = k0; }
+            } else {
+                __nanosleep(500);
+                if (clock64() - t0 > f.timeout_cycles) { if (lane == 0) { atomicMax(f.err, f.step); *ready = owned; } return; }
+            }
+        }
+        return;
+    }
+    const int workers = kFuseMathWarps - 1;
+    const int gw = cta * workers + (mw - 1), warps_total = ctas * workers;
+    int have = 0;
     for (long long u = gw; u < (long long)owned * 256; u += warps_total) {
         const int k = (int)(u >> 8), row_in = (int)(u & 255);
         const int t = f.rank + k * f.world;
-        if (t != waited) {
-            // lane r watches rank r's counter of this tile
-            if (lane < f.world) {
-                const long long t0 = clock64();
-                while ((int)(ld_acquire_sys(f.done[lane] + t) - target) < 0) {
-                    __nanosleep(500);
-                    if (clock64() - t0 > f.timeout_cycles) { atomicMax(f.err, f.step); break; }
-                }
-            }
-            __syncwarp();
-            waited = t;
+        if (k >= have) {
+            while ((have = *ready) <= k) __nanosleep(500);
+            fence_acquire_sys();       // the watcher's acquire, then this warp's own: data loads below see the tile
         }
         const int row = (t / f.tiles_n) * 256 + row_in;
         if (row >= f.Mc) continue;
