@@ -61,9 +61,9 @@ def parse():
     ap.add_argument("--engine", default="auto", choices=["auto", "fma", "tensor"])
     ap.add_argument("--fused-row-forward", action="store_true",
                     help="dense regime: run the row forward on math warps inside the product kernel (A/B; measured slower)")
-    ap.add_argument("--separate-exchange", action="store_true",
-                    help="N>1, peer exchange: sum g_R with the stand-alone reduce kernel after the product instead of tile "
-                         "by tile inside it (A/B)")
+    ap.add_argument("--fused-exchange", action="store_true",
+                    help="N>1, peer exchange: sum g_R tile by tile inside the g_R product kernel instead of with the "
+                         "stand-alone reduce kernel after it (A/B)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nvls", "nccl"],
                     help="N>1: how g_R is summed over ranks (peer = inside the backward over NVLink peer memory, "
                          "mpvae_b200.peer.PeerRing, falling back to nccl if the ring cannot be set up on every rank; "
@@ -317,8 +317,8 @@ def run_b200(a):
     flags = {"auto": 0, "fma": _lib.FLAG_CONTRACT_FMA, "tensor": _lib.FLAG_CONTRACT_TENSOR}[a.engine]
     if a.fused_row_forward:
         flags |= _lib.FLAG_FUSED_FORWARD
-    if a.separate_exchange:
-        flags |= _lib.FLAG_SEPARATE_EXCHANGE
+    if a.fused_exchange:
+        flags |= _lib.FLAG_FUSED_EXCHANGE
     infer = sh.mode == "test"       # BASELINE configs[2] (nuswide) is the test-time path: forward only, no_grad, S = n_test_sample
     dense = (Z >= 128 and L >= 128 and a.engine != "fma") or a.engine == "tensor"
     fused = dense and a.fused_row_forward and S <= 256
@@ -686,7 +686,7 @@ def run_b200(a):
                                 ("g_R summed inside the NVSwitch (multimem.ld_reduce / multimem.st by the chunk owners), inside "
                                  "the backward") if (ring is not None and a.exchange == "nvls") else
                                 ("g_R summed over NVLink peer memory after the product (chunk owners pull, add in rank order, "
-                                 "store to every rank)" if a.separate_exchange else
+                                 "store to every rank)" if not a.fused_exchange else
                                  "g_R summed over NVLink peer memory INSIDE the g_R product kernel, tile by tile (tile t belongs to "
                                  "rank t mod N: its math warps pull the finished tile from every rank, add in rank order, store to "
                                  "every rank; the K-sliced tail rows by the stand-alone reduce kernel)") if ring is not None

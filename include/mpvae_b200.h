@@ -46,8 +46,9 @@ extern "C" {
                                                before the product instead of on the product kernel's math warps, just
                                                ahead of the tiles that read them (A/B measurements; same numbers) */
 
-#define MPVAE_FLAG_SEPARATE_EXCHANGE    0x40u /* data-parallel dense regime: sum g_R over the ranks with the stand-alone reduce kernel
-                                               after the product instead of tile by tile inside it (A/B; same sums) */
+#define MPVAE_FLAG_FUSED_EXCHANGE       0x40u /* data-parallel dense regime, opt-in: sum g_R over the ranks tile by tile INSIDE the
+                                               g_R product kernel (peer_tile_done must be given) instead of with the
+                                               stand-alone reduce kernel after it; same sums */
 
 /* order of the six scalar outputs (first six entries of the 8-tuple at mpvae.py:210) */
 enum { MPVAE_TOTAL = 0, MPVAE_NLL = 1, MPVAE_NLL_X = 2, MPVAE_C = 3, MPVAE_C_X = 4, MPVAE_KL = 5 };

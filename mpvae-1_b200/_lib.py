@@ -19,7 +19,7 @@ FLAG_CONTRACT_FMA = 0x4
 FLAG_STABLE_CDF = 0x8
 FLAG_FUSED_FORWARD = 0x10
 FLAG_SEPARATE_NOISE = 0x20
-FLAG_SEPARATE_EXCHANGE = 0x40
+FLAG_FUSED_EXCHANGE = 0x40
 PEER_TILE_BYTES = 65536
 
 # every symbol include/mpvae_b200.h declares

@@ -484,7 +484,7 @@ int mpvae_probit_backward(const mpvae_probit_params* p_in, void* cuda_stream) {
         if (tensor) {
             // data-parallel: the finished tiles are summed over the ranks inside the product kernel (fused_rows.cuh)
             FusePeer fp{};
-            const bool fused_x = peer && p->peer_tile_done[p->peer_rank] != nullptr && !(p->flags & MPVAE_FLAG_SEPARATE_EXCHANGE) &&
+            const bool fused_x = peer && p->peer_tile_done[p->peer_rank] != nullptr && (p->flags & MPVAE_FLAG_FUSED_EXCHANGE) &&
                                  !(p->peer_mc_part && p->peer_mc_g_r) &&
                                  (size_t)ceil_div(p->L, 256) * ceil_div(p->Z, 256) * sizeof(uint32_t) <= MPVAE_PEER_TILE_BYTES;
             if (fused_x) {

@@ -177,4 +177,4 @@ FLAG_CONTRACT_TENSOR = _lib.FLAG_CONTRACT_TENSOR
 FLAG_CONTRACT_FMA = _lib.FLAG_CONTRACT_FMA
 FLAG_FUSED_FORWARD = _lib.FLAG_FUSED_FORWARD
 FLAG_SEPARATE_NOISE = _lib.FLAG_SEPARATE_NOISE
-FLAG_SEPARATE_EXCHANGE = _lib.FLAG_SEPARATE_EXCHANGE
+FLAG_FUSED_EXCHANGE = _lib.FLAG_FUSED_EXCHANGE
