@@ -31,7 +31,7 @@ def main():
     r32 = t.pop("r_sqrt_sigma").float().requires_grad_(True)
     noise = torch.randn(S, B, Z, device=dev) if a.external_noise else None
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
-    for name, flags in (("default", 0), ("separate_noise_kernel", _lib.FLAG_SEPARATE_NOISE)):
+    for name, flags in (("default", 0), ("separate_noise_kernel", _lib.FLAG_SEPARATE_NOISE), ("fused_row_forward", _lib.FLAG_FUSED_FORWARD)):
         args = synth.make_args(L, Z, n_train_sample=S, n_test_sample=S, mode=sh.mode, mpvae_flags=flags, noise_seed=1)
 
         def step(i):
