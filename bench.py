@@ -300,7 +300,7 @@ def run_b200(a):
     import torch.distributed as dist
     from mpvae_b200 import _lib, synth
     from mpvae_b200 import mpvae as M
-    from mpvae_b200.metrics import batch_metrics
+    from mpvae_b200.metrics import batch_metrics_tensor
     from mpvae_b200.train import shard_rows
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -399,8 +399,7 @@ def run_b200(a):
         if from_host:
             # the step's result as train.py:131 consumes it: the loss and the eight batch metrics (computed on the
             # device, SURVEY 8f-N1: mpvae_b200.metrics.batch_metrics) come back to the host
-            m = batch_metrics(out[6], t["y"], 0.5)
-            metrics_host.copy_(torch.stack(list(m.values())), non_blocking=True)
+            metrics_host.copy_(batch_metrics_tensor(out[6], t["y"], 0.5), non_blocking=True)
             loss_host.copy_(out[0].detach(), non_blocking=True)
         return out
 

@@ -19,6 +19,12 @@ NAMES = ("ACC", "HA", "ebF1", "miF1", "maF1", "p_at_1", "p_at_3", "p_at_5")
 def batch_metrics(indiv_prob: torch.Tensor, input_label: torch.Tensor, threshold: float = 0.5) -> dict:
     """Same keys as the reference's metrics_dict (the AUC/AUPR/FDR entries, 0 in this mode, are omitted).
     Values are 0-dim float64 CUDA tensors."""
+    out = batch_metrics_tensor(indiv_prob, input_label, threshold)
+    return dict(zip(NAMES, out.unbind(0)))
+
+
+def batch_metrics_tensor(indiv_prob: torch.Tensor, input_label: torch.Tensor, threshold: float = 0.5) -> torch.Tensor:
+    """The eight metrics in the order of `NAMES` as ONE (8,) float64 CUDA tensor (one device-to-host copy fetches them)."""
     if not (indiv_prob.is_cuda and input_label.is_cuda):
         raise RuntimeError("mpvae_b200.batch_metrics runs on CUDA tensors only (use the reference's evals on the host)")
     p = indiv_prob.detach().float().contiguous()
@@ -29,7 +35,7 @@ def batch_metrics(indiv_prob: torch.Tensor, input_label: torch.Tensor, threshold
     lib = _lib.lib()
     out = torch.empty(8, dtype=torch.float64, device=p.device)
     if B == 0:
-        return {k: out.new_full((), float("nan")) for k in NAMES}
+        return out.fill_(float("nan"))
     with torch.cuda.device(p.device):
         nbytes = int(lib.mpvae_batch_metrics_workspace(B, L))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=p.device)
@@ -37,7 +43,7 @@ def batch_metrics(indiv_prob: torch.Tensor, input_label: torch.Tensor, threshold
         _lib.check(lib.mpvae_batch_metrics(C.c_void_p(p.data_ptr()), C.c_void_p(y.data_ptr()), B, L, float(threshold),
                                            C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), nbytes, stream),
                    "mpvae_batch_metrics")
-    return dict(zip(NAMES, out.unbind(0)))
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------
