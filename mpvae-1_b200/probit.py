@@ -8,6 +8,7 @@ regulariser, fairsoft_train.py:76-140).  PyTorch is used for device memory and t
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -94,6 +95,13 @@ class ProbitELBO(torch.autograd.Function):
             scalars = [torch.empty((), dtype=torch.float32, device=dev) for _ in range(6)]
             prob = torch.empty((B, L), dtype=torch.float32, device=dev)
             prob_label = torch.empty((B, L), dtype=torch.float32, device=dev)
+            if os.environ.get("MPVAE_POISON_WORKSPACE") == "1":
+                # test hook (compute-sanitizer --tool initcheck is closed on this pool): every scratch / output byte starts
+                # as 0xFF (NaN as fp16 / fp32 / fp64, huge as a counter), so anything the kernels read before writing shows
+                ws.fill_(255)
+                prob.view(torch.uint8).fill_(255); prob_label.view(torch.uint8).fill_(255)
+                for t in scalars:
+                    t.view(torch.uint8).fill_(255)
             p = _lib.ProbitParams()
             p.struct_bytes = C.sizeof(_lib.ProbitParams)
             p.flags = flags
@@ -146,6 +154,9 @@ class ProbitELBO(torch.autograd.Function):
             g_fe_out = torch.empty_like(fe_out)
             g_fx_out = torch.empty_like(fx_out)
             g_mulv = [torch.empty_like(fe_mu) for _ in range(4)]
+            if os.environ.get("MPVAE_POISON_WORKSPACE") == "1":
+                for t in [g_fe_out, g_fx_out] + g_mulv:
+                    t.view(torch.uint8).fill_(255)
             peer = ctx.peer if need_r else None
             g_r = (torch.empty_like(r32) if peer is None else None) if need_r else None
             p = _lib.ProbitParams()

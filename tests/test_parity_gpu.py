@@ -606,3 +606,31 @@ def test_integration_stub_runs():
     torch.cuda.synchronize()
     for a, b in zip(got, want):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("S,B,L,Z", [(10, 16, 38, 38), (10, 33, 983, 10), (7, 33, 513, 130), (10, 128, 983, 983), (3, 77, 130, 256)])
+def test_poisoned_scratch_does_not_leak(S, B, L, Z, monkeypatch):
+    """compute-sanitizer (initcheck) is closed on this pool.  Stand-in: with MPVAE_POISON_WORKSPACE=1 the host wrapper fills
+    the scratch block and every output buffer with 0xFF bytes (NaN in every float format, huge as a counter) before the
+    calls; the three regimes (small, CUDA-core, tensor engine -- incl. ragged tiles and operand-plane padding) must
+    return exactly what they return on fresh memory, i.e. nothing is read before the library wrote it."""
+    from mpvae_b200 import synth
+    from mpvae_b200.mpvae import compute_loss
+    inp = synth.loss_inputs(L, Z, B, S, seed=S + L, sigma=1.0, label_rate=max(0.05, 20.0 / L), with_noise=False)
+    dev = torch.device("cuda:0")
+
+    def run():
+        args = orc.make_args(L, Z, n_train_sample=S, noise_seed=99, noise_offset=4)
+        t = {k: torch.from_numpy(v).to(dev).requires_grad_(k != "y") for k, v in inp.items()}
+        out = compute_loss(t["y"], t["fe_out"], t["fe_mu"], t["fe_logvar"], t["fx_out"], t["fx_mu"], t["fx_logvar"],
+                           t["r_sqrt_sigma"], args)
+        out[0].backward()
+        torch.cuda.synchronize()
+        return [o.detach().cpu().numpy() for o in out] + [t[k].grad.cpu().numpy() for k in H.GRAD_KEYS]
+
+    clean = run()
+    monkeypatch.setenv("MPVAE_POISON_WORKSPACE", "1")
+    poisoned = run()
+    for a, b in zip(clean, poisoned):
+        assert np.isfinite(b).all()
+        np.testing.assert_array_equal(a, b)
