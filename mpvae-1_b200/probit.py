@@ -99,9 +99,8 @@ class ProbitELBO(torch.autograd.Function):
                 # test hook (compute-sanitizer --tool initcheck is closed on this pool): every scratch / output byte starts
                 # as 0xFF (NaN as fp16 / fp32 / fp64, huge as a counter), so anything the kernels read before writing shows
                 ws.fill_(255)
-                prob.view(torch.uint8).fill_(255); prob_label.view(torch.uint8).fill_(255)
-                for t in scalars:
-                    t.view(torch.uint8).fill_(255)
+                for t in [prob, prob_label] + scalars:
+                    t.fill_(float("nan"))
             p = _lib.ProbitParams()
             p.struct_bytes = C.sizeof(_lib.ProbitParams)
             p.flags = flags
@@ -156,7 +155,7 @@ class ProbitELBO(torch.autograd.Function):
             g_mulv = [torch.empty_like(fe_mu) for _ in range(4)]
             if os.environ.get("MPVAE_POISON_WORKSPACE") == "1":
                 for t in [g_fe_out, g_fx_out] + g_mulv:
-                    t.view(torch.uint8).fill_(255)
+                    t.fill_(float("nan"))
             peer = ctx.peer if need_r else None
             g_r = (torch.empty_like(r32) if peer is None else None) if need_r else None
             p = _lib.ProbitParams()
