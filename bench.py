@@ -376,6 +376,8 @@ def run_b200(a):
         args.peer_ring = ring if use_ring else None
         step_no[0] += 1
         t = src
+        if t["y"].dtype != torch.float32:
+            t = dict(t, y=t["y"].float())        # the byte labels of the host path: one cast serves the loss and the metrics
         kw = {} if noise is None else {"noise": noise}
         if infer:
             with torch.no_grad():

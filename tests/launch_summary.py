@@ -10,7 +10,7 @@ rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 5]
 hdr = rows[0]
 ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
 seq = [(r[ki], float(r[vi].replace(",", ""))) for r in rows[1:]]
-marker = sys.argv[2] if len(sys.argv) > 2 else "philox_planes"
+marker = sys.argv[2] if len(sys.argv) > 2 else "absmax_kernel"
 need = sys.argv[3] if len(sys.argv) > 3 else None          # region must contain a kernel with this substring
 marks = [i for i, (k, _) in enumerate(seq) if marker in k]
 region = None
