@@ -39,7 +39,9 @@ ROW_KEYS = ["y", "fe_out", "fe_mu", "fe_logvar", "fx_out", "fx_mu", "fx_logvar"]
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
 # captures under profiles/ ((L, Z, S*B rows, fused row forward) -> bytes)
 TRAFFIC = {
-    (3993, 3993, 10240, False): 769.18e6,          # profiles/r01_final_ncu_full_summary.txt
+    # profiles/r02_final_ncu_full_summary.txt: 428.47 MB read + 226.55 MB written by the nt product that also draws its
+    # noise plane (round 1, separate Philox kernel: 769.18 MB, profiles/r01_final_ncu_full_summary.txt)
+    (3993, 3993, 10240, False): 655.02e6,
 }
 
 
