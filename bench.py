@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--engine", default="auto", choices=["auto", "fma", "tensor"])
     ap.add_argument("--fused-row-forward", action="store_true",
                     help="dense regime: run the row forward on math warps inside the product kernel (A/B; measured slower)")
+    ap.add_argument("--serial-exchange", action="store_true",
+                    help="N>1, peer exchange: sum g_R only after the g_R product instead of slab by slab beside it (A/B)")
     ap.add_argument("--fused-exchange", action="store_true",
                     help="N>1, peer exchange: sum g_R tile by tile inside the g_R product kernel instead of with the "
                          "stand-alone reduce kernel after it (A/B)")
@@ -321,6 +323,8 @@ def run_b200(a):
         flags |= _lib.FLAG_FUSED_FORWARD
     if a.fused_exchange:
         flags |= _lib.FLAG_FUSED_EXCHANGE
+    if a.serial_exchange:
+        flags |= _lib.FLAG_SERIAL_EXCHANGE
     infer = sh.mode == "test"       # BASELINE configs[2] (nuswide) is the test-time path: forward only, no_grad, S = n_test_sample
     dense = (Z >= 128 and L >= 128 and a.engine != "fma") or a.engine == "tensor"
     fused = dense and a.fused_row_forward and S <= 256
@@ -692,7 +696,11 @@ def run_b200(a):
                                 ("g_R summed inside the NVSwitch (multimem.ld_reduce / multimem.st by the chunk owners), inside "
                                  "the backward") if (ring is not None and a.exchange == "nvls") else
                                 ("g_R summed over NVLink peer memory after the product (chunk owners pull, add in rank order, "
-                                 "store to every rank)" if not a.fused_exchange else
+                                 "store to every rank)" if a.serial_exchange else
+                                 "g_R summed over NVLink peer memory slab by slab BESIDE the g_R product: the product leaves 8 SMs "
+                                 "free and publishes finished tiles; an exchange kernel on those SMs pulls each finished 256-row "
+                                 "slab from every rank, adds in rank order, stores to every rank; the K-sliced tail rows after the "
+                                 "product" if not a.fused_exchange else
                                  "g_R summed over NVLink peer memory INSIDE the g_R product kernel, tile by tile (tile t belongs to "
                                  "rank t mod N: its math warps pull the finished tile from every rank, add in rank order, store to "
                                  "every rank; the K-sliced tail rows by the stand-alone reduce kernel)") if ring is not None

@@ -46,6 +46,9 @@ extern "C" {
                                                before the product instead of on the product kernel's math warps, just
                                                ahead of the tiles that read them (A/B measurements; same numbers) */
 
+#define MPVAE_FLAG_SERIAL_EXCHANGE      0x80u /* data-parallel dense regime: sum g_R over the ranks only AFTER the g_R product (the
+                                               stand-alone reduce kernel) instead of slab by slab on a few reserved SMs beside
+                                               it (A/B measurements; same sums) */
 #define MPVAE_FLAG_FUSED_EXCHANGE       0x40u /* data-parallel dense regime, opt-in: sum g_R over the ranks tile by tile INSIDE the
                                                g_R product kernel (peer_tile_done must be given) instead of with the
                                                stand-alone reduce kernel after it; same sums */

@@ -20,6 +20,7 @@ FLAG_STABLE_CDF = 0x8
 FLAG_FUSED_FORWARD = 0x10
 FLAG_SEPARATE_NOISE = 0x20
 FLAG_FUSED_EXCHANGE = 0x40
+FLAG_SERIAL_EXCHANGE = 0x80
 PEER_TILE_BYTES = 65536
 
 # every symbol include/mpvae_b200.h declares

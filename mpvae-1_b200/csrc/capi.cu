@@ -201,6 +201,26 @@ int validate(const mpvae_probit_params* p, bool backward) {
     return 0;
 }
 
+// side stream + events of the exchange that runs beside the g_R product (one process per GPU: created once per device,
+// at the first data-parallel backward -- i.e. during warm-up, never under CUDA-graph capture)
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+SideStream* side_stream() {
+    static SideStream ss[64];
+    static int state[64] = {};      // 0 = not created, 1 = ok, -1 = failed
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (state[dev] == 0) {
+        state[dev] = -1;
+        if (cudaStreamCreateWithFlags(&ss[dev].stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ss[dev].fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ss[dev].join, cudaEventDisableTiming) == cudaSuccess)
+            state[dev] = 1;
+    }
+    if (state[dev] != 1) { set_error("peer: side stream unavailable"); return nullptr; }
+    return &ss[dev];
+}
+
 long long peer_timeout_cycles() {
     static long long v = 0;
     if (v == 0) {
@@ -484,9 +504,23 @@ int mpvae_probit_backward(const mpvae_probit_params* p_in, void* cuda_stream) {
         if (tensor) {
             // data-parallel: the finished tiles are summed over the ranks inside the product kernel (fused_rows.cuh)
             FusePeer fp{};
-            const bool fused_x = peer && p->peer_tile_done[p->peer_rank] != nullptr && (p->flags & MPVAE_FLAG_FUSED_EXCHANGE) &&
-                                 !(p->peer_mc_part && p->peer_mc_g_r) &&
-                                 (size_t)ceil_div(p->L, 256) * ceil_div(p->Z, 256) * sizeof(uint32_t) <= MPVAE_PEER_TILE_BYTES;
+            const bool tiles_ok = peer && p->peer_tile_done[p->peer_rank] != nullptr && !(p->peer_mc_part && p->peer_mc_g_r) &&
+                                  (size_t)ceil_div(p->L, 256) * ceil_div(p->Z, 256) * sizeof(uint32_t) <= MPVAE_PEER_TILE_BYTES;
+            // 3: on the product kernel's own math warps (opt-in); 4: slab by slab on a few reserved SMs beside the product
+            // (default); 0: after the product
+            int xmode = 0;
+            if (tiles_ok && (p->flags & MPVAE_FLAG_FUSED_EXCHANGE)) xmode = 3;
+            else if (tiles_ok && !(p->flags & MPVAE_FLAG_SERIAL_EXCHANGE) && ceil_div(p->Z, 256) <= 32 && p->L >= 512) xmode = 4;
+            const bool fused_x = xmode != 0;
+            SideStream* side = nullptr;
+            if (xmode == 4) {
+                side = side_stream();
+                if (!side) return 2;
+                if (cudaEventRecord(side->fork, stream) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork, 0) != cudaSuccess) {
+                    set_error("peer: fork failed");
+                    return 2;
+                }
+            }
             if (fused_x) {
                 fp.world = pctx.world; fp.rank = pctx.rank; fp.step = pctx.step; fp.step_dev = pctx.step_dev;
                 fp.timeout_cycles = pctx.timeout_cycles;
@@ -501,8 +535,19 @@ int mpvae_probit_backward(const mpvae_probit_params* p_in, void* cuda_stream) {
             int exchanged = 0;
             // the noise planes the forward left in the workspace are the MN-major B operand as they are
             rc = tc_gemm_tn(base + w.gxs_planes, base + w.noise_planes, g_r_out, M, p->L, p->Z, slots + SLOT_ABSMAX_GXS, nullptr, stream,
-                            p->noise ? 0 : 1, base + w.tn_tail, tc_tail_scratch_bytes(), 0, fused_x ? &fp : nullptr, &exchanged);
+                            p->noise ? 0 : 1, base + w.tn_tail, tc_tail_scratch_bytes(), 0, fused_x ? &fp : nullptr, &exchanged,
+                            xmode == 4 ? 4 : 3);
             if (rc) return rc;
+            if (xmode == 4) {
+                // the complete 256-row slabs among the exchanged tiles go over NVLink beside the product, on the SMs it left free
+                const int tiles_n4 = ceil_div(p->Z, 256);
+                if (int rc2 = launch_peer_reduce_slabs(pctx, p->peer_tile_done, tiles_n4, exchanged / tiles_n4, (size_t)256 * p->Z,
+                                                       kExchangeSMs, side->stream)) return rc2;
+                if (cudaEventRecord(side->join, side->stream) != cudaSuccess || cudaStreamWaitEvent(stream, side->join, 0) != cudaSuccess) {
+                    set_error("peer: join failed");
+                    return 2;
+                }
+            }
             if (fused_x) {
                 // what is left: the rows of the K-sliced tail tiles (complete only now, after the fix-up kernel), and the
                 // two flag phases that tell every rank that all deliveries of this step have landed

@@ -47,7 +47,9 @@ constexpr int kCtrlWarps = 4;
 constexpr int kEpiWarps = 16;                            // 4 TMEM lane quadrants x 4 column quarters
 constexpr int HB = BN / 2;                               // B-tile columns staged by each CTA of a pair
 
-constexpr int threads_of(int math) { return 32 * (kCtrlWarps + (math ? kFuseMathWarps : 0) + kEpiWarps); }
+// MATH 1..3 add eight math warps; MATH 4 only publishes tile completions (no extra warps)
+constexpr bool has_math_warps(int math) { return math >= 1 && math <= 3; }
+constexpr int threads_of(int math) { return 32 * (kCtrlWarps + (has_math_warps(math) ? kFuseMathWarps : 0) + kEpiWarps); }
 
 // One k-block is one 128-byte swizzle row of K (K-major) or one TMA box of k-rows (MN-major); fp16 pieces.
 template <bool MN>
@@ -221,12 +223,14 @@ struct GemmArgs {
 
 // MATH: what the eight extra "math" warps of the CTA do (fused_rows.cuh): 0 = there are none, 1 = the probit row
 // forward on finished tiles (opt-in), 2 = draw the Philox noise of the A operand just ahead of the tiles that read it,
-// 3 = sum the finished tiles over the ranks of a data-parallel run through NVLink peer memory.
+// 3 = sum the finished tiles over the ranks of a data-parallel run through NVLink peer memory, 4 = no math warps, but
+// finished tiles are published in peer memory for the exchange kernel that runs BESIDE this one on a few reserved SMs.
 template <bool MN, int EX, int MATH, bool STABLE>
 __global__ void __launch_bounds__(threads_of(MATH), 1)
 gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g,
                       const FuseFwd fz, const FuseNoise fnz, const FusePeer fpz) {
-    constexpr bool FUSE = MATH != 0;
+    constexpr bool FUSE = MATH >= 1 && MATH <= 3;
+    constexpr bool PUBLISH = MATH == 3 || MATH == 4;
     using G = Geo<MN>;
     using R2 = Ring<EX>;
     constexpr int STAGES2 = R2::STAGES, STAGE2_BYTES = R2::STAGE_BYTES;
@@ -261,7 +265,7 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         return it;
     };
     if (threadIdx.x == 0) {
-        if (MATH == 3) {   // the peer exchange's watermark and the promotion warps' arrival count
+        if (PUBLISH) {   // the peer exchange's watermark and the promotion warps' arrival count
             *reinterpret_cast<volatile int*>(gen + R2::RING_BYTES + 192) = 0;
             *reinterpret_cast<volatile int*>(gen + R2::RING_BYTES + 196) = 0;
         }
@@ -362,7 +366,7 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     if (++buf == 2) { buf = 0; bphase ^= 1u; }
                 }
             }
-        } else if (MATH == 3 && warp == 3 && lane == 0) {   // ------------------------------- tile publisher
+        } else if (PUBLISH && warp == 3 && lane == 0) {   // --------------------------------- tile publisher
             int n = 0;
             for (int w = cluster; w < num_items; w += num_clusters) {
                 const Item it = item_of(w, num_kb);
@@ -449,7 +453,7 @@ gemm_split_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 }
             }
             if (MATH == 1) fuse_signal_tile(fz.done, st, lane);   // this warp's part of the tile is in memory
-            if (MATH == 3 && it.slice == 0 && st < fpz.full_tiles)
+            if (PUBLISH && it.slice == 0 && st < fpz.full_tiles)
                 peer_arrive_tile(reinterpret_cast<volatile int*>(gen + R2::RING_BYTES + 196), lane);
 #pragma unroll
             for (int j = 0; j < 64; ++j) acc[j] = 0.0f;
@@ -645,7 +649,8 @@ int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, GemmArgs g, cons
         if (e != cudaSuccess || n <= 0) { set_error("cudaOccupancyMaxActiveClusters: %s", cudaGetErrorString(e)); return 4; }
         max_clusters[dev] = n < kNumSMs / 2 ? n : kNumSMs / 2;
     }
-    const int mc = max_clusters[dev];
+    // MATH == 4: a few SM pairs are left to the exchange kernel that runs beside this one (peer_reduce.cu)
+    const int mc = max_clusters[dev] - (MATH == 4 ? kExchangeSMs / 2 : 0);
     const int tiles = g.tiles_m * g.tiles_n;
     // K-split of the last, partial wave: worth it when the wave would leave at least half of the pairs idle and the
     // caller gave scratch for the slices
@@ -664,7 +669,7 @@ int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, GemmArgs g, cons
     const int items = g.full_tiles + (tiles - g.full_tiles) * g.ksplit;
     const int clusters = items < mc ? items : mc;
     cfg.gridDim = dim3(2 * clusters);
-    if (MATH == 3) {
+    if (MATH == 3 || MATH == 4) {
         // the K-sliced tail tiles are complete only after tail_fixup_kernel: they are exchanged after this kernel
         fpz.full_tiles = g.full_tiles;
         fpz.tiles_n = g.tiles_n;
@@ -687,7 +692,7 @@ template <bool MN>
 int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc, int Nc, int K, int ldc, const uint32_t* ma,
                 const uint32_t* mb, cudaStream_t stream, int ex, float* partials, size_t partials_bytes,
                 const FuseFwd* fuse = nullptr, const FuseNoise* noise = nullptr, const FusePeer* peer = nullptr,
-                int* exchanged_tiles = nullptr) {
+                int* exchanged_tiles = nullptr, int peer_mode = 3) {
     GemmArgs g{};
     g.C = C; g.Mc = Mc; g.Nc = Nc; g.K = K; g.ldc = ldc;
     g.tiles_m = ceil_div(Mc, 256); g.tiles_n = ceil_div(Nc, BN);
@@ -699,6 +704,10 @@ int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc, in
     const FuseNoise nonoise{};
     if (peer != nullptr) {
         if (!MN || ex == 1 || fuse != nullptr || noise != nullptr) { set_error("fused exchange: tn products only"); return 7; }
+        if (peer_mode == 4) {
+            if (ex == 2) return launch_gemm_2sm<true, 2, 4, false>(a, b, g, none, nonoise, stream, partials_bytes, *peer, exchanged_tiles);
+            return launch_gemm_2sm<true, 0, 4, false>(a, b, g, none, nonoise, stream, partials_bytes, *peer, exchanged_tiles);
+        }
         if (ex == 2) return launch_gemm_2sm<true, 2, 3, false>(a, b, g, none, nonoise, stream, partials_bytes, *peer, exchanged_tiles);
         return launch_gemm_2sm<true, 0, 3, false>(a, b, g, none, nonoise, stream, partials_bytes, *peer, exchanged_tiles);
     }
@@ -871,14 +880,14 @@ int tc_gemm_nt(const void* a_planes, const void* b_planes, float* C, int M, int 
 
 int tc_gemm_tn(const void* a_planes, const void* b_planes, float* C, int M, int N1, int N2, const uint32_t* absmax_a,
                const uint32_t* absmax_b, cudaStream_t stream, int b_exact, void* tail_scratch, size_t tail_scratch_bytes,
-               int a_pitch, const FusePeer* peer, int* exchanged_tiles) {
+               int a_pitch, const FusePeer* peer, int* exchanged_tiles, int peer_mode) {
     // a_pitch > 0: A is a column range of wider planes (row slab of C): a_planes points at its first column
     const int p1 = a_pitch > 0 ? a_pitch : pitch_of(N1), p2 = pitch_of(N2);
     CUtensorMap ma, mb;
     if (int rc = make_map(&ma, a_planes, N1, M, p1, 64, 64)) return rc;
     if (int rc = make_map(&mb, b_planes, N2, M, p2, 64, 64, b_exact ? 1 : 2)) return rc;
     return launch_gemm<true>(ma, mb, C, N1, N2, M, N2, absmax_a, absmax_b, stream, b_exact ? 2 : 0, static_cast<float*>(tail_scratch),
-                             tail_scratch_bytes, nullptr, nullptr, peer, exchanged_tiles);
+                             tail_scratch_bytes, nullptr, nullptr, peer, exchanged_tiles, peer_mode);
 }
 
 }  // namespace mpv

@@ -197,6 +197,110 @@ peer_reduce_nvls_kernel(PeerCtx ctx, const float* __restrict__ mc_part, float* _
 
 }  // namespace
 
+// ---- the exchange that runs BESIDE the g_R product (capi.cu forks a side stream for it) ----
+// The product (contract_tc.cu, MATH = 4) leaves kExchangeSMs SMs free and publishes every finished 256 x 256 tile in a
+// per-tile counter in peer memory.  This kernel owns those SMs (one 1024-thread CTA each, the shared-memory request keeps
+// them apart): it walks the 256-row slabs of g_R in the order the product finishes them, waits until slab s is complete
+// on EVERY rank, and does for the slab what peer_reduce_bcast_kernel does for the whole matrix (pull this rank's chunk of
+// the slab from all ranks, add in rank order, store to all ranks) -- while the tensor pipes of the other 140 SMs keep
+// working on later slabs.  The product never waits for this kernel, so the two cannot deadlock whatever the
+// scheduling; if the hardware ran them one after the other the result would be the same, only later.
+struct SlabArgs {
+    const unsigned int* done[8];   // every rank's per-tile counters
+    unsigned int step;             // a tile is complete when its counter has reached 32 * (step + *step_dev)
+    const unsigned int* step_dev;
+    int tiles_n, n_slabs;
+    size_t slab_elems;             // 256 * Z floats: a multiple of 4, slabs are 16-byte aligned
+};
+
+template <int W>
+__global__ void __launch_bounds__(1024, 1)
+peer_reduce_slabs_kernel(PeerCtx ctx, SlabArgs sa) {
+    __shared__ int s_go;
+    const unsigned int target = 32u * (sa.step + (sa.step_dev ? *sa.step_dev : 0u));
+    const size_t n4 = sa.slab_elems / 4, per = (n4 + W - 1) / W;
+    const size_t lo = (size_t)ctx.rank * per, hi = min(n4, lo + per);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int s = 0; s < sa.n_slabs; ++s) {
+        if (threadIdx.x < 32) {
+            // lane = tile of the slab (tiles_n <= 32); every rank's counter of that tile
+            const long long t0 = clock64();
+            bool ok = false;
+            while (!ok) {
+                ok = true;
+                if ((int)threadIdx.x < sa.tiles_n)
+                    for (int r = 0; r < W; ++r) {
+                        unsigned int v;
+                        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(sa.done[r] + s * sa.tiles_n + threadIdx.x) : "memory");
+                        ok = ok && (int)(v - target) >= 0;
+                    }
+                ok = __all_sync(0xffffffffu, ok);
+                if (!ok) {
+                    __nanosleep(500);
+                    if (clock64() - t0 > ctx.timeout_cycles) { if (threadIdx.x == 0) atomicMax(ctx.flags[ctx.rank] + kErrWord, sa.step); break; }
+                }
+            }
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            if (threadIdx.x == 0) s_go = s + 1;
+        }
+        __syncthreads();
+        const size_t base4 = (size_t)s * n4;
+        for (size_t i0 = lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < hi; i0 += stride * 2) {
+            const size_t i1 = i0 + stride;
+            const bool two = i1 < hi;
+            float4 v0[W], v1[W];
+#pragma unroll
+            for (int r = 0; r < W; ++r) {
+                v0[r] = reinterpret_cast<const float4*>(ctx.part[r])[base4 + i0];
+                if (two) v1[r] = reinterpret_cast<const float4*>(ctx.part[r])[base4 + i1];
+            }
+            float4 a = v0[0], b = two ? v1[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 1; r < W; ++r) {
+                a.x += v0[r].x; a.y += v0[r].y; a.z += v0[r].z; a.w += v0[r].w;
+                if (two) { b.x += v1[r].x; b.y += v1[r].y; b.z += v1[r].z; b.w += v1[r].w; }
+            }
+#pragma unroll
+            for (int r = 0; r < W; ++r) {
+                reinterpret_cast<float4*>(ctx.g_r[r])[base4 + i0] = a;
+                if (two) reinterpret_cast<float4*>(ctx.g_r[r])[base4 + i1] = b;
+            }
+        }
+        __syncthreads();      // s_go is rewritten by the next slab's wait
+    }
+    __threadfence_system();
+}
+
+int launch_peer_reduce_slabs(const PeerCtx& ctx, void* const* tile_done, int tiles_n, int n_slabs, size_t slab_elems, int ctas,
+                             cudaStream_t stream) {
+    if (n_slabs <= 0) return 0;
+    if (tiles_n > 32 || (slab_elems & 3) != 0) { set_error("peer slabs: tiles_n %d / slab of %zu floats unsupported", tiles_n, slab_elems); return 1; }
+    SlabArgs sa{};
+    for (int i = 0; i < ctx.world; ++i) sa.done[i] = static_cast<const unsigned int*>(tile_done[i]);
+    sa.step = ctx.step; sa.step_dev = ctx.step_dev;
+    sa.tiles_n = tiles_n; sa.n_slabs = n_slabs; sa.slab_elems = slab_elems;
+    // 160 KiB of (unused) dynamic shared memory per CTA: one CTA per SM, so `ctas` CTAs take exactly `ctas` SMs
+    const size_t smem = 160 * 1024;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+#define MPV_SLABS(Wn)                                                                                                             \
+    case Wn:                                                                                                                      \
+        if (!configured[dev] && cudaFuncSetAttribute(peer_reduce_slabs_kernel<Wn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { \
+            set_error("cudaFuncSetAttribute(peer slabs) failed");                                                                 \
+            return 4;                                                                                                             \
+        }                                                                                                                         \
+        peer_reduce_slabs_kernel<Wn><<<ctas, 1024, smem, stream>>>(ctx, sa);                                                      \
+        break;
+    switch (ctx.world) {
+        MPV_SLABS(2) MPV_SLABS(3) MPV_SLABS(4) MPV_SLABS(5) MPV_SLABS(6) MPV_SLABS(7) MPV_SLABS(8)
+        default: set_error("peer reduce: world size %d not in [2, 8]", ctx.world); return 1;
+    }
+#undef MPV_SLABS
+    return check_launch("peer_reduce_slabs_kernel");
+}
+
 template <int W>
 static void launch_reduce_w(const PeerCtx& ctx, size_t n, int ctas, int unroll, cudaStream_t stream) {
     if (unroll >= 4 && W <= 4) peer_reduce_bcast_kernel<W, 4><<<ctas, 256, 0, stream>>>(ctx, n);

@@ -920,9 +920,7 @@ int launch_row_forward(RowArgs a, cudaStream_t stream) {
     FusePart* part = const_cast<FusePart*>(a.part);
     // two CTAs of 256 threads per SM (<= 128 registers: sixteen cells in flight per lane, no spills); measured equal
     // to or faster than three (80 registers, spills) and four (64) on B200
-    static const int minb = getenv("MPVAE_FWD_MINB") ? atoi(getenv("MPVAE_FWD_MINB")) : 2;   // TEMP experiment knob
     if (a.stable) probit_row_fwd_tiled_kernel<true, 2><<<dim3(a.B, gy), kThreads, 0, stream>>>(a, part, nchunks);
-    else if (minb == 3) probit_row_fwd_tiled_kernel<false, 3><<<dim3(a.B, gy), kThreads, 0, stream>>>(a, part, nchunks);
     else probit_row_fwd_tiled_kernel<false, 2><<<dim3(a.B, gy), kThreads, 0, stream>>>(a, part, nchunks);
     if (int rc = check_launch("probit_row_fwd_tiled_kernel")) return rc;
     a.part_tiles = nchunks;

@@ -111,6 +111,10 @@ struct PeerCtx {
 size_t peer_flag_bytes();
 int peer_error_word();   // index of the error word inside a rank's flag block (0 = no wait has timed out)
 int launch_peer_reduce(const PeerCtx& ctx, size_t n, cudaStream_t stream, size_t first = 0);   // elements [first, first + n)
+// the same sum for the first n_slabs 256-row slabs of g_R, slab by slab as the product (running beside it) publishes
+// them in the per-tile counters `tile_done` (peer memory); `ctas` CTAs, one per SM
+int launch_peer_reduce_slabs(const PeerCtx& ctx, void* const* tile_done, int tiles_n, int n_slabs, size_t slab_elems, int ctas,
+                             cudaStream_t stream);
 int launch_peer_reduce_nvls(const PeerCtx& ctx, const float* mc_part, float* mc_gr, size_t n, cudaStream_t stream);
 
 // clip_grad_norm_ + Adam over flat buffers (optim.cu)

@@ -178,3 +178,4 @@ FLAG_CONTRACT_FMA = _lib.FLAG_CONTRACT_FMA
 FLAG_FUSED_FORWARD = _lib.FLAG_FUSED_FORWARD
 FLAG_SEPARATE_NOISE = _lib.FLAG_SEPARATE_NOISE
 FLAG_FUSED_EXCHANGE = _lib.FLAG_FUSED_EXCHANGE
+FLAG_SERIAL_EXCHANGE = _lib.FLAG_SERIAL_EXCHANGE
