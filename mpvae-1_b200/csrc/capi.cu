@@ -540,8 +540,12 @@ int mpvae_probit_backward(const mpvae_probit_params* p_in, void* cuda_stream) {
             if (rc) return rc;
             if (xmode == 4) {
                 // the complete 256-row slabs among the exchanged tiles go over NVLink beside the product, on the SMs it left free
+                // (only slabs of a full 256 rows: a partial last slab goes with the tail rows)
                 const int tiles_n4 = ceil_div(p->Z, 256);
-                if (int rc2 = launch_peer_reduce_slabs(pctx, p->peer_tile_done, tiles_n4, exchanged / tiles_n4, (size_t)256 * p->Z,
+                int n_slabs = exchanged / tiles_n4;
+                if (n_slabs > p->L / 256) n_slabs = p->L / 256;
+                exchanged = n_slabs * tiles_n4;
+                if (int rc2 = launch_peer_reduce_slabs(pctx, p->peer_tile_done, tiles_n4, n_slabs, (size_t)256 * p->Z,
                                                        kExchangeSMs, side->stream)) return rc2;
                 if (cudaEventRecord(side->join, side->stream) != cudaSuccess || cudaStreamWaitEvent(stream, side->join, 0) != cudaSuccess) {
                     set_error("peer: join failed");

@@ -660,10 +660,17 @@ int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, GemmArgs g, cons
     if (MATH != 1 && g.partials != nullptr && !no_split) {
         const int tail = tiles % mc, num_kb = ceil_div(g.K, Geo<MN>::BK);
         if (tail > 0) {
-            int f = mc / tail;
-            if (f > num_kb / g.kc) f = num_kb / g.kc;                  // a slice keeps at least one full TMEM chunk
-            if (f > 8) f = 8;
-            if (f >= 2 && (size_t)tail * (f - 1) * 256 * BN * sizeof(float) <= partials_bytes) { g.full_tiles = tiles - tail; g.ksplit = f; }
+            // f slices per tail tile: the tail then takes ceil(tail * f / mc) / f of a tile time instead of a whole one;
+            // the smallest f with the smallest cost, as long as a slice keeps a full TMEM chunk and the scratch holds it
+            int best = 1;
+            double best_cost = 1.0;
+            for (int f = 2; f <= 8; ++f) {
+                if (f > num_kb / g.kc) break;
+                if ((size_t)tail * (f - 1) * 256 * BN * sizeof(float) > partials_bytes) break;
+                const double cost = (double)ceil_div(tail * f, mc) / f;
+                if (cost < best_cost - 1e-9) { best_cost = cost; best = f; }
+            }
+            if (best >= 2) { g.full_tiles = tiles - tail; g.ksplit = best; }
         }
     }
     const int items = g.full_tiles + (tiles - g.full_tiles) * g.ksplit;
@@ -864,7 +871,8 @@ int tc_absmax(const float* src, size_t n, uint32_t* out_bits, cudaStream_t strea
     return check_launch("absmax_kernel");
 }
 
-size_t tc_tail_scratch_bytes() { return (size_t)(kNumSMs / 2 - 1) * 256 * BN * sizeof(float); }
+// room for two extra K-slices of every tile of a partial wave (three slices per tile), or seven of a short one
+size_t tc_tail_scratch_bytes() { return (size_t)(kNumSMs / 2 - 1) * 2 * 256 * BN * sizeof(float); }
 
 int tc_gemm_nt(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, const uint32_t* absmax_a,
                const uint32_t* absmax_b, cudaStream_t stream, int ldc, int a_exact, void* tail_scratch, size_t tail_scratch_bytes,

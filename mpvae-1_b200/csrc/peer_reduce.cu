@@ -291,6 +291,7 @@ int launch_peer_reduce_slabs(const PeerCtx& ctx, void* const* tile_done, int til
             set_error("cudaFuncSetAttribute(peer slabs) failed");                                                                 \
             return 4;                                                                                                             \
         }                                                                                                                         \
+        configured[dev] = true;                                                                                                   \
         peer_reduce_slabs_kernel<Wn><<<ctas, 1024, smem, stream>>>(ctx, sa);                                                      \
         break;
     switch (ctx.world) {
