@@ -1,6 +1,7 @@
 // extern "C" surface of libmpvae_b200 (include/mpvae_b200.h): argument validation, workspace carving and the
 // launch sequence of one forward / backward of the probit ELBO.
 #include <atomic>
+#include <map>
 #include <mutex>
 #include <stdlib.h>
 #include <string.h>
@@ -219,6 +220,17 @@ SideStream* side_stream() {
     }
     if (state[dev] != 1) { set_error("peer: side stream unavailable"); return nullptr; }
     return &ss[dev];
+}
+
+// Exchanges that go through the per-tile counters (beside / inside the product) count themselves per counter buffer: the
+// counters are monotonic and a tile is complete when its counter has reached 32 x this epoch.  Every rank takes the
+// same decisions for the same calls, so the epochs agree across the ranks; exchanges that do not touch the counters
+// (the stand-alone reduce, mpvae_peer_allreduce) do not advance them.
+std::mutex g_epoch_mu;
+std::map<const void*, uint32_t> g_tile_epoch;
+uint32_t next_tile_epoch(const void* counters) {
+    std::lock_guard<std::mutex> lk(g_epoch_mu);
+    return ++g_tile_epoch[counters];
 }
 
 long long peer_timeout_cycles() {
@@ -509,7 +521,8 @@ int mpvae_probit_backward(const mpvae_probit_params* p_in, void* cuda_stream) {
             // 3: on the product kernel's own math warps (opt-in); 4: slab by slab on a few reserved SMs beside the product
             // (default); 0: after the product
             int xmode = 0;
-            if (tiles_ok && (p->flags & MPVAE_FLAG_FUSED_EXCHANGE)) xmode = 3;
+            if (p->peer_step_dev != nullptr) xmode = 0;          // CUDA-graph replay: the epoch below would be baked in
+            else if (tiles_ok && (p->flags & MPVAE_FLAG_FUSED_EXCHANGE)) xmode = 3;
             else if (tiles_ok && !(p->flags & MPVAE_FLAG_SERIAL_EXCHANGE) && ceil_div(p->Z, 256) <= 32 && p->L >= 512) xmode = 4;
             const bool fused_x = xmode != 0;
             SideStream* side = nullptr;
@@ -521,8 +534,11 @@ int mpvae_probit_backward(const mpvae_probit_params* p_in, void* cuda_stream) {
                     return 2;
                 }
             }
+            PeerCtx sctx = pctx;                                 // the slab exchange: flag value = the tile epoch
             if (fused_x) {
-                fp.world = pctx.world; fp.rank = pctx.rank; fp.step = pctx.step; fp.step_dev = pctx.step_dev;
+                const uint32_t epoch = next_tile_epoch(p->peer_tile_done[p->peer_rank]);
+                sctx.step = epoch; sctx.step_dev = nullptr;
+                fp.world = pctx.world; fp.rank = pctx.rank; fp.step = epoch; fp.step_dev = nullptr;
                 fp.timeout_cycles = pctx.timeout_cycles;
                 fp.err = pctx.flags[pctx.rank] + peer_error_word();
                 for (int i = 0; i < pctx.world; ++i) {
@@ -545,7 +561,7 @@ int mpvae_probit_backward(const mpvae_probit_params* p_in, void* cuda_stream) {
                 int n_slabs = exchanged / tiles_n4;
                 if (n_slabs > p->L / 256) n_slabs = p->L / 256;
                 exchanged = n_slabs * tiles_n4;
-                if (int rc2 = launch_peer_reduce_slabs(pctx, p->peer_tile_done, tiles_n4, n_slabs, (size_t)256 * p->Z,
+                if (int rc2 = launch_peer_reduce_slabs(sctx, p->peer_tile_done, tiles_n4, n_slabs, (size_t)256 * p->Z,
                                                        kExchangeSMs, side->stream)) return rc2;
                 if (cudaEventRecord(side->join, side->stream) != cudaSuccess || cudaStreamWaitEvent(stream, side->join, 0) != cudaSuccess) {
                     set_error("peer: join failed");

@@ -207,17 +207,18 @@ peer_reduce_nvls_kernel(PeerCtx ctx, const float* __restrict__ mc_part, float* _
 // scheduling; if the hardware ran them one after the other the result would be the same, only later.
 struct SlabArgs {
     const unsigned int* done[8];   // every rank's per-tile counters
-    unsigned int step;             // a tile is complete when its counter has reached 32 * (step + *step_dev)
-    const unsigned int* step_dev;
+    unsigned int step;             // the tile epoch: a tile is complete when its counter has reached 32 * step
     int tiles_n, n_slabs;
     size_t slab_elems;             // 256 * Z floats: a multiple of 4, slabs are 16-byte aligned
 };
 
 template <int W>
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(512, 1)
 peer_reduce_slabs_kernel(PeerCtx ctx, SlabArgs sa) {
-    __shared__ int s_go;
-    const unsigned int target = 32u * (sa.step + (sa.step_dev ? *sa.step_dev : 0u));
+    // 16 loads of 16 bytes in flight per thread whatever the world size (an SM moves what it has in flight per NVLink
+    // round trip: 512 threads x 256 B = 128 KiB per ~2.5 us = ~50 GB/s per SM)
+    constexpr int U = (16 / W) < 1 ? 1 : (16 / W);
+    const unsigned int target = 32u * sa.step;
     const size_t n4 = sa.slab_elems / 4, per = (n4 + W - 1) / W;
     const size_t lo = (size_t)ctx.rank * per, hi = min(n4, lo + per);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -241,32 +242,30 @@ peer_reduce_slabs_kernel(PeerCtx ctx, SlabArgs sa) {
                 }
             }
             asm volatile("fence.acq_rel.sys;" ::: "memory");
-            if (threadIdx.x == 0) s_go = s + 1;
         }
         __syncthreads();
         const size_t base4 = (size_t)s * n4;
-        for (size_t i0 = lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < hi; i0 += stride * 2) {
-            const size_t i1 = i0 + stride;
-            const bool two = i1 < hi;
-            float4 v0[W], v1[W];
+        for (size_t i0 = lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < hi; i0 += stride * U) {
+            float4 v[U][W];
 #pragma unroll
-            for (int r = 0; r < W; ++r) {
-                v0[r] = reinterpret_cast<const float4*>(ctx.part[r])[base4 + i0];
-                if (two) v1[r] = reinterpret_cast<const float4*>(ctx.part[r])[base4 + i1];
-            }
-            float4 a = v0[0], b = two ? v1[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int u = 0; u < U; ++u) {
+                const size_t i = i0 + u * stride;
 #pragma unroll
-            for (int r = 1; r < W; ++r) {
-                a.x += v0[r].x; a.y += v0[r].y; a.z += v0[r].z; a.w += v0[r].w;
-                if (two) { b.x += v1[r].x; b.y += v1[r].y; b.z += v1[r].z; b.w += v1[r].w; }
+                for (int r = 0; r < W; ++r)
+                    v[u][r] = i < hi ? reinterpret_cast<const float4*>(ctx.part[r])[base4 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-            for (int r = 0; r < W; ++r) {
-                reinterpret_cast<float4*>(ctx.g_r[r])[base4 + i0] = a;
-                if (two) reinterpret_cast<float4*>(ctx.g_r[r])[base4 + i1] = b;
+            for (int u = 0; u < U; ++u) {
+                const size_t i = i0 + u * stride;
+                if (i >= hi) continue;
+                float4 a = v[u][0];
+#pragma unroll
+                for (int r = 1; r < W; ++r) { a.x += v[u][r].x; a.y += v[u][r].y; a.z += v[u][r].z; a.w += v[u][r].w; }
+#pragma unroll
+                for (int r = 0; r < W; ++r) reinterpret_cast<float4*>(ctx.g_r[r])[base4 + i] = a;
             }
         }
-        __syncthreads();      // s_go is rewritten by the next slab's wait
+        __syncthreads();
     }
     __threadfence_system();
 }
@@ -277,7 +276,7 @@ int launch_peer_reduce_slabs(const PeerCtx& ctx, void* const* tile_done, int til
     if (tiles_n > 32 || (slab_elems & 3) != 0) { set_error("peer slabs: tiles_n %d / slab of %zu floats unsupported", tiles_n, slab_elems); return 1; }
     SlabArgs sa{};
     for (int i = 0; i < ctx.world; ++i) sa.done[i] = static_cast<const unsigned int*>(tile_done[i]);
-    sa.step = ctx.step; sa.step_dev = ctx.step_dev;
+    sa.step = ctx.step;
     sa.tiles_n = tiles_n; sa.n_slabs = n_slabs; sa.slab_elems = slab_elems;
     // 160 KiB of (unused) dynamic shared memory per CTA: one CTA per SM, so `ctas` CTAs take exactly `ctas` SMs
     const size_t smem = 160 * 1024;
@@ -292,7 +291,7 @@ int launch_peer_reduce_slabs(const PeerCtx& ctx, void* const* tile_done, int til
             return 4;                                                                                                             \
         }                                                                                                                         \
         configured[dev] = true;                                                                                                   \
-        peer_reduce_slabs_kernel<Wn><<<ctas, 1024, smem, stream>>>(ctx, sa);                                                      \
+        peer_reduce_slabs_kernel<Wn><<<ctas, 512, smem, stream>>>(ctx, sa);                                                      \
         break;
     switch (ctx.world) {
         MPV_SLABS(2) MPV_SLABS(3) MPV_SLABS(4) MPV_SLABS(5) MPV_SLABS(6) MPV_SLABS(7) MPV_SLABS(8)
