@@ -562,7 +562,7 @@ int mpvae_probit_backward(const mpvae_probit_params* p_in, void* cuda_stream) {
                 if (n_slabs > p->L / 256) n_slabs = p->L / 256;
                 exchanged = n_slabs * tiles_n4;
                 if (int rc2 = launch_peer_reduce_slabs(sctx, p->peer_tile_done, tiles_n4, n_slabs, (size_t)256 * p->Z,
-                                                       kExchangeSMs, side->stream)) return rc2;
+                                                       exchange_sms(), side->stream)) return rc2;
                 if (cudaEventRecord(side->join, side->stream) != cudaSuccess || cudaStreamWaitEvent(stream, side->join, 0) != cudaSuccess) {
                     set_error("peer: join failed");
                     return 2;

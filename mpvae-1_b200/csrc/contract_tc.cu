@@ -650,7 +650,7 @@ int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, GemmArgs g, cons
         max_clusters[dev] = n < kNumSMs / 2 ? n : kNumSMs / 2;
     }
     // MATH == 4: a few SM pairs are left to the exchange kernel that runs beside this one (peer_reduce.cu)
-    const int mc = max_clusters[dev] - (MATH == 4 ? kExchangeSMs / 2 : 0);
+    const int mc = max_clusters[dev] - (MATH == 4 ? exchange_sms() / 2 : 0);
     const int tiles = g.tiles_m * g.tiles_n;
     // K-split of the last, partial wave: worth it when the wave would leave at least half of the pairs idle and the
     // caller gave scratch for the slices
@@ -739,6 +739,18 @@ int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc, in
 }  // namespace
 
 bool tc_available() { return true; }
+
+int exchange_sms() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("MPVAE_EXCHANGE_SMS");
+        v = e ? atoi(e) : 8;
+        if (v < 2) v = 2;
+        if (v > 64) v = 64;
+        v &= ~1;
+    }
+    return v;
+}
 
 // [absmax slots] [A planes] [B planes] [tail-wave scratch]
 size_t tc_workspace_nt(int M, int N, int K) {
