@@ -523,7 +523,8 @@ int mpvae_probit_backward(const mpvae_probit_params* p_in, void* cuda_stream) {
             int xmode = 0;
             if (p->peer_step_dev != nullptr) xmode = 0;          // CUDA-graph replay: the epoch below would be baked in
             else if (tiles_ok && (p->flags & MPVAE_FLAG_FUSED_EXCHANGE)) xmode = 3;
-            else if (tiles_ok && !(p->flags & MPVAE_FLAG_SERIAL_EXCHANGE) && ceil_div(p->Z, 256) <= 32 && p->L >= 512) xmode = 4;
+            else if (tiles_ok && !(p->flags & MPVAE_FLAG_SERIAL_EXCHANGE) && ceil_div(p->Z, 256) <= 32 && p->L >= 512 &&
+                     (long long)p->S * p->B >= 8192) xmode = 4;   // shorter products cannot hide the exchange (measured)
             const bool fused_x = xmode != 0;
             SideStream* side = nullptr;
             if (xmode == 4) {
@@ -562,7 +563,7 @@ int mpvae_probit_backward(const mpvae_probit_params* p_in, void* cuda_stream) {
                 if (n_slabs > p->L / 256) n_slabs = p->L / 256;
                 exchanged = n_slabs * tiles_n4;
                 if (int rc2 = launch_peer_reduce_slabs(sctx, p->peer_tile_done, tiles_n4, n_slabs, (size_t)256 * p->Z,
-                                                       exchange_sms(), side->stream)) return rc2;
+                                                       exchange_sms(p->peer_world), side->stream)) return rc2;
                 if (cudaEventRecord(side->join, side->stream) != cudaSuccess || cudaStreamWaitEvent(stream, side->join, 0) != cudaSuccess) {
                     set_error("peer: join failed");
                     return 2;

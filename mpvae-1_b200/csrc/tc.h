@@ -60,6 +60,6 @@ int tc_gemm_tn(const void* a_planes, const void* b_planes, float* C, int M, int 
                // peer memory) and leaves kExchangeSMs SMs free for the exchange kernel the caller runs beside it
                const FusePeer* peer = nullptr, int* exchanged_tiles = nullptr, int peer_mode = 3);
 // SMs the g_R product leaves to the exchange kernel running beside it (even; MPVAE_EXCHANGE_SMS overrides: experiments)
-int exchange_sms();
+int exchange_sms(int world);
 
 }  // namespace mpv
