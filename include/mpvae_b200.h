@@ -125,11 +125,13 @@ typedef struct mpvae_probit_params {
     /* optional DEVICE counter added to peer_step inside the exchange kernels and advanced by them after every exchange,
        so that a captured CUDA graph (which replays the same peer_step) keeps the flag values increasing; NULL = unused */
     uint32_t *peer_step_dev;
-    /* optional: every rank's per-tile completion counters (mpvae_peer_alloc'ed, MPVAE_PEER_TILE_BYTES each, zeroed once).
-       With them the g_R product of the dense regime sums its finished 256 x 256 tiles over the ranks INSIDE the product
-       kernel (csrc/fused_rows.cuh: tile t belongs to rank t mod world, whose math warps pull it from every rank over
-       NVLink, add in rank order and store to every rank) while the tensor pipe computes later tiles; NULL = the
-       stand-alone reduce kernel after the product */
+    /* optional: every rank's per-tile completion counters (mpvae_peer_alloc'ed, MPVAE_PEER_TILE_BYTES each, zeroed once,
+       never reset: the library keeps the epoch).  With them the g_R product of the dense regime publishes every finished
+       256 x 256 tile there and leaves a few SMs idle; an exchange kernel on those SMs (csrc/peer_reduce.cu, a side
+       stream forked from and joined to the caller's) sums finished 256-row slabs of g_R over the ranks through NVLink
+       while the tensor pipe computes later tiles.  MPVAE_FLAG_FUSED_EXCHANGE moves the sums onto the product kernel's
+       own math warps instead (csrc/fused_rows.cuh; slower), MPVAE_FLAG_SERIAL_EXCHANGE or NULL = the stand-alone
+       reduce kernel after the product.  Products of fewer than 8192 rows (S * B) always take the latter. */
     void *peer_tile_done[8];
 } mpvae_probit_params;
 #define MPVAE_PEER_TILE_BYTES 65536u
