@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-torch-baseline", action="store_true", help="skip the reference-on-this-GPU (torch CUDA ops) leg")
     ap.add_argument("--no-train-step", action="store_true", help="skip the full-training-step (steps/s) leg")
+    ap.add_argument("--profile-host", action="store_true",
+                    help="diagnostic: cProfile of 20 end-to-end steps on the host (top entries to stderr) after the timed legs")
     ap.add_argument("--engine", default="auto", choices=["auto", "fma", "tensor"])
     ap.add_argument("--fused-row-forward", action="store_true",
                     help="dense regime: run the row forward on math warps inside the product kernel (A/B; measured slower)")
@@ -473,6 +475,21 @@ def run_b200(a):
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     total_ms, total_e2e = max_over_ranks(total_ms, total_e2e)
+    if a.profile_host and rank == 0:
+        import cProfile
+        import io
+        import pstats
+        import time
+        torch.cuda.synchronize()
+        prof = cProfile.Profile()
+        t0 = time.perf_counter()
+        prof.enable()
+        timed_e2e(main, 20)
+        prof.disable()
+        buf = io.StringIO()
+        pstats.Stats(prof, stream=buf).sort_stats("cumulative").print_stats(45)
+        print(f"[bench] host wall per e2e step (incl. the final sync): {(time.perf_counter() - t0) / 20 * 1e3:.3f} ms\n"
+              + buf.getvalue(), file=sys.stderr)
     if ring is not None:
         ring.check()                # a flag wait that timed out would have produced invalid sums
 

@@ -27,49 +27,103 @@ label_counts_kernel(const float* __restrict__ prob, const float* __restrict__ y,
     if (fn) atomicAdd(&counts[2 * L + l], fn);
 }
 
-// warp per row: exact-match flag, xor count, tp, |pred|, |target|, and the hits among the top-1/3/5 scores
-__global__ void __launch_bounds__(256)
+// CTA (4 warps) per row: exact-match flag, xor count, tp, |pred|, |target|, and the hits among the top-1/3/5 scores.
+// ONE pass over the row: every thread keeps the five best of its own elements in registers (ordered by score, ties
+// towards the HIGHER index: np.argsort ascending, then reversed, evals.py:37), the warp merges the 32 lists with five
+// rounds of an arg-max over their heads, warp 0 merges the four warps' lists the same way.
+constexpr int kRowStatThreads = 128;
+
+__device__ __forceinline__ bool ahead(float v, int i, float w, int j) { return v > w || (v == w && i > j); }
+
+__device__ __forceinline__ void warp_top5(float (&tv)[5], int (&ti)[5], float (&ov)[5], int (&oi)[5], int lane) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        float bv = tv[0];
+        int bi = ti[0], bl = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float v = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int i = __shfl_xor_sync(0xffffffffu, bi, o);
+            const int l = __shfl_xor_sync(0xffffffffu, bl, o);
+            if (ahead(v, i, bv, bi) || (v == bv && i == bi && l < bl)) { bv = v; bi = i; bl = l; }
+        }
+        ov[k] = bv; oi[k] = bi;
+        if (lane == bl) {                      // the winner's list moves up by one
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { tv[q] = tv[q + 1]; ti[q] = ti[q + 1]; }
+            tv[4] = -INFINITY; ti[4] = -1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kRowStatThreads)
 row_stats_kernel(const float* __restrict__ prob, const float* __restrict__ y, int B, int L, float thr,
                  int* __restrict__ rows /* [B][8]: xor, tp, npred, ntarg, hit1, hit3, hit5, - */) {
-    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (b >= B) return;
+    constexpr int kWarps = kRowStatThreads / 32;
+    __shared__ float s_v[kWarps][5];
+    __shared__ int s_i[kWarps][5];
+    __shared__ int s_cnt[kWarps][4];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* __restrict__ pr = prob + (size_t)b * L;
     const float* __restrict__ yr = y + (size_t)b * L;
     int nx = 0, tp = 0, np = 0, nt = 0;
-    for (int l = lane; l < L; l += 32) {
-        const bool p = pr[l] >= thr, t = yr[l] != 0.0f;
+    float tv[5];
+    int ti[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { tv[k] = -INFINITY; ti[k] = -1; }
+#pragma unroll 4
+    for (int l = tid; l < L; l += kRowStatThreads) {
+        const float v = pr[l];
+        const bool p = v >= thr, t = yr[l] != 0.0f;
         nx += (p != t); tp += (p && t); np += p; nt += t;
+        if (v >= tv[4]) {                       // a thread walks its labels upwards: an equal score goes AHEAD of the kept one
+            tv[4] = v; ti[4] = l;
+            bool moving = true;                 // only the new element moves; kept equal scores stay in their order
+#pragma unroll
+            for (int k = 4; k > 0; --k) {
+                moving = moving && tv[k] >= tv[k - 1];
+                if (moving) {
+                    const float fv = tv[k]; tv[k] = tv[k - 1]; tv[k - 1] = fv;
+                    const int fi = ti[k]; ti[k] = ti[k - 1]; ti[k - 1] = fi;
+                }
+            }
+        }
     }
     nx = warp_sum(nx); tp = warp_sum(tp); np = warp_sum(np); nt = warp_sum(nt);
-    // top-5 by score, ties broken towards the HIGHER index (np.argsort ascending, then reversed: evals.py:37)
-    int hits[3] = {0, 0, 0};
-    float last_v = INFINITY;
-    int last_i = L;     // everything strictly "before" (last_v, last_i) in the descending order is already taken
-    const int kmax = L < 5 ? L : 5;
-    for (int k = 0; k < kmax; ++k) {
-        float bv = -INFINITY;
-        int bi = -1;
-        for (int l = lane; l < L; l += 32) {
-            const float v = pr[l];
-            const bool avail = (v < last_v) || (v == last_v && l < last_i);
-            if (avail && (v > bv || (v == bv && l > bi))) { bv = v; bi = l; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi > bi)) { bv = ov; bi = oi; }
-        }
-        last_v = bv; last_i = bi;
-        const int rel = (bi >= 0 && yr[bi] != 0.0f) ? 1 : 0;
-        if (k < 1) hits[0] += rel;
-        if (k < 3) hits[1] += rel;
-        hits[2] += rel;
-    }
+    float wv[5];
+    int wi[5];
+    warp_top5(tv, ti, wv, wi, lane);
     if (lane == 0) {
+        s_cnt[warp][0] = nx; s_cnt[warp][1] = tp; s_cnt[warp][2] = np; s_cnt[warp][3] = nt;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { s_v[warp][k] = wv[k]; s_i[warp][k] = wi[k]; }
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    // lane w < kWarps holds warp w's (already ordered) list
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        tv[k] = lane < kWarps ? s_v[lane][k] : -INFINITY;
+        ti[k] = lane < kWarps ? s_i[lane][k] : -1;
+    }
+    warp_top5(tv, ti, wv, wi, lane);
+    if (lane == 0) {
+        int hits[3] = {0, 0, 0};
+        const int kmax = L < 5 ? L : 5;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            if (k < kmax) {
+                const int rel = (wi[k] >= 0 && yr[wi[k]] != 0.0f) ? 1 : 0;
+                if (k < 1) hits[0] += rel;
+                if (k < 3) hits[1] += rel;
+                hits[2] += rel;
+            }
+        }
+        int c[4] = {0, 0, 0, 0};
+        for (int w = 0; w < kWarps; ++w)
+            for (int q = 0; q < 4; ++q) c[q] += s_cnt[w][q];
         int* r = rows + (size_t)b * 8;
-        r[0] = nx; r[1] = tp; r[2] = np; r[3] = nt; r[4] = hits[0]; r[5] = hits[1]; r[6] = hits[2]; r[7] = 0;
+        r[0] = c[0]; r[1] = c[1]; r[2] = c[2]; r[3] = c[3]; r[4] = hits[0]; r[5] = hits[1]; r[6] = hits[2]; r[7] = 0;
     }
 }
 
@@ -174,7 +228,7 @@ int launch_batch_metrics(const float* prob, const float* y, int B, int L, float 
     if (cudaMemsetAsync(counts, 0, (size_t)3 * L * sizeof(int), stream) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return 2; }
     label_counts_kernel<<<dim3(ceil_div(L, 256), ceil_div(B, 64)), 256, 0, stream>>>(prob, y, B, L, thr, counts);
     if (int rc = check_launch("label_counts_kernel")) return rc;
-    row_stats_kernel<<<ceil_div(B, 8), 256, 0, stream>>>(prob, y, B, L, thr, rows);
+    row_stats_kernel<<<B, kRowStatThreads, 0, stream>>>(prob, y, B, L, thr, rows);
     if (int rc = check_launch("row_stats_kernel")) return rc;
     metrics_finalize_kernel<<<1, 256, 0, stream>>>(counts, rows, B, L, out);
     return check_launch("metrics_finalize_kernel");

@@ -54,6 +54,28 @@ def test_device_metrics_full_size():
         assert abs(got[k].item() - float(want[k])) <= tol * max(abs(float(want[k])), 1.0), (k, got[k].item(), float(want[k]))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,L", [(7, 3), (9, 5), (33, 37), (64, 130), (16, 517), (128, 3993)])
+def test_device_precision_at_k_with_ties(B, L):
+    """Heavily tied scores: the kernel's ranking is 'stable argsort, reversed' (ties towards the higher index), one
+    pass per row with per-thread top-5 lists merged by warps -- every merge level sees ties here."""
+    from mpvae_b200.metrics import batch_metrics
+    rng = np.random.RandomState(B * 1000 + L)
+    p = (np.floor(rng.uniform(size=(B, L)) * 6) / 8).astype(np.float32)
+    p[0, :] = 0.25                                                       # a row of one single value
+    y = (rng.uniform(size=(B, L)) < 0.3).astype(np.float32)
+    got = batch_metrics(torch.from_numpy(p).cuda(), torch.from_numpy(y).cuda(), 0.5)
+    order = np.argsort(p, axis=1, kind="stable")[:, ::-1]
+    for k in (1, 3, 5):
+        kk = min(k, L)
+        hits = np.take_along_axis(y, order[:, :kk], axis=1).astype(np.float64).sum(axis=1)
+        want = float(np.mean(hits / k))
+        assert abs(got[f"p_at_{k}"].item() - want) <= 1e-12, (k, got[f"p_at_{k}"].item(), want)
+    want = ev.batch_metrics(p, y, 0.5)
+    for k in ("ACC", "HA"):
+        assert abs(got[k].item() - float(want[k])) <= 1e-12
+
+
 # ----------------------------------------------------------------------------- threshold sweep (SURVEY 8f-N2)
 CURVES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics_curves.npz")
 CURVE_CASES = ["yeast", "nuswide", "ties", "delicious"]
