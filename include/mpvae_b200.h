@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPVAE_ABI_VERSION 10
+#define MPVAE_ABI_VERSION 11
 
 /* flags */
 #define MPVAE_FLAG_SANITIZE_DEGENERATE 0x1u /* rows with n_pos*n_neg == 0 get zero ranking gradient instead of
@@ -145,6 +145,11 @@ uint64_t mpvae_peer_flag_bytes(void);
  * device pointers, this process being `rank`; `step` as peer_step above, shared with the backward's counter). */
 int mpvae_peer_allreduce(void *const *part, void *const *g_r, void *const *flags, int32_t world, int32_t rank,
                          uint32_t step, uint64_t n, void *cuda_stream);
+/* The same with the optional DEVICE step counter of peer_step_dev (CUDA-graph replay: flag value = step + *step_dev, the
+ * exchange advances *step_dev by one).  g_r[r] may equal part[r] on every rank: the sum then replaces the partials in
+ * place (an element is read and written by its owner rank only).  Table entries must be 16-byte aligned. */
+int mpvae_peer_allreduce_dev(void *const *part, void *const *g_r, void *const *flags, int32_t world, int32_t rank,
+                             uint32_t step, uint32_t *step_dev, uint64_t n, void *cuda_stream);
 /* ... with the in-switch reduction when mc_part / mc_g_r (multicast addresses of the same buffers) are given. */
 int mpvae_peer_allreduce_nvls(void *const *part, void *const *g_r, void *const *flags, void *mc_part, void *mc_g_r,
                               int32_t world, int32_t rank, uint32_t step, uint64_t n, void *cuda_stream);

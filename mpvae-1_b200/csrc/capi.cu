@@ -668,22 +668,32 @@ int mpvae_contract_tn(const float* A, const float* Bm, float* C, int32_t M, int3
 // the handle addresses exactly the buffer (no sub-allocation offsets). ----
 uint64_t mpvae_peer_flag_bytes(void) { return peer_flag_bytes(); }
 
-int mpvae_peer_allreduce(void* const* part, void* const* g_r, void* const* flags, int32_t world, int32_t rank, uint32_t step,
-                         uint64_t n, void* cuda_stream) {
+int mpvae_peer_allreduce_dev(void* const* part, void* const* g_r, void* const* flags, int32_t world, int32_t rank, uint32_t step,
+                             uint32_t* step_dev, uint64_t n, void* cuda_stream) {
     if (!part || !g_r || !flags || world < 2 || world > 8 || rank < 0 || rank >= world || step == 0 || n == 0) {
         set_error("peer_allreduce: bad arguments");
         return 1;
     }
     PeerCtx ctx{};
     ctx.world = world; ctx.rank = rank; ctx.step = step;
+    ctx.step_dev = step_dev; ctx.step_stride = 1;
     ctx.timeout_cycles = peer_timeout_cycles();
     for (int i = 0; i < world; ++i) {
         ctx.part[i] = static_cast<float*>(part[i]);
         ctx.g_r[i] = static_cast<float*>(g_r[i]);
         ctx.flags[i] = static_cast<uint32_t*>(flags[i]);
         if (!ctx.part[i] || !ctx.g_r[i] || !ctx.flags[i]) { set_error("peer_allreduce: NULL table entry %d", i); return 1; }
+        if ((reinterpret_cast<uintptr_t>(ctx.part[i]) | reinterpret_cast<uintptr_t>(ctx.g_r[i])) & 15) {
+            set_error("peer_allreduce: table entry %d is not 16-byte aligned", i);
+            return 1;
+        }
     }
     return launch_peer_reduce(ctx, (size_t)n, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int mpvae_peer_allreduce(void* const* part, void* const* g_r, void* const* flags, int32_t world, int32_t rank, uint32_t step,
+                         uint64_t n, void* cuda_stream) {
+    return mpvae_peer_allreduce_dev(part, g_r, flags, world, rank, step, nullptr, n, cuda_stream);
 }
 
 int mpvae_peer_allreduce_nvls(void* const* part, void* const* g_r, void* const* flags, void* mc_part, void* mc_g_r, int32_t world,

@@ -26,22 +26,21 @@ class _DevMem:
                                          "strides": None}
 
 
-class PeerRing:
+class _PeerBuffers:
+    """Allocation + handle exchange shared by the rings below: `sizes` = {name: bytes}; afterwards `self.ptrs[name][r]`
+    is rank r's buffer as seen from this process."""
+
     MAX_WORLD = 8
 
-    def __init__(self, L: int, Z: int, device, group=None):
+    def _setup(self, sizes, device, group):
         if not (dist.is_available() and dist.is_initialized()):
-            raise RuntimeError("PeerRing needs an initialised torch.distributed process group")
+            raise RuntimeError(f"{type(self).__name__} needs an initialised torch.distributed process group")
         self.group = group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if not 2 <= self.world <= self.MAX_WORLD:
-            raise ValueError(f"PeerRing: world size {self.world} not in [2, {self.MAX_WORLD}]")
+            raise ValueError(f"{type(self).__name__}: world size {self.world} not in [2, {self.MAX_WORLD}]")
         lib = _lib.lib()
-        self.L, self.Z = int(L), int(Z)
         self.device = torch.device(device)
-        # "tiles": per-tile completion counters of the exchange fused into the g_R product (monotonic, zeroed once here)
-        sizes = {"part": self.L * self.Z * 4, "g_r": self.L * self.Z * 4, "flags": int(lib.mpvae_peer_flag_bytes()),
-                 "tiles": _lib.PEER_TILE_BYTES}
         self._local, self._remote, handles = {}, {}, {}
         # Every collective below is entered by EVERY rank whatever happened locally, and the outcome is agreed on
         # collectively: either all ranks own a working ring or all of them raise (no rank is left waiting).
@@ -79,8 +78,96 @@ class PeerRing:
             dist.all_gather_object(verdicts, None if error is None else str(error), group=group)
             if any(v is not None for v in verdicts):
                 self._release()
-                raise RuntimeError("PeerRing: set-up failed on rank(s) " +
+                raise RuntimeError(f"{type(self).__name__}: set-up failed on rank(s) " +
                                    ", ".join(f"{r}: {v}" for r, v in enumerate(verdicts) if v is not None))
+
+    def _release(self):
+        lib = _lib.lib()
+        for ptrs in self._remote.values():
+            for ptr in ptrs:
+                lib.mpvae_peer_close(C.c_void_p(ptr))
+        self._remote = {}
+        for ptr in self._local.values():
+            lib.mpvae_peer_free(C.c_void_p(ptr))
+        self._local = {}
+
+    def check(self):
+        """Raise if a flag wait of this rank has ever timed out (a peer was more than MPVAE_PEER_TIMEOUT_S late): the
+        sums of that step are invalid and the caller should fall back to the NCCL all-reduce.  Synchronises the stream."""
+        lib = _lib.lib()
+        step = C.c_uint32(0)
+        with torch.cuda.device(self.device):
+            stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(lib.mpvae_peer_error(C.c_void_p(self.ptrs["flags"][self.rank]), C.byref(step), stream), "mpvae_peer_error")
+        if step.value:
+            raise RuntimeError(f"{type(self).__name__}: rank {self.rank} gave up waiting for a peer at exchange step {step.value}")
+
+    def enable_graph_replay(self):
+        """Flag values come from a DEVICE counter the exchange kernels advance themselves, so that a captured CUDA graph
+        (which replays identical launch arguments) keeps them increasing.  Call on every rank before capturing; from
+        then on the host hands out the constant base step."""
+        if getattr(self, "step_dev", None) is None:
+            self.step_dev = torch.full((1,), self.step, dtype=torch.int32, device=self.device)
+        return self.step_dev
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        if dist.is_initialized():
+            dist.barrier(group=self.group)      # nobody unmaps while a peer may still be reading
+        self._release()
+
+
+class PeerBucket(_PeerBuffers):
+    """One flat fp32 buffer per rank in peer-mapped memory, summed over the ranks IN PLACE (a range at a time) by the
+    library's exchange kernel: what the data-parallel step keeps its gradient bucket in when it runs without NCCL
+    (train.DataParallelStep(peer_all=True)), which is also what lets the whole step be captured as a CUDA graph on
+    every rank (NCCL collectives cannot be captured on this stack)."""
+
+    def __init__(self, numel: int, device, group=None):
+        lib = _lib.lib()
+        self.numel = int(numel)
+        self._setup({"buf": self.numel * 4, "flags": int(lib.mpvae_peer_flag_bytes())}, device, group)
+        with torch.cuda.device(self.device):
+            self.flat = torch.as_tensor(_DevMem(self._local["buf"], (self.numel,), "<f4"), device=self.device)
+        self.step = 0
+        dist.barrier(group=group)
+
+    def allreduce(self, first: int = 0, n: int = None):
+        """flat[first : first + n] = its sum over the ranks, on every rank (bit-identical); `first` a multiple of 4."""
+        n = self.numel - first if n is None else int(n)
+        if first % 4 or first < 0 or n <= 0 or first + n > self.numel:
+            raise ValueError(f"PeerBucket.allreduce: bad range [{first}, {first + n}) of {self.numel}")
+        lib = _lib.lib()
+        step_dev = getattr(self, "step_dev", None)
+        if step_dev is None:
+            self.step += 1
+            step = self.step
+        else:
+            step = 1
+        table = (C.c_void_p * self.world)(*[p + 4 * first for p in self.ptrs["buf"]])
+        flags = (C.c_void_p * self.world)(*self.ptrs["flags"])
+        with torch.cuda.device(self.device):
+            stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(lib.mpvae_peer_allreduce_dev(table, table, flags, self.world, self.rank, step,
+                                                    C.c_void_p(step_dev.data_ptr()) if step_dev is not None else C.c_void_p(0),
+                                                    n, stream), "mpvae_peer_allreduce_dev")
+        return self.flat
+
+    def _release(self):
+        self.flat = None
+        super()._release()
+
+
+class PeerRing(_PeerBuffers):
+
+    def __init__(self, L: int, Z: int, device, group=None):
+        lib = _lib.lib()
+        self.L, self.Z = int(L), int(Z)
+        # "tiles": per-tile completion counters of the exchange beside / inside the g_R product (monotonic, zeroed once here)
+        sizes = {"part": self.L * self.Z * 4, "g_r": self.L * self.Z * 4, "flags": int(lib.mpvae_peer_flag_bytes()),
+                 "tiles": _lib.PEER_TILE_BYTES}
+        self._setup(sizes, device, group)
+        with torch.cuda.device(self.device):
             self.g_r = torch.as_tensor(_DevMem(self._local["g_r"], (self.L, self.Z), "<f4"), device=self.device)
             self.part = torch.as_tensor(_DevMem(self._local["part"], (self.L, self.Z), "<f4"), device=self.device)
         self.step = 0
@@ -107,25 +194,6 @@ class PeerRing:
                 p.peer_tile_done[r] = self.ptrs["tiles"][r]
         return self.g_r
 
-    def check(self):
-        """Raise if a flag wait of this rank has ever timed out (a peer was more than MPVAE_PEER_TIMEOUT_S late): the
-        sums of that step are invalid and the caller should fall back to the NCCL all-reduce.  Synchronises the stream."""
-        lib = _lib.lib()
-        step = C.c_uint32(0)
-        with torch.cuda.device(self.device):
-            stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-            _lib.check(lib.mpvae_peer_error(C.c_void_p(self.ptrs["flags"][self.rank]), C.byref(step), stream), "mpvae_peer_error")
-        if step.value:
-            raise RuntimeError(f"PeerRing: rank {self.rank} gave up waiting for a peer at exchange step {step.value}")
-
-    def enable_graph_replay(self):
-        """Flag values come from a DEVICE counter the exchange kernels advance themselves, so that a captured CUDA graph
-        (which replays identical launch arguments) keeps them increasing.  Call on every rank before capturing; from
-        then on `fill` hands out the constant base step."""
-        if getattr(self, "step_dev", None) is None:
-            self.step_dev = torch.full((1,), self.step, dtype=torch.int32, device=self.device)
-        return self.step_dev
-
     def allreduce(self, n: int = None):
         """Stand-alone exchange: `self.g_r` (flat, first n floats) = sum over ranks of `self.part`."""
         lib = _lib.lib()
@@ -146,21 +214,8 @@ class PeerRing:
         return self.g_r
 
     def _release(self):
-        lib = _lib.lib()
-        for ptrs in self._remote.values():
-            for ptr in ptrs:
-                lib.mpvae_peer_close(C.c_void_p(ptr))
-        self._remote = {}
         self.g_r = self.part = None
-        for ptr in self._local.values():
-            lib.mpvae_peer_free(C.c_void_p(ptr))
-        self._local = {}
-
-    def close(self):
-        torch.cuda.synchronize(self.device)
-        if dist.is_initialized():
-            dist.barrier(group=self.group)      # nobody unmaps while a peer may still be reading
-        self._release()
+        super()._release()
 
 
 class NvlsRing(PeerRing):

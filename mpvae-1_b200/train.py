@@ -45,21 +45,30 @@ def shard_rows(n_rows: int, rank: int, world: int):
 
 
 class GradBucket:
-    """One flat fp32 buffer holding [g_R || all fp32 parameter gradients]; .grad of every fp32 parameter is a view
-    into it (autograd accumulates in place), so the all-reduce needs no gather / scatter copies."""
+    """One flat fp32 buffer holding [g_R | pad | all fp32 parameter gradients | pad | 8 scalar slots]; .grad of every fp32
+    parameter is a view into it (autograd accumulates in place), so the all-reduce needs no gather / scatter copies.
+    The segments start at multiples of four floats (16-byte accesses of the peer-memory exchange); the scalar slots
+    carry the step's loss terms through the same exchange when the step runs without NCCL.  `alloc(numel)` supplies the
+    storage (peer-mapped memory for `peer_all`), default torch.zeros."""
 
-    def __init__(self, r_shadow: Optional[torch.Tensor], params):
+    N_SCALARS = 8
+
+    def __init__(self, r_shadow: Optional[torch.Tensor], params, alloc: Optional[Callable] = None):
         self.params = [p for p in params if p.requires_grad and p.dtype == torch.float32]
-        sizes = ([r_shadow.numel()] if r_shadow is not None else []) + [p.numel() for p in self.params]
         dev = (r_shadow if r_shadow is not None else self.params[0]).device
-        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
-        off = 0
-        self.r_view = None
-        if r_shadow is not None:
-            self.r_view = self.flat[off:off + r_shadow.numel()].view_as(r_shadow)
-            off += r_shadow.numel()
-        self.r_numel = off
+        self.r_numel = r_shadow.numel() if r_shadow is not None else 0
+        self.mlp_off = -(-self.r_numel // 4) * 4
+        n_mlp = sum(p.numel() for p in self.params)
+        self.grads_end = self.mlp_off + n_mlp
+        self.scal_off = -(-self.grads_end // 4) * 4
+        total = self.scal_off + self.N_SCALARS
+        self.flat = alloc(total) if alloc is not None else torch.zeros(total, dtype=torch.float32, device=dev)
+        assert self.flat.numel() == total and self.flat.dtype == torch.float32
+        self.grads = self.flat[:self.grads_end]             # what the gradient norm is taken over (padding stays zero)
+        self.scalars = self.flat[self.scal_off:]
+        self.r_view = self.flat[:self.r_numel].view_as(r_shadow) if r_shadow is not None else None
         self.views = []
+        off = self.mlp_off
         for p in self.params:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
@@ -77,7 +86,8 @@ class DataParallelStep:
 
     def __init__(self, model: nn.Module, optimizer, scheduler, args, *, clip_norm: float = 100.0,
                  skip_nonfinite: bool = False, group=None, loss_fn: Optional[Callable] = None,
-                 regulariser: Optional[Callable] = None, distributed: bool = True, peer_g_r: bool = False):
+                 regulariser: Optional[Callable] = None, distributed: bool = True, peer_g_r: bool = False,
+                 peer_all: bool = False):
         self.model, self.optimizer, self.scheduler = model, optimizer, scheduler
         self.args = copy.copy(args)
         self.clip_norm = clip_norm                 # 100 in train.py:126, 10 in fairsoft_train.py:141
@@ -107,7 +117,22 @@ class DataParallelStep:
             # lives in the bucket, and is cast back to fp64 for the optimizer after the all-reduce
             self.r_shadow = self.r_param.detach().float().requires_grad_(True)
         others = [p for n, p in model.named_parameters() if p is not self.r_param]
-        self.bucket = GradBucket(self.r_shadow, others)
+        # peer_all=True: the whole bucket lives in peer-mapped memory and is summed over the ranks by the library's
+        # exchange kernel (peer.PeerBucket) -- no NCCL call anywhere in the step, which is what GraphedTrainStep needs
+        # at world_size > 1.  Set-up is collective: if it fails on any rank, every rank keeps the NCCL path.
+        self.pbucket = None
+        alloc = None
+        if peer_all and self.world > 1 and next(model.parameters()).is_cuda:
+            def alloc(numel):
+                from .peer import PeerBucket
+                try:
+                    self.pbucket = PeerBucket(numel, next(model.parameters()).device, self.group)
+                except RuntimeError as e:
+                    if self.rank == 0:
+                        print(f"[mpvae_b200] peer_all unavailable ({e}); NCCL all-reduce")
+                    return torch.zeros(numel, dtype=torch.float32, device=next(model.parameters()).device)
+                return self.pbucket.flat
+        self.bucket = GradBucket(self.r_shadow, others, alloc)
         self._pending = []
         self._r_issued = False          # the g_R segment's all-reduce of this step has been issued
         # CUDA-graph capture (GraphedTrainStep): every collective is issued from the main thread, on the capture stream,
@@ -147,7 +172,7 @@ class DataParallelStep:
 
     def _reduce_r_early(self, _):
         """Fires as soon as the probit backward has written g_R: overlap its all-reduce with the MLP backward."""
-        if self._ring_step or self._r_issued or (self._inline_collectives and _ is not None):
+        if self._ring_step or self._r_issued or self.pbucket is not None or (self._inline_collectives and _ is not None):
             return                                # g_R arrived already summed (peer ring) / already on its way / inline mode
         self._r_issued = True
         seg = self.bucket.flat[:self.bucket.r_numel]
@@ -162,9 +187,17 @@ class DataParallelStep:
         then the MLP gradients.  A rank whose sequence depended on its shard would hang NCCL."""
         if self.world == 1:
             return
+        if self.pbucket is not None:
+            # one in-place exchange over NVLink peer memory: MLP gradients + the scalar slots, and g_R too unless the
+            # probit backward already delivered it summed
+            first = self.bucket.mlp_off if (self._ring_step or not self.bucket.r_numel) else 0
+            self.pbucket.allreduce(first)
+            if divide:
+                self.bucket.grads.div_(self.world)
+            return
         if self.bucket.r_numel and not self._ring_step:
             self._reduce_r_early(None)            # no-op when the hook already issued it
-        seg = self.bucket.flat[self.bucket.r_numel:]
+        seg = self.bucket.flat[self.bucket.mlp_off:self.bucket.grads_end]
         if seg.numel():
             if self._inline_collectives:
                 dist.all_reduce(seg, group=self.group)
@@ -175,7 +208,7 @@ class DataParallelStep:
         self._pending = []
         self._r_issued = False
         if divide:
-            self.bucket.flat.div_(self.world)
+            self.bucket.grads.div_(self.world)
 
     # -- the step -------------------------------------------------------------------------------------------
     def step(self, input_label: torch.Tensor, input_feat: torch.Tensor, noise: Optional[torch.Tensor] = None,
@@ -222,7 +255,10 @@ class DataParallelStep:
             empty = input_label.new_zeros((0, input_label.shape[1]), dtype=torch.float32)
             out = (zero,) * 6 + (empty, empty)
         from .optim import FusedAdam
-        fused = isinstance(self.optimizer, FusedAdam) and not self.skip_nonfinite and total.is_cuda
+        fused = isinstance(self.optimizer, FusedAdam) and not self.skip_nonfinite and self.bucket.flat.is_cuda
+        if self.pbucket is not None and hi > lo:
+            # the step's loss terms ride in the bucket's scalar slots through the same exchange (row-weighted sums)
+            self.bucket.scalars[:6].copy_(torch.stack([t.detach().float() for t in out[:6]]) * ((hi - lo) / max(n_rows, 1)))
         self._finish_reduce(divide=not fused)
         stepped = True
         self._shadow_fresh = False
@@ -231,7 +267,7 @@ class DataParallelStep:
             # folded into the gradient multiplier, g_R is consumed as fp32, the fp32 shadow of R is refreshed in place
             f32 = {self.r_param: self.bucket.r_view} if self.r_param is not None else None
             shadows = {self.r_param: self.r_shadow} if self.r_param is not None else None
-            self.optimizer.step(max_norm=self.clip_norm, grad_scale=1.0 / self.world, flat_grad=self.bucket.flat,
+            self.optimizer.step(max_norm=self.clip_norm, grad_scale=1.0 / self.world, flat_grad=self.bucket.grads,
                                 f32_grads=f32, f32_shadows=shadows)
             grad_norm = self.optimizer.grad_norm
             self._shadow_fresh = self.r_param is not None and self.r_param in self.optimizer.shadowed
@@ -250,7 +286,9 @@ class DataParallelStep:
                     self.scheduler.step()
         self.step_no += 1
         scal = [t.detach() for t in out[:6]]
-        if self.world > 1:
+        if self.pbucket is not None:
+            scal = list(self.bucket.scalars[:6].clone().unbind(0))
+        elif self.world > 1:
             packed = torch.stack([t.float() for t in scal]) * ((hi - lo) / max(n_rows, 1))
             dist.all_reduce(packed, group=self.group)
             scal = list(packed.unbind(0))
@@ -292,15 +330,15 @@ class GraphedTrainStep:
     def __init__(self, stepper: DataParallelStep, warmup: int = 3):
         if stepper.skip_nonfinite:
             raise ValueError("GraphedTrainStep cannot skip non-finite steps (host decision); use DataParallelStep")
-        if stepper.world > 1:
+        if stepper.world > 1 and stepper.pbucket is None:
             # Capturing NCCL all-reduces hangs on this stack (torch 2.11 / NCCL 2.28.9, 2 x B200): in round 1 with the
             # early all-reduce issued from the autograd hook thread, and again in round 2 with every collective issued
-            # inline from the capturing thread on the capture stream (DataParallelStep._inline_collectives; 10 min
-            # until the test's timeout, profiles/r02_graph_multi_gpu.md).  The library side is ready for an NCCL-free
-            # graph step -- the peer-memory exchange takes its flag values from a device counter
-            # (PeerRing.enable_graph_replay, mpvae_probit_params.peer_step_dev) -- but the MLP gradients still travel
-            # by NCCL, so the graph path stays single-process.
-            raise NotImplementedError("GraphedTrainStep is single-process only; use DataParallelStep under torchrun")
+            # inline from the capturing thread on the capture stream (10 min until the test's timeout,
+            # profiles/r02_graph_multi_gpu.md).  So under N ranks the graph step needs the NCCL-free exchange:
+            # DataParallelStep(..., peer_all=True) keeps the gradient bucket in peer-mapped memory and sums it with the
+            # library's own kernel, whose flag values come from a device counter during replay.
+            raise NotImplementedError("GraphedTrainStep under torch.distributed needs DataParallelStep(peer_all=True) "
+                                      "(NCCL collectives cannot be captured on this stack)")
         self.stepper = stepper
         self.warmup = warmup
         self.graphs = {}
@@ -364,10 +402,12 @@ class GraphedTrainStep:
     def _capture(self, y, x):
         static_y, static_x = y.clone(), x.clone()
         st = self.stepper
-        if st.world > 1 and st._want_ring:
-            ring = st._peer_ring(y.shape[0])
-            if ring is not None:
-                ring.enable_graph_replay()
+        if st.world > 1:
+            st.pbucket.enable_graph_replay()
+            if st._want_ring:
+                ring = st._peer_ring(y.shape[0])
+                if ring is not None:
+                    ring.enable_graph_replay()
         snap = self._snapshot()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
