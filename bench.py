@@ -312,6 +312,7 @@ def run_b200(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MPVAE_PEER_TIMEOUT_S", "30")     # a rank that never arrives ends the bench, it does not hang it
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
@@ -677,14 +678,40 @@ def run_b200(a):
                  "what": "zero_grad, VAE fwd (large layers on this library's tcgen05 engine), probit ELBO fwd+bwd (this library), "
                          "MLP bwd, grad all-reduce, clip_grad_norm_(100) + Adam(wd=1e-5) (mpvae_b200.optim.FusedAdam), "
                          "StepLR; per-step host metrics excluded"}
+        from mpvae_b200.train import GraphedTrainStep
+        if world > 1:
+            # the NCCL-free step: g_R summed beside its product, the rest of the gradient bucket (and the loss terms) in
+            # place over NVLink peer memory by the library's exchange kernel -- and, because no NCCL call is left, the
+            # whole N-rank step as a CUDA graph.  Set-up is collective; a failure on any rank is reported, not fatal.
+            del stepper, opt, vae
+            try:
+                np.random.seed(4)
+                torch.manual_seed(0)
+                vae = M.VAE(margs).to(dev)
+                opt = FusedAdam(vae.parameters(), lr=torch.tensor(1e-3, device=dev), weight_decay=1e-5)
+                sched = torch.optim.lr_scheduler.StepLR(opt, 1000, 0.5)
+                stepper = DataParallelStep(vae, opt, sched, margs, clip_norm=100.0, peer_g_r=True, peer_all=True)
+                if stepper.pbucket is None:
+                    raise RuntimeError("peer-mapped gradient bucket unavailable")
+                p_ms, p_wall, out_p = time_steps(stepper.step)
+                train["nccl_free"] = {"steps_per_s": 1e3 / p_ms, "ms_per_step": p_ms, "wall_ms_per_step": p_wall,
+                                      "loss": float(out_p.total_loss.detach()),
+                                      "what": "DataParallelStep(peer_g_r=True, peer_all=True): no NCCL call in the step"}
+            except Exception as exc:   # noqa: BLE001
+                train["nccl_free"] = {"error": repr(exc)[:200]}
+                stepper = None
         try:   # the same step captured once as a CUDA graph and replayed (mpvae_b200.train.GraphedTrainStep)
-            if world > 1:
-                raise NotImplementedError("graph capture is single-process only")
-            from mpvae_b200.train import GraphedTrainStep
+            if stepper is None:
+                raise RuntimeError("no stepper to capture")
             graphed = GraphedTrainStep(stepper)
             g_ms, g_wall, out_g = time_steps(graphed.step)
             train["cuda_graph"] = {"steps_per_s": 1e3 / g_ms, "ms_per_step": g_ms, "wall_ms_per_step": g_wall,
                                    "loss": float(out_g.total_loss.detach())}
+            if world > 1:
+                train["cuda_graph"]["what"] = "the NCCL-free step captured on every rank"
+                for r_ in (stepper.ring, stepper.pbucket):
+                    if r_ is not None:
+                        r_.check()
         except Exception as exc:   # noqa: BLE001 - the graph leg is informative, never fatal for the bench line
             train["cuda_graph"] = {"error": repr(exc)[:200]}
         del vae, opt, stepper

@@ -126,7 +126,8 @@ typedef struct mpvae_probit_params {
        so that a captured CUDA graph (which replays the same peer_step) keeps the flag values increasing; NULL = unused */
     uint32_t *peer_step_dev;
     /* optional: every rank's per-tile completion counters (mpvae_peer_alloc'ed, MPVAE_PEER_TILE_BYTES each, zeroed once,
-       never reset: the library keeps the epoch).  With them the g_R product of the dense regime publishes every finished
+       never reset: the library keeps the exchange's epoch in the buffer's last word, on the device, so captured CUDA graphs
+       replay correctly).  With them the g_R product of the dense regime publishes every finished
        256 x 256 tile there and leaves a few SMs idle; an exchange kernel on those SMs (csrc/peer_reduce.cu, a side
        stream forked from and joined to the caller's) sums finished 256-row slabs of g_R over the ranks through NVLink
        while the tensor pipe computes later tiles.  MPVAE_FLAG_FUSED_EXCHANGE moves the sums onto the product kernel's

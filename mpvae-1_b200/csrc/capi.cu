@@ -222,16 +222,12 @@ SideStream* side_stream() {
     return &ss[dev];
 }
 
-// Exchanges that go through the per-tile counters (beside / inside the product) count themselves per counter buffer: the
-// counters are monotonic and a tile is complete when its counter has reached 32 x this epoch.  Every rank takes the
-// same decisions for the same calls, so the epochs agree across the ranks; exchanges that do not touch the counters
-// (the stand-alone reduce, mpvae_peer_allreduce) do not advance them.
-std::mutex g_epoch_mu;
-std::map<const void*, uint32_t> g_tile_epoch;
-uint32_t next_tile_epoch(const void* counters) {
-    std::lock_guard<std::mutex> lk(g_epoch_mu);
-    return ++g_tile_epoch[counters];
-}
+// Exchanges that go through the per-tile counters (beside / inside the product): the counters are monotonic and a tile is
+// complete when its counter has reached 32 x the epoch of the exchange.  The epoch lives on the DEVICE, in the last word
+// of the rank's own counter buffer (zeroed at allocation): the kernels read 1 + that word, the last kernel of the exchange
+// advances it -- so a captured CUDA graph replays correctly, and exchanges that do not touch the counters (the
+// stand-alone reduce, mpvae_peer_allreduce) leave it alone.  Every rank makes the same calls, so the epochs agree.
+constexpr size_t kTileEpochWord = MPVAE_PEER_TILE_BYTES / sizeof(uint32_t) - 1;
 
 long long peer_timeout_cycles() {
     static long long v = 0;
@@ -517,12 +513,11 @@ int mpvae_probit_backward(const mpvae_probit_params* p_in, void* cuda_stream) {
             // data-parallel: the finished tiles are summed over the ranks inside the product kernel (fused_rows.cuh)
             FusePeer fp{};
             const bool tiles_ok = peer && p->peer_tile_done[p->peer_rank] != nullptr && !(p->peer_mc_part && p->peer_mc_g_r) &&
-                                  (size_t)ceil_div(p->L, 256) * ceil_div(p->Z, 256) * sizeof(uint32_t) <= MPVAE_PEER_TILE_BYTES;
+                                  (size_t)ceil_div(p->L, 256) * ceil_div(p->Z, 256) < kTileEpochWord;
             // 3: on the product kernel's own math warps (opt-in); 4: slab by slab on a few reserved SMs beside the product
             // (default); 0: after the product
             int xmode = 0;
-            if (p->peer_step_dev != nullptr) xmode = 0;          // CUDA-graph replay: the epoch below would be baked in
-            else if (tiles_ok && (p->flags & MPVAE_FLAG_FUSED_EXCHANGE)) xmode = 3;
+            if (tiles_ok && (p->flags & MPVAE_FLAG_FUSED_EXCHANGE)) xmode = 3;
             else if (tiles_ok && !(p->flags & MPVAE_FLAG_SERIAL_EXCHANGE) && ceil_div(p->Z, 256) <= 32 && p->L >= 512 &&
                      (long long)p->S * p->B >= 8192) xmode = 4;   // shorter products cannot hide the exchange (measured)
             const bool fused_x = xmode != 0;
@@ -537,9 +532,10 @@ int mpvae_probit_backward(const mpvae_probit_params* p_in, void* cuda_stream) {
             }
             PeerCtx sctx = pctx;                                 // the slab exchange: flag value = the tile epoch
             if (fused_x) {
-                const uint32_t epoch = next_tile_epoch(p->peer_tile_done[p->peer_rank]);
-                sctx.step = epoch; sctx.step_dev = nullptr;
-                fp.world = pctx.world; fp.rank = pctx.rank; fp.step = epoch; fp.step_dev = nullptr;
+                uint32_t* epoch_word = static_cast<uint32_t*>(p->peer_tile_done[p->peer_rank]) + kTileEpochWord;
+                sctx.step = 1; sctx.step_dev = epoch_word; sctx.step_stride = 0;
+                pctx.epoch_dev = epoch_word;                     // advanced by the closing flag phase below
+                fp.world = pctx.world; fp.rank = pctx.rank; fp.step = 1; fp.step_dev = epoch_word;
                 fp.timeout_cycles = pctx.timeout_cycles;
                 fp.err = pctx.flags[pctx.rank] + peer_error_word();
                 for (int i = 0; i < pctx.world; ++i) {

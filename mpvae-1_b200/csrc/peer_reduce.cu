@@ -68,6 +68,7 @@ __global__ void peer_wait_kernel(PeerCtx ctx, int phase) {
     if (p < ctx.world) wait_flag(ctx, ctx.flags[ctx.rank] + phase * 8 + p, step_of(ctx));
     __syncthreads();
     if (p == 0 && ctx.step_dev) *ctx.step_dev += ctx.step_stride;
+    if (p == 0 && ctx.epoch_dev) *ctx.epoch_dev += 1u;
 }
 
 template <int W, int U>   // world size; float4 groups per thread and iteration (all loads are issued before the adds)
@@ -207,7 +208,8 @@ peer_reduce_nvls_kernel(PeerCtx ctx, const float* __restrict__ mc_part, float* _
 // scheduling; if the hardware ran them one after the other the result would be the same, only later.
 struct SlabArgs {
     const unsigned int* done[8];   // every rank's per-tile counters
-    unsigned int step;             // the tile epoch: a tile is complete when its counter has reached 32 * step
+    unsigned int step;             // the tile epoch (step + *step_dev): a tile is complete when its counter has reached 32 x epoch
+    const unsigned int* step_dev;
     int tiles_n, n_slabs;
     size_t slab_elems;             // 256 * Z floats: a multiple of 4, slabs are 16-byte aligned
 };
@@ -218,7 +220,8 @@ peer_reduce_slabs_kernel(PeerCtx ctx, SlabArgs sa) {
     // 16 loads of 16 bytes in flight per thread whatever the world size (an SM moves what it has in flight per NVLink
     // round trip: 512 threads x 256 B = 128 KiB per ~2.5 us = ~50 GB/s per SM)
     constexpr int U = (16 / W) < 1 ? 1 : (16 / W);
-    const unsigned int target = 32u * sa.step;
+    const unsigned int epoch = sa.step + (sa.step_dev ? *sa.step_dev : 0u);
+    const unsigned int target = 32u * epoch;
     const size_t n4 = sa.slab_elems / 4, per = (n4 + W - 1) / W;
     const size_t lo = (size_t)ctx.rank * per, hi = min(n4, lo + per);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -238,7 +241,7 @@ peer_reduce_slabs_kernel(PeerCtx ctx, SlabArgs sa) {
                 ok = __all_sync(0xffffffffu, ok);
                 if (!ok) {
                     __nanosleep(500);
-                    if (clock64() - t0 > ctx.timeout_cycles) { if (threadIdx.x == 0) atomicMax(ctx.flags[ctx.rank] + kErrWord, sa.step); break; }
+                    if (clock64() - t0 > ctx.timeout_cycles) { if (threadIdx.x == 0) atomicMax(ctx.flags[ctx.rank] + kErrWord, epoch); break; }
                 }
             }
             asm volatile("fence.acq_rel.sys;" ::: "memory");
@@ -276,7 +279,7 @@ int launch_peer_reduce_slabs(const PeerCtx& ctx, void* const* tile_done, int til
     if (tiles_n > 32 || (slab_elems & 3) != 0) { set_error("peer slabs: tiles_n %d / slab of %zu floats unsupported", tiles_n, slab_elems); return 1; }
     SlabArgs sa{};
     for (int i = 0; i < ctx.world; ++i) sa.done[i] = static_cast<const unsigned int*>(tile_done[i]);
-    sa.step = ctx.step;
+    sa.step = ctx.step; sa.step_dev = ctx.step_dev;
     sa.tiles_n = tiles_n; sa.n_slabs = n_slabs; sa.slab_elems = slab_elems;
     // 160 KiB of (unused) dynamic shared memory per CTA: one CTA per SM, so `ctas` CTAs take exactly `ctas` SMs
     const size_t smem = 160 * 1024;

@@ -103,6 +103,7 @@ struct PeerCtx {
     uint32_t step;             // flag value of this exchange (strictly increasing, the same on every rank)
     uint32_t* step_dev;        // optional device counter added to `step` and advanced by step_stride after the exchange
     uint32_t step_stride;      //   (a captured CUDA graph replays the same launch arguments)
+    uint32_t* epoch_dev;       // optional: the tile-counter epoch of this rank, advanced by one after the exchange
     long long timeout_cycles;  // a flag wait gives up after this many SM cycles and records the failure (peer_error_word)
     float* part[8];     // every rank's partial g_R (the rank's own product output)
     float* g_r[8];      // every rank's final g_R
