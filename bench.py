@@ -480,7 +480,6 @@ def run_b200(a):
         import cProfile
         import io
         import pstats
-        import time
         torch.cuda.synchronize()
         prof = cProfile.Profile()
         t0 = time.perf_counter()
@@ -683,7 +682,7 @@ def run_b200(a):
             # the NCCL-free step: g_R summed beside its product, the rest of the gradient bucket (and the loss terms) in
             # place over NVLink peer memory by the library's exchange kernel -- and, because no NCCL call is left, the
             # whole N-rank step as a CUDA graph.  Set-up is collective; a failure on any rank is reported, not fatal.
-            del stepper, opt, vae
+            vae = opt = stepper = None
             try:
                 np.random.seed(4)
                 torch.manual_seed(0)
@@ -714,7 +713,7 @@ def run_b200(a):
                         r_.check()
         except Exception as exc:   # noqa: BLE001 - the graph leg is informative, never fatal for the bench line
             train["cuda_graph"] = {"error": repr(exc)[:200]}
-        del vae, opt, stepper
+        vae = opt = stepper = None
 
     if rank != 0:
         if world > 1:
