@@ -537,6 +537,17 @@ def run_b200(a):
     _lib.profile(False)
     kernels = {k: v[0] / v[1] for k, v in prof.items()}
     barrier()
+    kernels_by_rank = None
+    if world > 1:
+        # every rank's per-kernel times: the spread over the ranks of a kernel that WAITS for the others (the exchange, and
+        # the g_R product when the exchange runs beside it) is the skew, the spread of the others is rank-to-rank variation
+        gathered = [None] * world
+        dist.all_gather_object(gathered, kernels)
+        keys = list(kernels)
+        kernels_by_rank = {k: {"min": min(g.get(k, float("nan")) for g in gathered),
+                               "max": max(g.get(k, float("nan")) for g in gathered),
+                               "ranks": [round(g.get(k, float("nan")), 4) for g in gathered]} for k in keys}
+        kernels_by_rank["sum of the kernels"] = {"ranks": [round(sum(g.values()), 4) for g in gathered]}
     if rank == 0:
         f_max = peaks["sm_max_mhz"] * 1e6
         nt_key = next((k for k in kernels if k.startswith("product nt")), None)
@@ -756,7 +767,7 @@ def run_b200(a):
                 "ms_per_step": total_e2e / a.steps},
         "gpu_launches": int(launches),
         "loss_steps_per_s": a.steps / (total_ms * 1e-3),
-        "kernel_ms": kernels,
+        "kernel_ms": kernels, "kernel_ms_by_rank": kernels_by_rank,
         "train_step": train,
         "roofline": roof,
     }

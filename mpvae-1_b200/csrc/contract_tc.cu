@@ -741,15 +741,17 @@ int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, float* C, int Mc, in
 bool tc_available() { return true; }
 
 int exchange_sms(int world) {
-    // measured on 8 B200s (eurlex weak scaling, loss step): 8 SMs 1.85 ms, 16 SMs 1.73 ms, 24 SMs 1.76 ms, 32 SMs 1.80 ms
-    // (the exchange behind the product: 1.95 ms); on 2 GPUs, where each rank moves less, 8 SMs are enough
+    // measured on 8 B200s (eurlex weak scaling, loss step; profiles/r02_fused_exchange.md): 8 SMs 1.85 ms, 16 SMs 1.73 - 1.83 ms,
+    // 20 SMs 1.73 ms, 24 SMs 1.76 ms, 32 SMs 1.80 ms (exchange behind the product: 1.95 ms).  20 SMs leave 64 CTA pairs:
+    // the 256 tiles of the eurlex g_R are then exactly four waves, no K-sliced tail.  On 2 GPUs, where each rank moves
+    // less, 8 SMs are enough.
     static int forced = -1;
     if (forced < 0) {
         const char* e = getenv("MPVAE_EXCHANGE_SMS");
         forced = e ? atoi(e) : 0;
         if (forced != 0) forced = (forced < 2 ? 2 : forced > 64 ? 64 : forced) & ~1;
     }
-    return forced != 0 ? forced : (world > 2 ? 16 : 8);
+    return forced != 0 ? forced : (world > 2 ? 20 : 8);
 }
 
 // [absmax slots] [A planes] [B planes] [tail-wave scratch]
