@@ -11,6 +11,10 @@ all-reduce over NVLink; the g_R segment is launched from an autograd hook as soo
 produced it, so it overlaps the MLP backward.  Noise is Philox keyed by the GLOBAL row index, which makes the
 result independent of the world size (an external (S, B_global, Z) noise tensor is sliced instead).
 
+`peer_all=True` replaces every NCCL call of the step by the library's own exchange over NVLink peer memory (the bucket
+is allocated there and summed in place; the loss terms ride in its scalar slots), which is what lets GraphedTrainStep
+capture the step on every rank.
+
 The reference has no distributed code at all; with world_size == 1 this object is exactly
 its single-GPU step.
 """
@@ -102,7 +106,6 @@ class DataParallelStep:
         # rank-specific stream; call it AFTER the model has been built.  (Those draws then still depend on the world
         # size: that is inherent to sharding torch's generator and is a documented limitation.)
         self._rng_decorrelated = False
-        self._inline_collectives = False
         self._library_loss = loss_fn is None
         if loss_fn is None:
             from .mpvae import compute_loss as loss_fn
@@ -135,8 +138,6 @@ class DataParallelStep:
         self.bucket = GradBucket(self.r_shadow, others, alloc)
         self._pending = []
         self._r_issued = False          # the g_R segment's all-reduce of this step has been issued
-        # CUDA-graph capture (GraphedTrainStep): every collective is issued from the main thread, on the capture stream,
-        # synchronously -- an all-reduce launched from the autograd hook thread hung the capture at 2 ranks
         # peer_g_r=True: g_R is summed over the ranks inside the probit backward, over NVLink peer memory (peer.py),
         # instead of the NCCL all-reduce of that bucket segment.  Off by default: measured on 2 and 4 B200 the
         # exchange itself is 5-15 % faster than NCCL's (both move the same bytes over NVLink), but inside the
@@ -172,14 +173,11 @@ class DataParallelStep:
 
     def _reduce_r_early(self, _):
         """Fires as soon as the probit backward has written g_R: overlap its all-reduce with the MLP backward."""
-        if self._ring_step or self._r_issued or self.pbucket is not None or (self._inline_collectives and _ is not None):
-            return                                # g_R arrived already summed (peer ring) / already on its way / inline mode
+        if self._ring_step or self._r_issued or self.pbucket is not None:
+            return                                # g_R arrived already summed (peer ring) / already on its way / peer bucket
         self._r_issued = True
         seg = self.bucket.flat[:self.bucket.r_numel]
-        if self._inline_collectives:
-            dist.all_reduce(seg, group=self.group)
-        else:
-            self._pending.append(dist.all_reduce(seg, group=self.group, async_op=True))
+        self._pending.append(dist.all_reduce(seg, group=self.group, async_op=True))
 
     def _finish_reduce(self, divide: bool = True):
         """Every rank issues the SAME collectives in the SAME order whatever its local data was: first the g_R segment
@@ -199,10 +197,7 @@ class DataParallelStep:
             self._reduce_r_early(None)            # no-op when the hook already issued it
         seg = self.bucket.flat[self.bucket.mlp_off:self.bucket.grads_end]
         if seg.numel():
-            if self._inline_collectives:
-                dist.all_reduce(seg, group=self.group)
-            else:
-                self._pending.append(dist.all_reduce(seg, group=self.group, async_op=True))
+            self._pending.append(dist.all_reduce(seg, group=self.group, async_op=True))
         for w in self._pending:
             w.wait()
         self._pending = []
