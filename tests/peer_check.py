@@ -22,7 +22,10 @@ def main():
     dev = torch.device("cuda", torch.cuda.current_device())
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for (L, Z, B, S) in ((983, 983, 128, 10), (3993, 3993, 512, 10)):
+    # the exchange runs BESIDE the g_R product from S * B >= 8192 rows per rank (all full slabs published; 7 of 9 slabs + a
+    # K-sliced tail; ragged Z), behind it below that and when every tile is K-sliced (1000 x 700: twelve tiles)
+    for (L, Z, B, S) in ((983, 983, 128, 10), (3993, 3993, 512, 10), (3993, 3993, 1024, 10), (2304, 2100, 1024, 8),
+                         (1000, 700, 1024, 10)):
         inp = synth.loss_inputs(L, Z, B * world, S, seed=11, with_noise=False, label_rate=20.0 / L)
         rows = slice(rank * B, (rank + 1) * B)
         t = {k: torch.from_numpy(v if k == "r_sqrt_sigma" else v[rows]).to(dev) for k, v in inp.items()}
@@ -32,7 +35,8 @@ def main():
         def run(use_ring, step):
             # PEER_CHECK_FUSED=1: the sum runs tile by tile inside the g_R product kernel (MPVAE_FLAG_FUSED_EXCHANGE)
             args = synth.make_args(L, Z, n_train_sample=S, noise_seed=5, noise_offset=step,
-                                   mpvae_flags=0x40 if (use_ring and os.environ.get("PEER_CHECK_FUSED") == "1") else 0)
+                                   mpvae_flags=(0x40 if os.environ.get("PEER_CHECK_FUSED") == "1" else
+                                                0x80 if os.environ.get("PEER_CHECK_SERIAL") == "1" else 0) if use_ring else 0)
             args.dp_global_batch, args.dp_row0 = B * world, rank * B
             args.peer_ring = ring if use_ring else None
             leaves = {k: (v if k in ("y", "r_sqrt_sigma") else v.clone().requires_grad_(True)) for k, v in t.items()}
@@ -97,6 +101,26 @@ def main():
         if rank == 0:
             print(f"L={L}: loss fwd+bwd+exchange per step: peer ring {t_ring:.3f} ms, nccl {t_nccl:.3f} ms")
         ring.close()
+    # the gradient bucket of the NCCL-free step: ranges of one peer-mapped buffer summed in place
+    from mpvae_b200.peer import PeerBucket
+    n = 3_000_011
+    bucket = PeerBucket(n, dev)
+    for first, cnt in ((0, n), (1024, n - 1024), (4, 1001), (n - 7 - (n - 7) % 4, None)):
+        bucket.flat.normal_()
+        want = bucket.flat.clone()
+        lo_, hi_ = first, n if cnt is None else first + cnt
+        seg = want[lo_:hi_].clone(); dist.all_reduce(seg); want[lo_:hi_] = seg
+        torch.cuda.synchronize(); dist.barrier()          # every rank has filled its buffer before anyone pulls
+        got = bucket.allreduce(first, cnt).clone()
+        rel = ((got - want).abs().max() / want.abs().max()).item()
+        gathered = [torch.empty_like(seg) for _ in range(world)]
+        dist.all_gather(gathered, got[lo_:hi_].contiguous())
+        same = all(torch.equal(gathered[0], x) for x in gathered)
+        if rank == 0:
+            print(f"bucket [{lo_}, {hi_}) in place: rel diff vs nccl {rel:.2e}, range identical on all ranks: {same}")
+        ok = ok and rel <= 1e-6 and same
+    bucket.check()
+    bucket.close()
     if rank == 0:
         print("PEER_CHECK", "PASS" if ok else "FAIL")
     dist.barrier()
