@@ -307,7 +307,7 @@ def run_b200(a):
     from mpvae_b200 import _lib, synth
     from mpvae_b200 import mpvae as M
     from mpvae_b200.metrics import batch_metrics_tensor
-    from mpvae_b200.train import shard_rows
+    from mpvae_b200.train import pack_labels, shard_rows, unpack_labels
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -349,8 +349,9 @@ def run_b200(a):
             inp = synth.loss_inputs(L, Z, max(hi - lo, 1), S, seed=seed, label_rate=sh.label_rate, with_noise=False)
             self.host = {k: torch.from_numpy(inp[k][:hi - lo]).pin_memory() for k in ROW_KEYS}
             self.dev = {k: self.host[k].to(dev) for k in ROW_KEYS}
-            # the {0,1} label matrix crosses PCIe as bytes (a quarter of the fp32 size); compute_loss casts it on the device
-            self.host["y"] = torch.from_numpy(inp["y"][:hi - lo]).to(torch.uint8).pin_memory()
+            # the {0,1} label matrix crosses PCIe as bits (1/32 of the fp32 size; packed once, the labels of a data set do
+            # not change); mpvae_b200.train.unpack_labels restores the fp32 matrix on the device
+            self.host["y"] = pack_labels(inp["y"][:hi - lo]).pin_memory()
             self.args = synth.make_args(L, Z, n_train_sample=S, n_test_sample=S, mode=sh.mode, nll_coeff=0.5, c_coeff=10.0,
                                         mpvae_flags=flags, noise_seed=1234, dp_global_batch=rows_global, dp_row0=lo)
 
@@ -386,7 +387,7 @@ def run_b200(a):
         step_no[0] += 1
         t = src
         if t["y"].dtype != torch.float32:
-            t = dict(t, y=t["y"].float())        # the byte labels of the host path: one cast serves the loss and the metrics
+            t = dict(t, y=unpack_labels(t["y"], L))   # the bit-packed labels of the host path: one unpack serves the loss and the metrics
         kw = {} if noise is None else {"noise": noise}
         if infer:
             with torch.no_grad():
@@ -761,7 +762,7 @@ def run_b200(a):
                                 else "NCCL all-reduce of g_R (fp32) per step")},
         "clocks": clocks,
         "e2e": {"value": units / (total_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": bi, "d2h_bytes_per_step": 4 + 64,
-                "how": "mpvae_b200.compute_loss + backward from pinned host buffers (labels as uint8, the rest fp32), H2D "
+                "how": "mpvae_b200.compute_loss + backward from pinned host buffers (labels as bits: mpvae_b200.train.pack_labels, the rest fp32), H2D "
                        "double-buffered on a side stream; the loss and the step's eight metrics (train.py:131, computed on "
                        "the device by mpvae_b200.metrics.batch_metrics) copied back to the host every step",
                 "ms_per_step": total_e2e / a.steps},

@@ -439,6 +439,24 @@ class GraphedTrainStep:
         return entry["out"]
 
 
+def pack_labels(y) -> torch.Tensor:
+    """{0,1} label matrix (B, L) -> bits, (B, ceil(L/8)) uint8, label l in bit l % 8 of byte l // 8.  Labels are what the
+    loader keeps on the HOST for the whole run (train.py:106-111 slices them per batch); as bits they cross PCIe at 1/32
+    of the fp32 size and are packed once per data set, not per step."""
+    import numpy as np
+    a = y.cpu().numpy() if torch.is_tensor(y) else np.asarray(y)
+    if not np.isin(a, (0, 1)).all():
+        raise ValueError("pack_labels: the label matrix must hold only 0 and 1")
+    return torch.from_numpy(np.packbits(a.astype(np.uint8), axis=1, bitorder="little"))
+
+
+def unpack_labels(bits: torch.Tensor, n_labels: int) -> torch.Tensor:
+    """Inverse of `pack_labels` on the tensor's device: (B, ceil(L/8)) uint8 -> (B, L) float32."""
+    shifts = torch.arange(8, device=bits.device, dtype=torch.uint8)
+    y = torch.bitwise_and(torch.bitwise_right_shift(bits.unsqueeze(-1), shifts), 1)
+    return y.reshape(bits.shape[0], -1)[:, :n_labels].float()
+
+
 class HostBatchPrefetcher:
     """Double-buffered host -> device staging of a step's inputs (train.py:106-111 does a blocking
     `torch.from_numpy(...).to(device)` per step).  Batches are copied from PINNED host tensors on a side stream into

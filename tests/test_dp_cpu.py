@@ -206,3 +206,20 @@ def test_single_process_step_matches_plain_autograd():
     assert abs(float(out.total_loss) - float(terms[0])) < 1e-5
     for (k, a), (_, b) in zip(model.state_dict().items(), twin.state_dict().items()):
         assert torch.allclose(a.double(), b.double(), rtol=1e-5, atol=1e-7), k
+
+
+def test_label_bits_round_trip():
+    """pack_labels / unpack_labels (the host format of the label matrix in bench.py's e2e leg): lossless for any width."""
+    import numpy as np
+    import pytest
+    import torch
+    from mpvae_b200.train import pack_labels, unpack_labels
+    rng = np.random.RandomState(3)
+    for B, L in ((1, 1), (5, 8), (7, 14), (16, 3993), (3, 81)):
+        y = (rng.uniform(size=(B, L)) < 0.3).astype(np.float32)
+        bits = pack_labels(y)
+        assert bits.dtype == torch.uint8 and tuple(bits.shape) == (B, (L + 7) // 8)
+        back = unpack_labels(bits, L)
+        assert back.dtype == torch.float32 and torch.equal(back, torch.from_numpy(y))
+    with pytest.raises(ValueError):
+        pack_labels(np.array([[0.0, 0.5]]))
