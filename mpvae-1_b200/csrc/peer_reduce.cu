@@ -199,11 +199,11 @@ peer_reduce_nvls_kernel(PeerCtx ctx, const float* __restrict__ mc_part, float* _
 }  // namespace
 
 // ---- the exchange that runs BESIDE the g_R product (capi.cu forks a side stream for it) ----
-// The product (contract_tc.cu, MATH = 4) leaves kExchangeSMs SMs free and publishes every finished 256 x 256 tile in a
-// per-tile counter in peer memory.  This kernel owns those SMs (one 1024-thread CTA each, the shared-memory request keeps
+// The product (contract_tc.cu, MATH = 4) leaves exchange_sms() SMs free and publishes every finished 256 x 256 tile in a
+// per-tile counter in peer memory.  This kernel owns those SMs (one 512-thread CTA each, the shared-memory request keeps
 // them apart): it walks the 256-row slabs of g_R in the order the product finishes them, waits until slab s is complete
 // on EVERY rank, and does for the slab what peer_reduce_bcast_kernel does for the whole matrix (pull this rank's chunk of
-// the slab from all ranks, add in rank order, store to all ranks) -- while the tensor pipes of the other 140 SMs keep
+// the slab from all ranks, add in rank order, store to all ranks) -- while the tensor pipes of the other SMs keep
 // working on later slabs.  The product never waits for this kernel, so the two cannot deadlock whatever the
 // scheduling; if the hardware ran them one after the other the result would be the same, only later.
 struct SlabArgs {

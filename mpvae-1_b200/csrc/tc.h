@@ -57,7 +57,7 @@ int tc_gemm_tn(const void* a_planes, const void* b_planes, float* C, int M, int 
                // peer != nullptr: C is this rank's partial; tiles [0, *exchanged_tiles) are summed over the ranks inside the
                // kernel (into every rank's g_r), the K-sliced tail tiles are left to the caller
                // peer_mode 3: on the kernel's own math warps; 4: the kernel only PUBLISHES finished tiles (per-tile counters in
-               // peer memory) and leaves kExchangeSMs SMs free for the exchange kernel the caller runs beside it
+               // peer memory) and leaves exchange_sms() SMs free for the exchange kernel the caller runs beside it
                const FusePeer* peer = nullptr, int* exchanged_tiles = nullptr, int peer_mode = 3);
 // SMs the g_R product leaves to the exchange kernel running beside it (even; MPVAE_EXCHANGE_SMS overrides: experiments)
 int exchange_sms(int world);
