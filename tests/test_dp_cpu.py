@@ -223,3 +223,40 @@ def test_label_bits_round_trip():
         assert back.dtype == torch.float32 and torch.equal(back, torch.from_numpy(y))
     with pytest.raises(ValueError):
         pack_labels(np.array([[0.0, 0.5]]))
+
+
+def test_grad_bucket_layout():
+    """[g_R | pad | MLP gradients | pad | 8 scalar slots]: segments start at multiples of four floats (16-byte accesses of
+    the peer-memory exchange), `grads` excludes the scalar slots, padding stays zero, external storage is accepted."""
+    import torch
+    from mpvae_b200.train import GradBucket
+    r = torch.zeros(7, 9, requires_grad=True)                     # 63 floats: an odd segment like eurlex's 3993 x 3993
+    ps = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(2)), torch.nn.Parameter(torch.zeros(1), requires_grad=False)]
+    for alloc in (None, lambda n: torch.full((n,), 7.0)):
+        b = GradBucket(r, ps, alloc)
+        assert b.r_numel == 63 and b.mlp_off == 64 and b.grads_end == 64 + 17 and b.scal_off == 84
+        assert b.flat.numel() == 84 + GradBucket.N_SCALARS and b.grads.numel() == b.grads_end
+        assert b.scalars.data_ptr() == b.flat.data_ptr() + 4 * b.scal_off
+        assert [v.shape for v in b.views] == [ps[0].shape, ps[1].shape]      # the frozen parameter has no slot
+        b.attach(r)
+        assert float(b.flat.abs().sum()) == 0.0                   # attach = zero_grad: also clears external storage
+        assert r.grad.data_ptr() == b.flat.data_ptr() and ps[0].grad.data_ptr() == b.flat.data_ptr() + 4 * 64
+        (r.sum() * 2 + ps[0].sum() * 3 + ps[1].sum() * 5).backward()
+        assert float(b.flat[:63].sum()) == 126.0 and float(b.flat[63]) == 0.0
+        assert float(b.flat[64:81].sum()) == 45.0 + 10.0 and float(b.flat[81:].abs().sum()) == 0.0
+        r.grad = None
+        for q in ps:
+            q.grad = None
+    # no trainable R: the MLP segment starts at 0
+    b = GradBucket(None, ps[:2])
+    assert b.r_numel == 0 and b.mlp_off == 0 and b.r_view is None
+
+
+def test_peer_all_is_a_cuda_feature():
+    """peer_all needs CUDA IPC: on CPU tensors the stepper keeps the torch.distributed path (and a single process has
+    nothing to exchange); GraphedTrainStep says what it needs under N ranks."""
+    args = make_args()
+    model, step, _ = build(args)
+    from mpvae_b200.train import DataParallelStep
+    st = DataParallelStep(model, step.optimizer, None, args, clip_norm=100.0, loss_fn=step.loss_fn, peer_all=True, peer_g_r=True)
+    assert st.pbucket is None and st.ring is None
