@@ -477,7 +477,7 @@ def run_b200(a):
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     total_ms, total_e2e = max_over_ranks(total_ms, total_e2e)
-    if a.profile_host and rank == 0:
+    if a.profile_host and world == 1:      # (one process only: under N ranks a lone rank would wait for the others' exchange)
         import cProfile
         import io
         import pstats
